@@ -1,0 +1,227 @@
+/*
+ * yelprec_b200.h — C ABI of the B200-native BPR-MF / NGCF train + full-catalog eval hot path.
+ *
+ * One shared library (libyelprec_b200.so), extern "C", plain pointers and sizes only.
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _h;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; nothing is allocated inside the library: callers own all buffers;
+ *   - return value: 0 = ok, 1..999 = cudaError_t of the launch, >=1000 = yr_status (bad argument);
+ *   - embedding tables are fp32 row-major [rows x d]; ids are int64 exactly as the reference's
+ *     default-collated batches (data/datasets/mf_dataset.py:26-31);
+ *   - "reference" citations are relative to twndus/YelpRecommendation.
+ *
+ * The reference has no FFI of its own (pure Python/PyTorch); each entry point below names the
+ * reference interface whose body it replaces. INTEGRATION.md shows the ctypes stub a maintainer adds.
+ */
+#ifndef YELPREC_B200_H
+#define YELPREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* yr_stream; /* cudaStream_t */
+
+enum yr_status {
+  YR_OK = 0,
+  YR_ERR_BAD_ARG = 1000,      /* null pointer / non-positive size */
+  YR_ERR_BAD_DIM = 1001,      /* embedding width not supported by the kernels */
+  YR_ERR_BAD_OPT = 1002,      /* unknown optimizer kind (reference: NotImplementedError, base_trainer.py:41-43) */
+  YR_ERR_WORKSPACE = 1003,    /* workspace too small */
+  YR_ERR_COOP = 1004          /* device cannot co-schedule the cooperative grid */
+};
+
+enum yr_opt_kind { YR_OPT_SGD = 0, YR_OPT_ADAM = 1, YR_OPT_ADAMW = 2 };
+
+/* Optimizer hyper-parameters with torch.optim defaults semantics (trainers/base_trainer.py:34-40).
+ * `step` is the 1-based index of the FIRST optimizer step the call performs (Adam bias correction). */
+typedef struct yr_opt {
+  int32_t kind;
+  int32_t step;
+  double lr, weight_decay, beta1, beta2, eps;
+} yr_opt;
+
+/* Library / device info. */
+int yr_version(void);
+int yr_device_sm_count(int* sm_count_h);
+
+/* ------------------------------------------------------------------------------------------------
+ * BPR-MF  (models/mf.py, loss.py, trainers/mf_trainer.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* MatrixFactorization.forward (models/mf.py:20-23): out[b] = sum_k U[uid[b],k] * V[iid[b],k],
+ * accumulated as one fp32 fma chain k = 0..d-1 (the canonical order the oracle uses).
+ * Out-of-range ids set *err (sticky, non-zero) instead of reading out of bounds. */
+int yr_mf_score(const float* U, const float* V, int64_t nU, int64_t nI, int d,
+                const int64_t* uid, const int64_t* iid, int64_t B, float* out, int32_t* err,
+                yr_stream stream);
+
+/* Backward of yr_mf_score for autograd users (an unmodified reference trainer calling
+ * loss.backward(), trainers/mf_trainer.py:111): gU[uid[b]] += gout[b]*V[iid[b]], gV[iid[b]] += gout[b]*U[uid[b]].
+ * gU/gV are dense [rows x d] and are accumulated into (caller zeroes them). */
+int yr_mf_score_bwd(const float* U, const float* V, int64_t nU, int64_t nI, int d,
+                    const int64_t* uid, const int64_t* iid, int64_t B, const float* gout,
+                    float* gU, float* gV, yr_stream stream);
+
+/* BPRLoss.forward (loss.py:25-27): *loss = mean_b( -logsigmoid(pos[b]-neg[b]) ). */
+int yr_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* loss, yr_stream stream);
+/* d loss / d pos, d loss / d neg scaled by *gloss (device scalar). */
+int yr_bpr_loss_bwd(const float* pos, const float* neg, int64_t B, const float* gloss,
+                    float* gpos, float* gneg, yr_stream stream);
+
+/* State of the fused trainer: parameters, optimizer moments and the sparse-accumulate scratch.
+ * gU/gV/flagU/flagV must be all-zero on first use; every call leaves them all-zero again. */
+typedef struct yr_mf_state {
+  float *U, *V;             /* [nU x d], [nI x d] */
+  float *mU, *vU, *mV, *vV; /* Adam exp_avg / exp_avg_sq, same shapes (unused for SGD, may be NULL) */
+  float *gU, *gV;           /* gradient scratch rows (only touched rows ever become non-zero) */
+  int32_t *flagU, *flagV;   /* [nU], [nI] touched flags */
+  int32_t *rows;            /* [3*B] unique touched rows of the current step */
+  int32_t *counters;        /* 64-byte block, 8-byte aligned, zero on first use: 8 x int32 counters + 2 x double loss accumulators */
+  int32_t *err;             /* [1] sticky bad-id flag (reference: IndexError from nn.Embedding) */
+  int64_t nU, nI;
+  int32_t d;
+} yr_mf_state;
+
+/* MFTrainer.train hot loop (trainers/mf_trainer.py:100-116) for `n_triples` pre-collated triples cut
+ * into consecutive batches of B (last one short, as DataLoader keeps it, train.py:76): per batch
+ * forward x2, BPR loss, gradient with duplicate rows summed, ONE optimizer update per row
+ * (SGD / Adam / AdamW with torch dense semantics), all inside one persistent cooperative kernel.
+ * loss_sum (double, device) += sum over batches of the batch-mean loss (quirk Q1);
+ * step_loss (float, device, may be NULL) receives every batch mean. */
+int yr_bpr_mf_train(const yr_mf_state* st, const yr_opt* opt,
+                    const int64_t* uid, const int64_t* pos, const int64_t* neg,
+                    int64_t n_triples, int32_t B, double* loss_sum, float* step_loss,
+                    yr_stream stream);
+
+/* MFTrainer.validate (trainers/mf_trainer.py:118-132): same batching, forward + loss only. */
+int yr_bpr_mf_validate(const float* U, const float* V, int64_t nU, int64_t nI, int d,
+                       const int64_t* uid, const int64_t* pos, const int64_t* neg,
+                       int64_t n_triples, int32_t B, double* loss_sum, float* step_loss,
+                       int32_t* err, yr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NGCF  (models/ngcf.py, trainers/ngcf_trainer.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Y = A X (accumulate == 0) or Y += A X (accumulate != 0) for a CSR matrix with int32 indices and
+ * fp32 values, X/Y row-major [n_rows x d]; row sums run in CSR order as one fma chain.
+ * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */
+int yr_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int d,
+                const float* X, float* Y, int accumulate, yr_stream stream);
+
+/* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
+ *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
+ * W1, W2 are nn.Linear weights [d x d] (out x in). LE_save [n x d] receives L E (kept for backward). */
+int yr_ngcf_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n, int d,
+                      const float* E, const float* W1, const float* W2, float slope,
+                      float* E_next, float* LE_save, yr_stream stream);
+
+/* Backward of one layer. G_next = dLoss/dE_next. (rowptrT,colT,valT) is the CSR of L^T.
+ *   dZ = G_next * leaky'(E_next); dS = dZ W1; dP = dZ W2;
+ *   G += dS + dP*LE + L^T (dS + dP*E);   dW1 += dZ^T (LE+E);  dW2 += dZ^T (E*LE)
+ * T [n x d] is scratch for the transposed SpMM operand; ws holds per-CTA dW partials
+ * (yr_ngcf_layer_bwd_ws_bytes). dW1/dW2 are OVERWRITTEN with this layer's weight gradient. */
+size_t yr_ngcf_layer_bwd_ws_bytes(int d);
+int yr_ngcf_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int64_t n, int d,
+                      const float* E, const float* LE, const float* E_next, const float* G_next,
+                      const float* W1, const float* W2, float slope,
+                      float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
+                      yr_stream stream);
+
+/* Tail of NGCF.bpr_forward + BPRLoss (models/ngcf.py:37-45, loss.py:25-27) and its backward:
+ * rows u / nU+pos / nU+neg are gathered from every layer output E_l (l = 0..n_layers), the concatenated
+ * dots give pos/neg scores, the batch-mean loss is added to
+ * *loss_sum and written to *step_loss, and, if G_layers != NULL, the row gradients are scatter-added
+ * into G_l. E_layers / G_layers are DEVICE arrays of n_layers+1 device pointers. */
+/* loss_sum is a device double[2]: [0] += batch mean, [1] is a zeroed scratch accumulator. */
+int yr_ngcf_tail(const float* const* E_layers, float* const* G_layers, int n_layers, int64_t nU,
+                 int64_t nI, int d, const int64_t* uid, const int64_t* pos, const int64_t* neg,
+                 int64_t B, float* pos_out, float* neg_out, double* loss_sum, float* step_loss,
+                 int32_t* err, yr_stream stream);
+
+/* One dense torch.optim step over a flat parameter (Adam / AdamW / SGD, single-tensor op order of
+ * torch.optim, trainers/base_trainer.py:34-40). m, v may be NULL for SGD. */
+int yr_dense_opt_step(float* p, const float* g, float* m, float* v, int64_t n, const yr_opt* opt,
+                      yr_stream stream);
+
+/* Whole NGCFTrainer.train step (trainers/ngcf_trainer.py:106-115) as one host call: n_layers x layer_fwd,
+ * tail (+loss), n_layers x layer_bwd, dense optimizer step over embedding.weight and every W1/W2.
+ * All buffers are caller-owned; E[0] is the embedding parameter, E[1..n_layers] the layer outputs. */
+#define YR_NGCF_MAX_LAYERS 7
+typedef struct yr_ngcf_state {
+  int64_t nU, nI;
+  int32_t d, n_layers;
+  const int32_t *rowptr, *col;   const float* val;    /* CSR of L   */
+  const int32_t *rowptrT, *colT; const float* valT;   /* CSR of L^T */
+  float* E[YR_NGCF_MAX_LAYERS + 1];   /* [n x d] each, n = nU + nI */
+  float* LE[YR_NGCF_MAX_LAYERS];      /* saved L E_l */
+  float* G[YR_NGCF_MAX_LAYERS + 1];   /* dLoss/dE_l */
+  float* T;                           /* [n x d] scratch */
+  float *W1[YR_NGCF_MAX_LAYERS], *W2[YR_NGCF_MAX_LAYERS];      /* [d x d] nn.Linear weights */
+  float *dW1[YR_NGCF_MAX_LAYERS], *dW2[YR_NGCF_MAX_LAYERS];
+  float *mE, *vE;                                              /* Adam moments (NULL for SGD) */
+  float *mW1[YR_NGCF_MAX_LAYERS], *vW1[YR_NGCF_MAX_LAYERS], *mW2[YR_NGCF_MAX_LAYERS], *vW2[YR_NGCF_MAX_LAYERS];
+  const float* const* E_dev;          /* device copy of E[0..n_layers] */
+  float* const* G_dev;                /* device copy of G[0..n_layers] */
+  void* ws; size_t ws_bytes;          /* >= yr_ngcf_layer_bwd_ws_bytes(d) */
+  double* loss;                       /* device double[2]: [0] running sum of batch means, [1] scratch (zero) */
+  int32_t* err;
+} yr_ngcf_state;
+
+/* forward only: fills E[1..n_layers] (and LE[]) — used by validate / evaluate (propagate ONCE, not per user) */
+int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream stream);
+int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                       const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                       float* step_loss, yr_stream stream);
+/* out[r, l*d + k] = E_l[r, k]: the concatenation torch.concat(..., dim=1) of models/ngcf.py:41-43. */
+int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-catalog evaluation (trainers/mf_trainer.py:134-178, metric.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Vt[k, i] = V[i, k] for i < nI; Vt is [d x ldt], ldt >= nI (padding columns are zero-filled). */
+int yr_transpose_items(const float* V, int64_t nI, int d, float* Vt, int64_t ldt, yr_stream stream);
+
+size_t yr_eval_ws_bytes(int64_t n_eval, int d, int K);
+
+/* MFTrainer.evaluate / NGCFTrainer.evaluate fused: for eval row e (user eval_uid[e]) score every item
+ * (one fp32 fma chain over k = 0..d-1), overwrite mask_items with -3.40282e+38 (Q4), keep the K best by
+ * (score desc, item id asc), then accumulate the reference's metrics (metric.py:7-109, quirks Q6-Q8).
+ *   Uemb [nU x d] row-major; Vt [d x ldt] item table transposed (yr_transpose_items);
+ *   mask_ptr/mask_idx: CSR over eval rows, item ids ascending per row;
+ *   act_ptr/act_idx:  CSR over eval rows, pos_items in their ORIGINAL order; act_nuniq[e] = |set(pos_items)|;
+ *   inv_log2 [K] (double) = 1/log2(i+2), host-computed so DCG matches Python's math.log2;
+ *   topk_out [n_eval x K] int64 best first; user_metrics [n_eval x 4] double =
+ *   (hits/K, hits/|set(A)| or 0, AP, NDCG) per row; metric_sums [6] double =
+ *   (sum precision, sum recall, sum AP, sum NDCG, #rows with |set(A)|>0, #rows with len(A)>0).
+ * The score matrix is never written to memory. */
+int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* Vt, int64_t ldt, int64_t nI, int d,
+                         const int64_t* eval_uid, int64_t n_eval,
+                         const int32_t* mask_ptr, const int32_t* mask_idx,
+                         const int32_t* act_ptr, const int32_t* act_idx, const int32_t* act_nuniq,
+                         const double* inv_log2, int K,
+                         int64_t* topk_out, float* topk_score, double* user_metrics, double* metric_sums,
+                         void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+
+/* MFTrainer._generate_top_k_recommendation (trainers/mf_trainer.py:163-178) for ONE score row:
+ * mask_idx (int64, any order, n_mask entries) positions get -3.40282e+38, then the K best by
+ * (score desc, item id asc) are written best-first. `pred` is not modified. */
+int yr_topk_masked_row(const float* pred, int64_t nI, const int64_t* mask_idx, int64_t n_mask, int K,
+                       int64_t* topk_out, yr_stream stream);
+
+/* metric.py:7-109 on device for already-computed recommendations: predicted [n x ldp] int64 (first K columns
+ * used), actual as CSR in original order. Same outputs as yr_eval_topk_metrics. */
+int yr_topk_metrics(const int64_t* predicted, int64_t ldp, int64_t n, const int32_t* act_ptr,
+                    const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2, int K,
+                    double* user_metrics, double* metric_sums, yr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YELPREC_B200_H */

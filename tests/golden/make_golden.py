@@ -1,0 +1,258 @@
+"""Generates tests/golden/*.npz|json by running the UNMODIFIED reference (twndus/YelpRecommendation, mounted at
+/root/reference) on small seeded inputs. Run here (the build container); the fixtures are committed because the
+GPU box has no /root/reference.
+
+    python tests/golden/make_golden.py
+
+What is imported from the reference (nothing is copied): metric.py, models/mf.py, models/ngcf.py, loss.py,
+trainers/mf_trainer.py, trainers/ngcf_trainer.py, data/datasets/mf_data_pipeline.py, ngcf_data_pipeline.py.
+Shims: `omegaconf` (type annotation only, trainers/base_trainer.py:10) and, for the Laplacian only, a
+`Tensor.to('cuda')` no-op because ngcf_data_pipeline.py:38-39 hard-codes the device.
+"""
+import json
+import os
+import sys
+import tempfile
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import pandas as pd
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("YR_REFERENCE_DIR", "/root/reference")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+oc, dc = types.ModuleType("omegaconf"), types.ModuleType("omegaconf.dictconfig")
+
+
+class DictConfig(dict):
+    pass
+
+
+dc.DictConfig = oc.DictConfig = DictConfig
+oc.dictconfig = dc
+sys.modules["omegaconf"], sys.modules["omegaconf.dictconfig"] = oc, dc
+
+import metric as ref_metric                                   # noqa: E402
+from trainers.mf_trainer import MFTrainer as RefMFTrainer     # noqa: E402
+from trainers.ngcf_trainer import NGCFTrainer as RefNGCFTrainer  # noqa: E402
+from data.datasets.mf_data_pipeline import MFDataPipeline     # noqa: E402
+from data.datasets.ngcf_data_pipeline import NGCFDataPipeline  # noqa: E402
+
+from yelprecommendation_b200.data import synthetic as syn     # noqa: E402
+
+from loguru import logger                                     # noqa: E402
+logger.remove()
+
+TMP = tempfile.mkdtemp()
+
+
+def cfg(**kw):
+    base = dict(device="cpu", model_dir=TMP, embed_size=64, optimizer="sgd", lr=1e-2, weight_decay=0.0, top_n=10,
+                wandb=False, num_orders=3, epochs=1, patience=1, best_metric="loss", loss_name="bpr", seed=42,
+                batch_size=256)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def frame(inter):
+    return pd.DataFrame({"user_id": inter.user, "business_id": inter.item, "rating": inter.rating})
+
+
+# ------------------------------------------------------------------------------------------------
+def golden_metrics():
+    rng = np.random.default_rng(11)
+    cases = []
+
+    def add(actual, predicted, k):
+        cases.append(dict(actual=[list(map(int, a)) for a in actual], predicted=[list(map(int, p)) for p in predicted],
+                          k=k, precision=ref_metric.precision_at_k(actual, predicted, k),
+                          recall=ref_metric.recall_at_k(actual, predicted, k),
+                          map=ref_metric.map_at_k(actual, predicted, k), ndcg=ref_metric.ndcg_at_k(actual, predicted, k)))
+
+    # the reference's own test vectors (test/test_metric.py:9-47)
+    for k in range(1, 6):
+        add([[1, 2, 3, 4, 5], [6, 7, 8, 9, 10]], [[1, 6, 7, 11, 12], [6, 7, 14, 16, 20]], k)
+    # order dependence of AP (Q7), NDCG window (Q8), empty users (Q6)
+    for A in ([1, 5, 9], [9, 5, 1], [5, 9, 1]):
+        add([A], [[5, 9, 1, 7, 8, 11, 12, 13, 14, 15]], 10)
+    add([[1, 2]], [[7, 8, 1, 2, 3, 4, 5, 6, 9, 10]], 10)
+    add([[1, 2]], [[1, 8, 7, 2, 3, 4, 5, 6, 9, 10]], 10)
+    add([[1], []], [[1, 2], [3, 4]], 2)
+    # random: shuffled actual, len(actual) < k, duplicates in actual, empty rows
+    for t in range(40):
+        n = int(rng.integers(1, 7))
+        k = int(rng.integers(1, 13))
+        actual, predicted = [], []
+        for _ in range(n):
+            la = int(rng.integers(0, 15))
+            a = rng.integers(0, 30, size=la).tolist() if t % 3 == 0 else rng.permutation(30)[:la].tolist()
+            actual.append(a)
+            predicted.append(rng.permutation(30)[:max(k, 12)].tolist())
+        if all(len(set(a)) == 0 for a in actual):
+            actual[0] = [3]
+        add(actual, predicted, k)
+    with open(os.path.join(HERE, "metric_cases.json"), "w") as f:
+        json.dump(cases, f)
+    print("metric cases:", len(cases))
+
+
+# ------------------------------------------------------------------------------------------------
+def golden_split_and_mf():
+    inter = syn.make_interactions(num_users=160, num_items=240, nnz=3200, seed=5, n_clusters=4)
+    df = frame(inter)
+    pipe = MFDataPipeline(cfg())
+    pipe.num_users, pipe.num_items = inter.num_users, inter.num_items
+    train_data, valid_data, valid_eval, test_eval = pipe.split(df)
+    out = dict(user=inter.user, item=inter.item, rating=inter.rating, num_users=inter.num_users,
+               num_items=inter.num_items)
+
+    def pack(prefix, ev):
+        out[f"{prefix}_uid"] = ev.index.to_numpy().astype(np.int64)
+        for col in ("pos_items", "mask_items"):
+            lens = np.array([len(x) for x in ev[col]], dtype=np.int64)
+            out[f"{prefix}_{col}_ptr"] = np.concatenate([[0], np.cumsum(lens)])
+            out[f"{prefix}_{col}"] = np.concatenate([np.asarray(x, dtype=np.int64) for x in ev[col]])
+
+    pack("valid_eval", valid_eval)
+    pack("test_eval", test_eval)
+    out["train_user"] = train_data["user_id"].to_numpy().astype(np.int64)
+    out["train_item"] = train_data["business_id"].to_numpy().astype(np.int64)
+    out["valid_user"] = valid_data["user_id"].to_numpy().astype(np.int64)
+    out["valid_item"] = valid_data["business_id"].to_numpy().astype(np.int64)
+
+    # pre-sampled triples (ours — the reference samples inside Dataset.__getitem__ from the global RNG)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tp, tn = syn.sample_triples(split, inter.num_items, seed=42)
+    vu, vp, vn = syn.sample_triples(split, inter.num_items, seed=43, which="valid", reject="train+valid")
+    out.update(tri_u=tu, tri_p=tp, tri_n=tn, vtri_u=vu, vtri_p=vp, vtri_n=vn)
+    B = 256
+    batches = syn.to_batches(tu, tp, tn, B)[:6]
+    vbatches = syn.to_batches(vu, vp, vn, B)
+
+    configs = [("sgd", 1e-2, 0.0), ("sgd", 1e-2, 1e-2), ("adam", 1e-2, 0.0), ("adam", 1e-3, 1e-3), ("adamw", 1e-2, 1e-2)]
+    for ci, (name, lr, wd) in enumerate(configs):
+        torch.manual_seed(42)
+        tr = RefMFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd), inter.num_items, inter.num_users)
+        if ci == 0:
+            out["mf_U0"] = tr.model.user_embedding.weight.detach().numpy().copy()
+            out["mf_V0"] = tr.model.item_embedding.weight.detach().numpy().copy()
+            out["mf_valid0"] = tr.validate(vbatches)
+            u = torch.from_numpy(tu[:300])
+            out["mf_score0"] = tr.model(u, torch.from_numpy(tp[:300])).detach().numpy()
+        # per-step losses need a second pass structure: call train() batch by batch
+        losses = [tr.train([b]) for b in batches]
+        out[f"mf_{ci}_cfg"] = np.array([lr, wd])
+        out[f"mf_{ci}_name"] = name
+        out[f"mf_{ci}_losses"] = np.array(losses)
+        out[f"mf_{ci}_U"] = tr.model.user_embedding.weight.detach().numpy().copy()
+        out[f"mf_{ci}_V"] = tr.model.item_embedding.weight.detach().numpy().copy()
+        if ci == 2:
+            out["mf_valid_after"] = tr.validate(vbatches)
+    out["n_mf_cfg"] = len(configs)
+
+    # evaluation: planted ("trained-ish") tables so that top-10 gaps and metrics are realistic
+    Up, Vp = syn.planted_embeddings(inter, d=64, seed=7)
+    tr = RefMFTrainer(cfg(), inter.num_items, inter.num_users)
+    with torch.no_grad():
+        tr.model.user_embedding.weight.copy_(torch.from_numpy(Up))
+        tr.model.item_embedding.weight.copy_(torch.from_numpy(Vp))
+    out["eval_U"], out["eval_V"] = Up, Vp
+    for prefix, ev in (("valid_eval", valid_eval), ("test_eval", test_eval)):
+        out[f"{prefix}_metrics"] = np.array(tr.evaluate(ev, "valid"))
+        preds = []
+        items = torch.arange(inter.num_items)
+        for uid, row in ev.iterrows():
+            pred = tr.model(torch.tensor([uid] * inter.num_items), items)
+            preds.append(tr._generate_top_k_recommendation(pred, row["mask_items"]))
+        out[f"{prefix}_topk"] = np.stack(preds).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "mf_small.npz"), **out)
+    print("mf_small: valid users", len(valid_eval), "metrics", out["valid_eval_metrics"])
+    return inter, split
+
+
+# ------------------------------------------------------------------------------------------------
+def golden_ngcf():
+    out = {}
+    for tag, stars in (("bin", False), ("star", True)):
+        inter = syn.make_interactions(num_users=96, num_items=128, nnz=1500, seed=9, n_clusters=4, star_ratings=stars)
+        df = frame(inter)
+        pipe = NGCFDataPipeline(cfg())
+        pipe.num_users, pipe.num_items = inter.num_users, inter.num_items
+        orig_to = torch.Tensor.to
+
+        def to_shim(self, *a, **k):   # ngcf_data_pipeline.py:38-39 hard-codes 'cuda'
+            if a and a[0] == "cuda":
+                return self
+            return orig_to(self, *a, **k)
+
+        torch.Tensor.to = to_shim
+        try:
+            pipe._set_laplacian_matrix(df)
+        finally:
+            torch.Tensor.to = orig_to
+        L = pipe.laplacian_matrix.coalesce()
+        out[f"{tag}_user"], out[f"{tag}_item"], out[f"{tag}_rating"] = inter.user, inter.item, inter.rating
+        out[f"{tag}_L_idx"] = L.indices().numpy()
+        out[f"{tag}_L_val"] = L.values().numpy()
+        out[f"{tag}_nU"], out[f"{tag}_nI"] = inter.num_users, inter.num_items
+        if tag == "star":
+            continue
+        split = syn.split_per_user(inter, seed=42)
+        tu, tp, tn = syn.sample_triples(split, inter.num_items, seed=42)
+        out.update(tri_u=tu, tri_p=tp, tri_n=tn)
+        B = 128
+        batches = syn.to_batches(tu, tp, tn, B)[:3]
+        for ci, (name, lr, wd) in enumerate([("sgd", 1e-2, 0.0), ("adam", 1e-3, 0.0), ("adamw", 1e-3, 1e-2)]):
+            torch.manual_seed(42)
+            tr = RefNGCFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd, num_orders=3), inter.num_items,
+                                inter.num_users, L)
+            if ci == 0:
+                sd = {k: v.detach().numpy().copy() for k, v in tr.model.state_dict().items()}
+                for k, v in sd.items():
+                    out["ngcf_init_" + k] = v
+                with torch.no_grad():
+                    e = tr.model.embedding.weight
+                    for l, (w1, w2) in enumerate(zip(tr.model.W1, tr.model.W2)):
+                        e = tr.model.embedding_propagation(e, w1, w2, L)   # verbatim, torch.eye and all
+                        out[f"ngcf_layer{l + 1}"] = e.numpy().copy()
+                    b0 = batches[0]
+                    p, n = tr.model.bpr_forward(b0["user_id"], b0["pos_item"], b0["neg_item"], L)
+                    out["ngcf_pos0"], out["ngcf_neg0"] = p.numpy().copy(), n.numpy().copy()
+                    out["ngcf_valid0"] = tr.validate(batches)
+                    # per-user forward exactly as trainers/ngcf_trainer.py:144 does it
+                    items = torch.arange(inter.num_items)
+                    users = [0, 5, 17, 40]
+                    out["ngcf_eval_users"] = np.array(users)
+                    out["ngcf_eval_scores"] = np.stack([
+                        tr.model(torch.tensor([u] * inter.num_items), items, L).numpy() for u in users])
+                # gradients of the first step (autograd), for the backward kernels
+                b0 = batches[0]
+                p, n = tr.model.bpr_forward(b0["user_id"], b0["pos_item"], b0["neg_item"], L)
+                loss = tr.loss(p, n)
+                tr.optimizer.zero_grad()
+                loss.backward()
+                for k, prm in tr.model.named_parameters():
+                    out["ngcf_grad_" + k] = prm.grad.detach().numpy().copy()
+                tr.optimizer.zero_grad()
+            losses = [tr.train([b]) for b in batches]
+            out[f"ngcf_{ci}_name"] = name
+            out[f"ngcf_{ci}_cfg"] = np.array([lr, wd])
+            out[f"ngcf_{ci}_losses"] = np.array(losses)
+            for k, v in tr.model.state_dict().items():
+                out[f"ngcf_{ci}_final_" + k] = v.detach().numpy().copy()
+        out["n_ngcf_cfg"] = 3
+    np.savez_compressed(os.path.join(HERE, "ngcf_small.npz"), **out)
+    print("ngcf_small: losses", out["ngcf_0_losses"])
+
+
+if __name__ == "__main__":
+    golden_metrics()
+    golden_split_and_mf()
+    golden_ngcf()
+    print("fixtures written to", HERE)
+    os.system(f"ls -la {HERE}")

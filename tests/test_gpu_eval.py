@@ -1,0 +1,161 @@
+"""GPU parity: fused full-catalog evaluation (score + mask + top-K + metrics) vs the oracle and the reference."""
+from math import isclose
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from util import RTOL, cfg, lists_from, load_npz, metric_cases, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(U, V, csr, K=10):
+    from yelprecommendation_b200 import ops
+    dev = torch.device("cuda")
+    ecsr = ops.DeviceEvalCSR(csr, dev, K)
+    topk, tsc, um, sums, err = ops.eval_topk_metrics(torch.from_numpy(U).to(dev), torch.from_numpy(V).to(dev), ecsr)
+    assert int(err.item()) == 0
+    return topk.cpu().numpy(), tsc.cpu().numpy(), um.cpu().numpy(), sums.cpu().numpy()
+
+
+def check_vs_oracle(U, V, csr, K=10):
+    topk, tsc, um, sums = run_gpu(U, V, csr, K)
+    otopk, otsc, oum, osums = cport.eval_topk_metrics(U, V, csr.eval_uid, csr.mask_ptr, csr.mask_idx, csr.act_ptr,
+                                                      csr.act_idx, K)
+    assert np.array_equal(topk, otopk), "top-K ids must be bit-exact under (score desc, id asc)"
+    assert np.array_equal(tsc, otsc), "scores are one fma chain on both sides"
+    assert np.array_equal(um, oum), "per-row metric terms use the same double arithmetic"
+    assert np.allclose(sums, osums, rtol=1e-12, atol=0)
+    return topk, sums
+
+
+@pytest.mark.parametrize("prefix", ["valid_eval", "test_eval"])
+def test_eval_golden_small(prefix):
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    from yelprecommendation_b200 import ops
+    g = load_npz("mf_small.npz")
+    U, V = g["eval_U"], g["eval_V"]
+    uid = g[f"{prefix}_uid"]
+    csr = build_eval_csr(uid, lists_from(g, prefix, "pos_items"), lists_from(g, prefix, "mask_items"), int(g["num_items"]))
+    topk, sums = check_vs_oracle(U, V, csr)
+    ref = g[f"{prefix}_topk"]
+    diff = [r for r in range(len(uid)) if not np.array_equal(topk[r], ref[r])]
+    for r in diff:   # only fp32-noise ties against the reference's NumPy order (Q5)
+        sa, sb = (cport.mf_score(U, V, np.full(10, uid[r]), x[r]) for x in (topk, ref))
+        assert np.abs(sa - sb).max() <= 4e-6 * np.abs(sb).max()
+    assert len(diff) <= max(1, len(uid) // 50)
+    if not diff:
+        assert np.allclose(ops.metrics_from_sums(sums, csr.n_eval), g[f"{prefix}_metrics"], rtol=1e-12, atol=0)
+
+
+def _random_problem(rng, nU, nI, d, n_eval, heavy=False, ties=False):
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    U = rng.standard_normal((nU, d)).astype(np.float32)
+    V = rng.standard_normal((nI, d)).astype(np.float32)
+    if ties:
+        V[nI // 2:] = V[: nI - nI // 2]                      # exact score ties between item i and i + nI/2
+        V[5] = 0
+    uid = rng.integers(0, nU, n_eval)
+    pos, mask = [], []
+    for e in range(n_eval):
+        la = int(rng.integers(0, 25)) if e % 7 else 0       # some rows have no positives (Q6)
+        pos.append(rng.permutation(nI)[:la].tolist())
+        lm = int(rng.integers(0, 60))
+        if heavy and e % 5 == 0:
+            lm = int(nI * 0.9)                               # > kMCap masked pairs per tile -> CSR fallback
+        m = rng.permutation(nI)[:lm].tolist()
+        if e % 11 == 0 and lm:
+            m = m + m[:3]                                    # duplicates in mask_items
+        mask.append(m)
+    return U, V, build_eval_csr(uid, pos, mask, nI)
+
+
+@pytest.mark.parametrize("nU,nI,d,n_eval,K", [(64, 100, 64, 1, 10), (300, 1000, 64, 129, 10), (500, 3001, 64, 400, 20),
+                                               (200, 777, 256, 130, 10), (128, 640, 32, 128, 1), (90, 512, 128, 77, 32),
+                                               (50, 33, 20, 40, 10)])
+def test_eval_random_vs_oracle(nU, nI, d, n_eval, K):
+    rng = np.random.default_rng(nI + d)
+    U, V, csr = _random_problem(rng, nU, nI, d, n_eval)
+    check_vs_oracle(U, V, csr, K)
+
+
+def test_eval_heavy_masks_and_ties():
+    rng = np.random.default_rng(5)
+    U, V, csr = _random_problem(rng, 100, 2000, 64, 150, heavy=True, ties=True)
+    topk, _ = check_vs_oracle(U, V, csr, 10)
+    # masked items never appear unless fewer than K unmasked items exist
+    for e in range(csr.n_eval):
+        m = set(csr.mask_idx[csr.mask_ptr[e]:csr.mask_ptr[e + 1]].tolist())
+        if 2000 - len(m) >= 10:
+            assert not (set(topk[e].tolist()) & m)
+
+
+def test_eval_more_masked_than_catalog_minus_k():
+    """Fewer than K unmasked items: masked ones (-3.40282e+38) fill the tail, id ascending."""
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    rng = np.random.default_rng(9)
+    U, V = rng.standard_normal((4, 64)).astype(np.float32), rng.standard_normal((40, 64)).astype(np.float32)
+    csr = build_eval_csr([0, 1], [[1, 2], [3]], [list(range(35)), list(range(40))], 40)
+    check_vs_oracle(U, V, csr, 10)
+
+
+def test_trainer_evaluate_dataframe_interface():
+    """MFTrainer.evaluate(eval_data DataFrame) + _generate_top_k_recommendation, as train.py calls them."""
+    import pandas as pd
+    from yelprecommendation_b200.trainers import MFTrainer
+    g = load_npz("mf_small.npz")
+    tr = MFTrainer(cfg(), int(g["num_items"]), int(g["num_users"]))
+    with torch.no_grad():
+        tr.model.user_embedding.weight.copy_(torch.from_numpy(g["eval_U"]))
+        tr.model.item_embedding.weight.copy_(torch.from_numpy(g["eval_V"]))
+    uid = g["valid_eval_uid"]
+    ev = pd.DataFrame({"pos_items": lists_from(g, "valid_eval", "pos_items"),
+                       "mask_items": lists_from(g, "valid_eval", "mask_items")}, index=pd.Index(uid, name="user_id"))
+    got = tr.evaluate(ev, "valid")
+    assert np.allclose(got, g["valid_eval_metrics"], rtol=2e-2)
+    ref = g["valid_eval_topk"]
+    same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ref[r]) for r in range(len(uid)))
+    assert same >= len(uid) - max(1, len(uid) // 50)
+    # single-row helper
+    items = torch.arange(int(g["num_items"]))
+    for r in (0, 3, 11):
+        pred = tr.model(torch.full_like(items, int(uid[r])), items)
+        top = tr._generate_top_k_recommendation(pred, ev.iloc[r]["mask_items"])
+        assert np.array_equal(top, tr.last_topk[r].cpu().numpy())
+
+
+def test_metric_module_vs_reference_cases():
+    from yelprecommendation_b200 import metric
+    for c in metric_cases():
+        a, p, k = c["actual"], c["predicted"], c["k"]
+        assert isclose(metric.precision_at_k(a, p, k), c["precision"], rel_tol=1e-12, abs_tol=1e-15)
+        assert isclose(metric.recall_at_k(a, p, k), c["recall"], rel_tol=1e-12, abs_tol=1e-15)
+        assert isclose(metric.map_at_k(a, p, k), c["map"], rel_tol=1e-12, abs_tol=1e-15)
+        assert isclose(metric.ndcg_at_k(a, p, k), c["ndcg"], rel_tol=1e-12, abs_tol=1e-15)
+
+
+def test_full_catalog_yelp_shape_properties():
+    """BASELINE config 3 shape: all 31,668 users x 38,048 items. Size-independent checks + sampled oracle rows."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    inter = syn.make_interactions()
+    assert inter.user.size == 1_561_406 and inter.num_users == 31_668 and inter.num_items == 38_048
+    split = syn.split_per_user(inter, seed=42)
+    uid, pos, mask = syn.eval_lists(split, "valid")
+    csr = build_eval_csr(uid, pos, mask, inter.num_items)
+    U, V = syn.planted_embeddings(inter)
+    topk, tsc, um, sums = run_gpu(U, V, csr, 10)
+    assert topk.shape == (len(uid), 10) and topk.min() >= 0 and topk.max() < inter.num_items
+    assert np.all(np.diff(tsc, axis=1) <= 0)                                  # best first
+    assert np.all(np.sort(topk, axis=1)[:, 1:] != np.sort(topk, axis=1)[:, :-1])   # distinct ids
+    rows = np.random.default_rng(0).choice(len(uid), 96, replace=False)
+    for e in rows:                                                             # never a masked item
+        assert not (set(topk[e].tolist()) & set(mask[e]))
+    sub = build_eval_csr(uid[rows], [pos[e] for e in rows], [mask[e] for e in rows], inter.num_items)
+    otopk, otsc, oum, _ = cport.eval_topk_metrics(U, V, sub.eval_uid, sub.mask_ptr, sub.mask_idx, sub.act_ptr, sub.act_idx, 10)
+    assert np.array_equal(topk[rows], otopk) and np.array_equal(tsc[rows], otsc) and np.array_equal(um[rows], oum)
+    # checksum of checksums: metric sums equal the sum of the per-row terms
+    assert np.allclose(sums[:4], um.sum(axis=0), rtol=1e-12)
+    assert sums[0] / len(uid) > 0.01                                          # planted structure is recoverable

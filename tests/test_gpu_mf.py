@@ -1,0 +1,175 @@
+"""GPU parity: BPR-MF kernels (through the Python mirror -> C ABI) vs the oracle and the reference goldens."""
+from math import isclose
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from util import RTOL, batches_from, cfg, load_npz, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(g, name, lr, wd, **kw):
+    from yelprecommendation_b200.trainers import MFTrainer
+    tr = MFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd, **kw), int(g["num_items"]), int(g["num_users"]))
+    with torch.no_grad():
+        tr.model.user_embedding.weight.copy_(torch.from_numpy(g["mf_U0"]))
+        tr.model.item_embedding.weight.copy_(torch.from_numpy(g["mf_V0"]))
+    return tr
+
+
+def test_native_library_is_loaded():
+    from yelprecommendation_b200 import _cabi
+    lib = _cabi.load()
+    import ctypes
+    n = ctypes.c_int(0)
+    assert lib.yr_device_sm_count(ctypes.byref(n)) == 0 and n.value > 0
+    assert any("libyelprec_b200.so" in l for l in open("/proc/self/maps"))
+
+
+def test_mf_score_bit_exact_vs_oracle_and_golden():
+    from yelprecommendation_b200 import ops
+    g = load_npz("mf_small.npz")
+    U, V = torch.from_numpy(g["mf_U0"]).cuda(), torch.from_numpy(g["mf_V0"]).cuda()
+    u, p = g["tri_u"], g["tri_p"]
+    s = ops.mf_score(U, V, torch.from_numpy(u), torch.from_numpy(p)).cpu().numpy()
+    assert np.array_equal(s, cport.mf_score(g["mf_U0"], g["mf_V0"], u, p))          # canonical fma chain
+    assert rel_err(s[:300], g["mf_score0"]) < RTOL
+    for d in (8, 20, 64, 100, 256):                                                   # generic widths
+        rng = np.random.default_rng(d)
+        A, B = rng.standard_normal((50, d)).astype(np.float32), rng.standard_normal((70, d)).astype(np.float32)
+        a, b = rng.integers(0, 50, 333), rng.integers(0, 70, 333)
+        s = ops.mf_score(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(a), torch.from_numpy(b))
+        assert np.array_equal(s.cpu().numpy(), cport.mf_score(A, B, a, b))
+
+
+def test_mf_score_rejects_bad_ids_like_embedding():
+    from yelprecommendation_b200 import ops
+    U, V = torch.randn(10, 64).cuda(), torch.randn(12, 64).cuda()
+    with pytest.raises(IndexError):
+        ops.mf_score(U, V, torch.tensor([0, 10]), torch.tensor([0, 1]))
+    with pytest.raises(IndexError):
+        ops.mf_score(U, V, torch.tensor([0, 1]), torch.tensor([-1, 1]))
+
+
+def test_bpr_loss_fwd_bwd():
+    from yelprecommendation_b200.loss import BPRLoss
+    rng = np.random.default_rng(0)
+    for B in (1, 7, 2048, 5000):
+        pos = torch.from_numpy(rng.standard_normal(B).astype(np.float32) * 4)
+        neg = torch.from_numpy(rng.standard_normal(B).astype(np.float32) * 4)
+        pc, nc = pos.clone().requires_grad_(), neg.clone().requires_grad_()
+        ref = torch.mean(-torch.nn.functional.logsigmoid(pc - nc))
+        ref.backward()
+        pg, ng = pos.cuda().requires_grad_(), neg.cuda().requires_grad_()
+        out = BPRLoss()(pg, ng)
+        (out * 3.0).backward()
+        assert isclose(out.item(), ref.item(), rel_tol=RTOL)
+        assert isclose(out.item(), cport.bpr_loss(pos.numpy(), neg.numpy()), rel_tol=1e-6)
+        assert rel_err(pg.grad.cpu().numpy(), 3.0 * pc.grad.numpy()) < RTOL
+        assert rel_err(ng.grad.cpu().numpy(), 3.0 * nc.grad.numpy()) < RTOL
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4])
+def test_fused_training_vs_reference_golden(ci):
+    g = load_npz("mf_small.npz")
+    name, (lr, wd) = str(g[f"mf_{ci}_name"]), g[f"mf_{ci}_cfg"]
+    tr = _trainer(g, name, float(lr), float(wd))
+    batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 256, limit=6)
+    total = tr.train(batches)
+    steps = tr.last_step_losses.cpu().numpy()
+    assert rel_err(steps, g[f"mf_{ci}_losses"]) < RTOL
+    assert isclose(total, float(np.sum(g[f"mf_{ci}_losses"])), rel_tol=RTOL)           # Q1: sum of batch means
+    assert rel_err(tr.model.user_embedding.weight.detach().cpu().numpy(), g[f"mf_{ci}_U"]) < RTOL
+    assert rel_err(tr.model.item_embedding.weight.detach().cpu().numpy(), g[f"mf_{ci}_V"]) < RTOL
+    sc = tr._scratch                                                                      # all-zero invariant
+    for k in ("gU", "gV", "flagU", "flagV"):
+        assert int(torch.count_nonzero(sc[k]).item()) == 0, k
+    # one launch per batch (steps_per_launch=1) must give the same result as one launch for all
+    tr2 = _trainer(g, name, float(lr), float(wd), steps_per_launch=1)
+    total2 = tr2.train(batches)
+    assert isclose(total2, total, rel_tol=1e-6)
+    assert rel_err(tr2.model.user_embedding.weight.detach().cpu().numpy(), g[f"mf_{ci}_U"]) < RTOL
+
+
+def test_validate_and_short_last_batch():
+    g = load_npz("mf_small.npz")
+    tr = _trainer(g, "adam", 1e-2, 0.0)
+    vb = batches_from(g["vtri_u"], g["vtri_p"], g["vtri_n"], 256)
+    assert vb[-1]["user_id"].numel() < 256                                               # DataLoader keeps it
+    assert isclose(tr.validate(vb), float(g["mf_valid0"]), rel_tol=RTOL)
+    tr.train(batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 256, limit=6))
+    assert isclose(tr.validate(vb), float(g["mf_valid_after"]), rel_tol=RTOL)
+    # a training pass that ends with a short batch, checked against the C oracle
+    tr = _trainer(g, "sgd", 1e-2, 0.0)
+    n = 256 * 3 + 77
+    b = batches_from(g["tri_u"][:n], g["tri_p"][:n], g["tri_n"][:n], 256)
+    total = tr.train(b)
+    orc = cport.MFTrainerOracle(g["mf_U0"], g["mf_V0"], "sgd", 1e-2, 0.0)
+    ototal, _ = orc.train([{k: v.numpy() for k, v in x.items()} for x in b])
+    assert isclose(total, ototal, rel_tol=RTOL)
+    assert rel_err(tr.model.item_embedding.weight.detach().cpu().numpy(), orc.V) < RTOL
+
+
+def test_train_bad_id_raises_index_error():
+    g = load_npz("mf_small.npz")
+    tr = _trainer(g, "sgd", 1e-2, 0.0)
+    b = batches_from(g["tri_u"][:256].copy(), g["tri_p"][:256].copy(), g["tri_n"][:256].copy(), 256)
+    b[0]["pos_item"][3] = int(g["num_items"])
+    with pytest.raises(IndexError):
+        tr.train(b)
+
+
+def test_reference_style_autograd_loop_on_dropin_modules():
+    """An unmodified reference trainer body (mf_trainer.py:104-114) on the drop-in model + loss + torch.optim."""
+    from yelprecommendation_b200.loss import BPRLoss
+    from yelprecommendation_b200.models.mf import MatrixFactorization
+    g = load_npz("mf_small.npz")
+    model = MatrixFactorization(cfg(), int(g["num_users"]), int(g["num_items"])).cuda()
+    assert sorted(model.state_dict().keys()) == ["item_embedding.weight", "user_embedding.weight"]
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(torch.from_numpy(g["mf_U0"]))
+        model.item_embedding.weight.copy_(torch.from_numpy(g["mf_V0"]))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=0.0)
+    loss_fn, losses = BPRLoss(), []
+    for data in batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 256, limit=6):
+        u, p, n = data["user_id"].cuda(), data["pos_item"].cuda(), data["neg_item"].cuda()
+        pos_pred, neg_pred = model(u, p), model(u, n)
+        opt.zero_grad()
+        loss = loss_fn(pos_pred, neg_pred)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert rel_err(losses, g["mf_2_losses"]) < RTOL
+    assert rel_err(model.user_embedding.weight.detach().cpu().numpy(), g["mf_2_U"]) < 2e-5
+
+
+@pytest.mark.parametrize("name,wd", [("sgd", 0.0), ("adam", 0.0)])
+def test_full_size_yelp_shape_vs_oracle(name, wd):
+    """BASELINE config 1 shape (31,668 x 38,048, d=64, B=2048): 12 fused steps vs the C oracle."""
+    from types import SimpleNamespace
+    from yelprecommendation_b200.trainers import MFTrainer
+    rng = np.random.default_rng(1)
+    nU, nI, B, steps = 31_668, 38_048, 2048, 12
+    tr = MFTrainer(cfg(optimizer=name, lr=1e-2, weight_decay=wd, batch_size=B), nI, nU)
+    U0 = tr.model.user_embedding.weight.detach().cpu().numpy().copy()
+    V0 = tr.model.item_embedding.weight.detach().cpu().numpy().copy()
+    u = rng.integers(0, nU, B * steps)
+    u[:64] = 7                                                    # heavy duplicate rows inside one batch
+    p, n = rng.integers(0, nI, B * steps), rng.integers(0, nI, B * steps)
+    b = batches_from(u, p, n, B)
+    total = tr.train(b)
+    orc = cport.MFTrainerOracle(U0, V0, name, 1e-2, wd)
+    ototal, osteps = orc.train([{k: v.numpy() for k, v in x.items()} for x in b])
+    assert isclose(total, ototal, rel_tol=RTOL)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), osteps) < RTOL
+    assert rel_err(tr.model.user_embedding.weight.detach().cpu().numpy(), orc.U) < RTOL
+    assert rel_err(tr.model.item_embedding.weight.detach().cpu().numpy(), orc.V) < RTOL
+    # linearity property of the SGD step: untouched rows are bit-identical to the initial table
+    if name == "sgd":
+        touched = np.zeros(nU, bool)
+        touched[u] = True
+        Ug = tr.model.user_embedding.weight.detach().cpu().numpy()
+        assert np.array_equal(Ug[~touched], U0[~touched])

@@ -1,0 +1,193 @@
+"""GPU parity: NGCF propagation / backward / train step vs the oracle and the reference goldens."""
+from math import isclose
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport, torch_port as tp
+from util import RTOL, batches_from, cfg, load_npz, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden():
+    from yelprecommendation_b200.data.graph import coo_to_csr
+    g = load_npz("ngcf_small.npz")
+    nU, nI = int(g["bin_nU"]), int(g["bin_nI"])
+    idx, val = g["bin_L_idx"], g["bin_L_val"]
+    L = torch.sparse_coo_tensor(torch.from_numpy(idx), torch.from_numpy(val), size=(nU + nI, nU + nI)).coalesce()
+    csr = coo_to_csr(idx[0], idx[1], val, nU + nI)
+    csrT = coo_to_csr(idx[1], idx[0], val, nU + nI)
+    W1 = [g[f"ngcf_init_W1.{l}.weight"] for l in range(3)]
+    W2 = [g[f"ngcf_init_W2.{l}.weight"] for l in range(3)]
+    return g, nU, nI, L, csr, csrT, g["ngcf_init_embedding.weight"], W1, W2
+
+
+def _trainer(g, nU, nI, L, name="sgd", lr=1e-2, wd=0.0):
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    tr = NGCFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd, num_orders=3), nI, nU, L)
+    sd = {k[len("ngcf_init_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("ngcf_init_")}
+    tr.model.load_state_dict(sd)          # identical state_dict keys to the reference model
+    return tr
+
+
+def test_spmm_bit_exact_vs_oracle():
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian, laplacian_to_csr
+    inter = syn.make_interactions(num_users=700, num_items=900, nnz=20000, seed=4, n_clusters=4, star_ratings=True)
+    L = build_laplacian(inter.user, inter.item, inter.rating, 700, 900)
+    csr = laplacian_to_csr(L, "cuda")
+    rng = np.random.default_rng(0)
+    for d in (32, 64, 128, 256):
+        X = rng.standard_normal((1600, d)).astype(np.float32)
+        Y0 = rng.standard_normal((1600, d)).astype(np.float32)
+        c = (csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(), csr.val.cpu().numpy())
+        y = ops.spmm_csr(csr.rowptr, csr.col, csr.val, torch.from_numpy(X).cuda())
+        assert np.array_equal(y.cpu().numpy(), cport.spmm_csr(*c, X))
+        ya = torch.from_numpy(Y0).cuda()
+        ops.spmm_csr(csr.rowptr_t, csr.col_t, csr.val_t, torch.from_numpy(X).cuda(), out=ya, accumulate=True)
+        ct = (csr.rowptr_t.cpu().numpy(), csr.col_t.cpu().numpy(), csr.val_t.cpu().numpy())
+        assert np.array_equal(ya.cpu().numpy(), cport.spmm_csr(*ct, X, Y0))
+
+
+def test_layer_forward_bit_exact_vs_oracle_and_golden():
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data.graph import laplacian_to_csr
+    g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
+    dcsr = laplacian_to_csr(L, "cuda")
+    E = torch.from_numpy(E0).cuda()
+    Ec = E0
+    for l in range(3):
+        En, LE = ops.ngcf_layer_fwd(dcsr, E, torch.from_numpy(W1[l]).cuda(), torch.from_numpy(W2[l]).cuda())
+        Eo, LEo = cport.ngcf_layer_fwd(csr, Ec, W1[l], W2[l])
+        assert np.array_equal(LE.cpu().numpy(), LEo)
+        assert np.array_equal(En.cpu().numpy(), Eo)                      # same fma chain order -> bit-exact
+        assert rel_err(En.cpu().numpy(), g[f"ngcf_layer{l + 1}"]) < RTOL   # vs the reference (torch.eye and all)
+        E, Ec = En, Eo
+
+
+def test_layer_backward_vs_oracle_and_autograd_golden():
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data.graph import laplacian_to_csr
+    g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
+    dcsr = laplacian_to_csr(L, "cuda")
+    layers, LEs = [E0], []
+    for l in range(3):
+        E, LE = cport.ngcf_layer_fwd(csr, layers[-1], W1[l], W2[l])
+        layers.append(E)
+        LEs.append(LE)
+    u, p, n = g["tri_u"][:128], g["tri_p"][:128], g["tri_n"][:128]
+    _, _, _, G = cport.ngcf_tail(layers, nU, u, p, n, want_grad=True)
+    Gd = [torch.from_numpy(x).cuda() for x in G]
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for l in (2, 1, 0):
+        G[l], dW1o, dW2o = cport.ngcf_layer_bwd(csrT, layers[l], LEs[l], layers[l + 1], G[l + 1], W1[l], W2[l], G[l])
+        dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(layers[l]), cu(LEs[l]), cu(layers[l + 1]), Gd[l + 1], cu(W1[l]), cu(W2[l]), Gd[l])
+        assert rel_err(Gd[l].cpu().numpy(), G[l]) < RTOL
+        assert rel_err(dW1.cpu().numpy(), dW1o) < RTOL and rel_err(dW2.cpu().numpy(), dW2o) < RTOL
+        assert rel_err(dW1.cpu().numpy(), g[f"ngcf_grad_W1.{l}.weight"]) < 2e-5
+        assert rel_err(dW2.cpu().numpy(), g[f"ngcf_grad_W2.{l}.weight"]) < 2e-5
+    assert rel_err(Gd[0].cpu().numpy(), g["ngcf_grad_embedding.weight"]) < 2e-5
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_train_steps_vs_reference_golden(ci):
+    g, nU, nI, L, *_ = _golden()
+    name, (lr, wd) = str(g[f"ngcf_{ci}_name"]), g[f"ngcf_{ci}_cfg"]
+    tr = _trainer(g, nU, nI, L, name, float(lr), float(wd))
+    batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 128, limit=3)
+    if ci == 0:
+        assert isclose(tr.validate(batches), float(g["ngcf_valid0"]), rel_tol=RTOL)
+    total = tr.train(batches)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), g[f"ngcf_{ci}_losses"]) < RTOL
+    assert isclose(total, float(np.sum(g[f"ngcf_{ci}_losses"])), rel_tol=RTOL)
+    sd = tr.model.state_dict()
+    assert rel_err(sd["embedding.weight"].cpu().numpy(), g[f"ngcf_{ci}_final_embedding.weight"]) < RTOL
+    for l in range(3):
+        assert rel_err(sd[f"W1.{l}.weight"].cpu().numpy(), g[f"ngcf_{ci}_final_W1.{l}.weight"]) < 5e-5
+        assert rel_err(sd[f"W2.{l}.weight"].cpu().numpy(), g[f"ngcf_{ci}_final_W2.{l}.weight"]) < 5e-5
+
+
+def test_dropin_model_signatures_and_autograd():
+    """NGCF.forward / bpr_forward / embedding_propagation with the reference's signatures + loss.backward()."""
+    from yelprecommendation_b200.loss import BPRLoss
+    g, nU, nI, L, *_ = _golden()
+    tr = _trainer(g, nU, nI, L)
+    m = tr.model
+    assert sorted(m.state_dict().keys()) == sorted(["embedding.weight"] + [f"W{j}.{l}.weight" for j in (1, 2) for l in range(3)])
+    Ld = L.cuda()
+    u, p, n = (torch.from_numpy(g[k][:128]) for k in ("tri_u", "tri_p", "tri_n"))
+    pos, neg = m.bpr_forward(u, p, n, Ld)
+    assert rel_err(pos.detach().cpu().numpy(), g["ngcf_pos0"]) < RTOL
+    assert rel_err(neg.detach().cpu().numpy(), g["ngcf_neg0"]) < RTOL
+    BPRLoss()(pos, neg).backward()
+    for k, prm in m.named_parameters():
+        assert rel_err(prm.grad.cpu().numpy(), g["ngcf_grad_" + k]) < 2e-5, k
+    items = torch.arange(nI)
+    for j, usr in enumerate(g["ngcf_eval_users"]):
+        s = m(torch.full_like(items, int(usr)), items, Ld)
+        assert rel_err(s.detach().cpu().numpy(), g["ngcf_eval_scores"][j]) < RTOL
+    e1 = m.embedding_propagation(m.embedding.weight, m.W1[0], m.W2[0], Ld)
+    assert rel_err(e1.detach().cpu().numpy(), g["ngcf_layer1"]) < RTOL
+
+
+def test_evaluate_vs_port_and_sample100_mode():
+    import pandas as pd
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
+    inter = syn.Interactions(nU, nI, g["bin_user"], g["bin_item"], g["bin_rating"], None, None)
+    split = syn.split_per_user(inter, seed=42)
+    uid, pos, mask = syn.eval_lists(split, "valid")
+    tr = _trainer(g, nU, nI, L)
+    got = tr.evaluate(build_eval_csr(uid, pos, mask, nI))
+    port = tp.NGCFPort(torch.from_numpy(E0), [torch.from_numpy(w) for w in W1], [torch.from_numpy(w) for w in W2], nU, L)
+    want, ppred = port.evaluate(uid, mask, pos)
+    same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ppred[r]) for r in range(len(uid)))
+    assert same >= len(uid) - max(1, len(uid) // 25)
+    assert np.allclose(got, want, rtol=5e-2)
+    # C oracle on the concatenated embeddings: bit-exact ids
+    layers = [E0]
+    for l in range(3):
+        layers.append(cport.ngcf_layer_fwd(csr, layers[-1], W1[l], W2[l])[0])
+    cat = np.concatenate(layers, axis=1)
+    ec = build_eval_csr(uid, pos, mask, nI)
+    otopk, _, _, osums = cport.eval_topk_metrics(cat[:nU], cat[nU:], ec.eval_uid, ec.mask_ptr, ec.mask_idx, ec.act_ptr, ec.act_idx, 10)
+    assert np.array_equal(tr.last_topk.cpu().numpy(), otopk)
+    assert np.allclose(got, cport.metrics_from_sums(osums, ec.n_eval), rtol=1e-12)
+    # Q12 compat: 100 rows drawn from the global NumPy RNG, with replacement
+    ev = pd.DataFrame({"pos_items": pos, "mask_items": mask}, index=pd.Index(uid, name="user_id"))
+    tr.cfg.ngcf_eval_mode = "sample100"
+    np.random.seed(3)
+    r1 = tr.evaluate(ev)
+    np.random.seed(3)
+    rows = np.random.randint(ev.shape[0], size=100)
+    assert tr.last_topk.shape[0] == 100
+    sub = build_eval_csr(uid[rows], [pos[r] for r in rows], [mask[r] for r in rows], nI)
+    _, _, _, s2 = cport.eval_topk_metrics(cat[:nU], cat[nU:], sub.eval_uid, sub.mask_ptr, sub.mask_idx, sub.act_ptr, sub.act_idx, 10)
+    assert np.allclose(r1, cport.metrics_from_sums(s2, 100), rtol=1e-12)
+
+
+def test_medium_graph_train_step_vs_port():
+    """A 6k-node degree-skewed graph, one Adam step: CUDA vs the torch-CPU port (identity hoisted)."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    inter = syn.make_interactions(num_users=2500, num_items=3500, nnz=90_000, seed=8, n_clusters=8)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tpos, tneg = syn.sample_triples(split, inter.num_items, seed=42)
+    batches = syn.to_batches(tu, tpos, tneg, 2048)[:2]
+    torch.manual_seed(5)
+    tr = NGCFTrainer(cfg(optimizer="adam", lr=1e-3, num_orders=3, batch_size=2048), inter.num_items, inter.num_users, L)
+    sd = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    port = tp.NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(3)],
+                       [sd[f"W2.{l}.weight"] for l in range(3)], inter.num_users, L, "adam", 1e-3, 0.0)
+    total = tr.train(batches)
+    ptotal, psteps = port.train(batches)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), psteps) < RTOL
+    assert rel_err(tr.model.embedding.weight.detach().cpu().numpy(), port.emb.detach().numpy()) < 2e-5
+    for l in range(3):
+        assert rel_err(tr.model.W1[l].weight.detach().cpu().numpy(), port.W1[l].detach().numpy()) < 1e-4

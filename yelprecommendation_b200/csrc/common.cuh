@@ -1,0 +1,157 @@
+// Shared device helpers for the sm_100a kernels. No torch headers anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include "../../include/yelprec_b200.h"
+
+namespace cg = cooperative_groups;
+
+#define YR_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return (int)e__;                \
+  } while (0)
+
+#define YR_CUDA(call)                                       \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return (int)e__;                \
+  } while (0)
+
+namespace yr {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// Per-lane slice of an embedding row: VPL = d/32 contiguous floats starting at lane*VPL.
+template <int VPL> struct Row { float x[VPL]; };
+
+template <int VPL>
+__device__ __forceinline__ Row<VPL> ld_row(const float* __restrict__ row, int lane) {
+  Row<VPL> r;
+  if constexpr (VPL == 1) {
+    r.x[0] = row[lane];
+  } else if constexpr (VPL == 2) {
+    float2 t = reinterpret_cast<const float2*>(row)[lane];
+    r.x[0] = t.x; r.x[1] = t.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL / 4; ++j) {
+      float4 t = reinterpret_cast<const float4*>(row)[lane * (VPL / 4) + j];
+      r.x[4 * j + 0] = t.x; r.x[4 * j + 1] = t.y; r.x[4 * j + 2] = t.z; r.x[4 * j + 3] = t.w;
+    }
+  }
+  return r;
+}
+
+template <int VPL>
+__device__ __forceinline__ void st_row(float* __restrict__ row, int lane, const Row<VPL>& r) {
+  if constexpr (VPL == 1) {
+    row[lane] = r.x[0];
+  } else if constexpr (VPL == 2) {
+    reinterpret_cast<float2*>(row)[lane] = make_float2(r.x[0], r.x[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL / 4; ++j)
+      reinterpret_cast<float4*>(row)[lane * (VPL / 4) + j] =
+          make_float4(r.x[4 * j + 0], r.x[4 * j + 1], r.x[4 * j + 2], r.x[4 * j + 3]);
+  }
+}
+
+// Vector reduction into global memory (sm_90+ has native float2/float4 atomics: RED.E.ADD.F32x2/x4).
+template <int VPL>
+__device__ __forceinline__ void red_row(float* __restrict__ row, int lane, const Row<VPL>& r) {
+  if constexpr (VPL == 1) {
+    atomicAdd(row + lane, r.x[0]);
+  } else if constexpr (VPL == 2) {
+    atomicAdd(reinterpret_cast<float2*>(row) + lane, make_float2(r.x[0], r.x[1]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL / 4; ++j)
+      atomicAdd(reinterpret_cast<float4*>(row) + lane * (VPL / 4) + j,
+                make_float4(r.x[4 * j + 0], r.x[4 * j + 1], r.x[4 * j + 2], r.x[4 * j + 3]));
+  }
+}
+
+template <int VPL>
+__device__ __forceinline__ float dot_partial(const Row<VPL>& a, const Row<VPL>& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) s = fmaf(a.x[j], b.x[j], s);
+  return s;
+}
+
+// -logsigmoid(x) with torch's formulation: logsigmoid(x) = min(x,0) - log1p(exp(-|x|))
+// (aten/src/ATen/native/cpu/Activation.cpp log_sigmoid_cpu_kernel); loss.py:25-27.
+__device__ __forceinline__ float neg_logsigmoid(float x) {
+  return log1pf(expf(-fabsf(x))) - fminf(x, 0.f);
+}
+// d(-logsigmoid(x))/dx = -sigmoid(-x), in torch's backward formulation.
+__device__ __forceinline__ float neg_logsigmoid_grad(float x) {
+  const float z = expf(-fabsf(x));
+  const float s = (x < 0.f) ? 1.f - z / (1.f + z) : z / (1.f + z);   // sigmoid(-x)
+  return -s;
+}
+
+// torch.optim single-tensor update of one element (torch/optim/{sgd,adam,adamw}.py op order).
+struct OptScalars {
+  int kind;
+  float lr, wd;            // SGD: lr, coupled wd; AdamW: lr*wd decoupled
+  float w_lerp;            // (float)(1 - beta1)
+  float beta2, omb2;       // (float)beta2, (float)(1 - beta2)
+  float eps;
+  float step_size;         // (float)(lr / (1 - beta1^t))
+  float bc2_sqrt;          // (float)sqrt(1 - beta2^t)
+  float decay;             // AdamW: (float)(1 - lr*wd)
+};
+
+__device__ __forceinline__ void opt_scalars_for_step(OptScalars& s, const yr_opt& o, int t) {
+  s.kind = o.kind;
+  s.lr = (float)o.lr;
+  s.wd = (float)o.weight_decay;
+  s.w_lerp = (float)(1.0 - o.beta1);
+  s.beta2 = (float)o.beta2;
+  s.omb2 = (float)(1.0 - o.beta2);
+  s.eps = (float)o.eps;
+  const double bc1 = 1.0 - pow(o.beta1, (double)t);
+  const double bc2 = 1.0 - pow(o.beta2, (double)t);
+  s.step_size = (float)(o.lr / bc1);
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.decay = (float)(1.0 - o.lr * o.weight_decay);
+}
+
+__device__ __forceinline__ void opt_update(const OptScalars& s, float& p, float g, float& m, float& v) {
+  if (s.kind == YR_OPT_SGD) {
+    if (s.wd != 0.f) g = fmaf(p, s.wd, g);            // grad.add(param, alpha=wd)
+    p = fmaf(g, -s.lr, p);                            // param.add_(grad, alpha=-lr)
+    return;
+  }
+  if (s.kind == YR_OPT_ADAMW) {
+    p = p * s.decay;                                  // param.mul_(1 - lr*wd)
+  } else if (s.wd != 0.f) {
+    g = fmaf(p, s.wd, g);                             // grad.add(param, alpha=wd)
+  }
+  m = fmaf(s.w_lerp, g - m, m);                       // exp_avg.lerp_(grad, 1-beta1)
+  v = v * s.beta2;                                    // exp_avg_sq.mul_(beta2)
+  v = v + (s.omb2 * g) * g;                           //   .addcmul_(grad, grad, value=1-beta2)
+  const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;  // (sqrt(v)/sqrt(bc2)).add_(eps)
+  p = p + (-s.step_size * m) / denom;                 // param.addcdiv_(m, denom, value=-step_size)
+}
+
+inline int dim_vpl(int d) {
+  switch (d) { case 32: return 1; case 64: return 2; case 128: return 4; case 256: return 8; default: return 0; }
+}
+
+}  // namespace yr

@@ -1,0 +1,626 @@
+// NGCF propagation kernels (sm_100a).
+//   yr_spmm_csr          — torch.sparse.mm(L, E) (reference models/ngcf.py:64,67)
+//   yr_ngcf_layer_fwd    — NGCF.embedding_propagation (reference models/ngcf.py:60-72)
+//   yr_ngcf_layer_bwd    — its gradient (autograd through the two SpMMs / two Linear layers)
+//   yr_ngcf_tail         — gather/concat/dot tail of bpr_forward + BPRLoss and its scatter backward
+//                          (reference models/ngcf.py:37-45, loss.py:25-27)
+//   yr_dense_opt_step    — torch.optim Adam/AdamW/SGD single-tensor step (trainers/base_trainer.py:34-40)
+#include "common.cuh"
+
+namespace yr {
+
+// ---------------------------------------------------------------------------------------------
+// CSR SpMM, warp per row, lanes across the embedding width, fma chain in CSR order.
+// ---------------------------------------------------------------------------------------------
+template <int VPL, bool ACC>
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const float* __restrict__ val, int64_t n_rows, const float* __restrict__ X,
+                float* __restrict__ Y) {
+  constexpr int D = VPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += nwarps) {
+    const int s = rowptr[row], e = rowptr[row + 1];
+    Row<VPL> acc;
+    if constexpr (ACC) {
+      acc = ld_row<VPL>(Y + row * D, lane);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) acc.x[j] = 0.f;
+    }
+    for (int j0 = s; j0 < e; j0 += 32) {
+      const int j = j0 + lane;
+      const int c = (j < e) ? __ldg(col + j) : 0;
+      const float a = (j < e) ? __ldg(val + j) : 0.f;
+      const int cnt = min(32, e - j0);
+      int t = 0;
+      for (; t + 4 <= cnt; t += 4) {
+        const int c0 = __shfl_sync(kFull, c, t), c1 = __shfl_sync(kFull, c, t + 1);
+        const int c2 = __shfl_sync(kFull, c, t + 2), c3 = __shfl_sync(kFull, c, t + 3);
+        const float a0 = __shfl_sync(kFull, a, t), a1 = __shfl_sync(kFull, a, t + 1);
+        const float a2 = __shfl_sync(kFull, a, t + 2), a3 = __shfl_sync(kFull, a, t + 3);
+        const Row<VPL> x0 = ld_row<VPL>(X + (int64_t)c0 * D, lane);
+        const Row<VPL> x1 = ld_row<VPL>(X + (int64_t)c1 * D, lane);
+        const Row<VPL> x2 = ld_row<VPL>(X + (int64_t)c2 * D, lane);
+        const Row<VPL> x3 = ld_row<VPL>(X + (int64_t)c3 * D, lane);
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          acc.x[q] = fmaf(a0, x0.x[q], acc.x[q]);
+          acc.x[q] = fmaf(a1, x1.x[q], acc.x[q]);
+          acc.x[q] = fmaf(a2, x2.x[q], acc.x[q]);
+          acc.x[q] = fmaf(a3, x3.x[q], acc.x[q]);
+        }
+      }
+      for (; t < cnt; ++t) {
+        const int c0 = __shfl_sync(kFull, c, t);
+        const float a0 = __shfl_sync(kFull, a, t);
+        const Row<VPL> x0 = ld_row<VPL>(X + (int64_t)c0 * D, lane);
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) acc.x[q] = fmaf(a0, x0.x[q], acc.x[q]);
+      }
+    }
+    st_row<VPL>(Y + row * D, lane, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense part of one layer, forward: out = leaky( [LE+E | E*LE] . [W1^T ; W2^T] ).
+// 256 threads, tile = TM rows x D cols, thread = 4 rows x 4 cols, k runs 0..2D-1 as one fma chain
+// (first the W1 term, then the W2 term — the order the oracle restates).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct DenseCfg {
+  static constexpr int kThreads = 256;
+  static constexpr int kColGroups = D / 4;
+  static constexpr int kRowGroups = kThreads / kColGroups;
+  static constexpr int TM = 4 * kRowGroups;                       // 64 for D=64
+  static constexpr size_t kSmemFwd = (size_t)(2 * D * TM + 2 * D * D) * sizeof(float);
+  static constexpr size_t kSmemBwd = (size_t)(3 * TM * D + 2 * D * D) * sizeof(float);
+};
+
+template <int D>
+__global__ void __launch_bounds__(256)
+ngcf_dense_fwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
+                      const float* __restrict__ W1, const float* __restrict__ W2, float slope,
+                      int64_t n, float* __restrict__ Eout) {
+  using C = DenseCfg<D>;
+  constexpr int TM = C::TM;
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                 // [2D][TM]   k-major: S then P
+  float* Ws = smem + 2 * D * TM;    // [2D][D]    Ws[k][o] = Wcat[o][k]
+  const int tid = threadIdx.x;
+  const int tx = tid % C::kColGroups, ty = tid / C::kColGroups;
+
+  for (int idx = tid; idx < D * D; idx += C::kThreads) {
+    const int o = idx / D, k = idx % D;
+    Ws[k * D + o] = W1[idx];
+    Ws[(D + k) * D + o] = W2[idx];
+  }
+  const int64_t n_tiles = (n + TM - 1) / TM;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TM;
+    __syncthreads();   // previous tile's readers are done with As (and Ws is written on the first pass)
+    for (int idx = tid; idx < TM * (D / 4); idx += C::kThreads) {
+      const int r = idx % TM, c4 = idx / TM;
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f), le = e;
+      if (r0 + r < n) {
+        e = __ldg(reinterpret_cast<const float4*>(E + (r0 + r) * D) + c4);
+        le = __ldg(reinterpret_cast<const float4*>(LE + (r0 + r) * D) + c4);
+      }
+      const int k = c4 * 4;
+      As[(k + 0) * TM + r] = le.x + e.x; As[(k + 1) * TM + r] = le.y + e.y;
+      As[(k + 2) * TM + r] = le.z + e.z; As[(k + 3) * TM + r] = le.w + e.w;
+      As[(D + k + 0) * TM + r] = e.x * le.x; As[(D + k + 1) * TM + r] = e.y * le.y;
+      As[(D + k + 2) * TM + r] = e.z * le.z; As[(D + k + 3) * TM + r] = e.w * le.w;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 2 * D; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(As + k * TM + ty * 4);
+      const float4 w = *reinterpret_cast<const float4*>(Ws + k * D + tx * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty * 4 + i;
+      if (r < n) {
+        float4 o;
+        o.x = acc[i][0] > 0.f ? acc[i][0] : acc[i][0] * slope;
+        o.y = acc[i][1] > 0.f ? acc[i][1] : acc[i][1] * slope;
+        o.z = acc[i][2] > 0.f ? acc[i][2] : acc[i][2] * slope;
+        o.w = acc[i][3] > 0.f ? acc[i][3] : acc[i][3] * slope;
+        reinterpret_cast<float4*>(Eout + r * D)[tx] = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense part of one layer, backward. Per tile of TM rows:
+//   dZ = G_next * (E_next > 0 ? 1 : slope)
+//   dS = dZ W1, dP = dZ W2          -> T = dS + dP*E (SpMM operand), G += dS + dP*LE
+//   dW1 += dZ^T (LE+E), dW2 += dZ^T (E*LE)   (register accumulators across the CTA's tiles,
+//                                             per-CTA partials to ws, fixed-order reduce afterwards)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
+                      const float* __restrict__ Enext, const float* __restrict__ Gnext,
+                      const float* __restrict__ W1, const float* __restrict__ W2, float slope,
+                      int64_t n, float* __restrict__ G, float* __restrict__ T,
+                      float* __restrict__ ws) {
+  using C = DenseCfg<D>;
+  constexpr int TM = C::TM;
+  static_assert(C::kColGroups * C::kColGroups == C::kThreads, "dW tiling assumes D == 64");
+  extern __shared__ __align__(16) float smem[];
+  float* dZs = smem;                    // [TM][D]
+  float* Es = dZs + TM * D;             // [TM][D]
+  float* LEs = Es + TM * D;             // [TM][D]
+  float* W1s = LEs + TM * D;            // [D][D]  (o, i) as stored
+  float* W2s = W1s + D * D;
+  const int tid = threadIdx.x;
+  const int tx = tid % C::kColGroups, ty = tid / C::kColGroups;
+
+  for (int idx = tid; idx < D * D / 4; idx += C::kThreads) {
+    reinterpret_cast<float4*>(W1s)[idx] = __ldg(reinterpret_cast<const float4*>(W1) + idx);
+    reinterpret_cast<float4*>(W2s)[idx] = __ldg(reinterpret_cast<const float4*>(W2) + idx);
+  }
+  float dw1[4][4], dw2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dw1[i][j] = 0.f; dw2[i][j] = 0.f; }
+
+  const int64_t n_tiles = (n + TM - 1) / TM;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TM;
+    __syncthreads();
+    for (int idx = tid; idx < TM * (D / 4); idx += C::kThreads) {
+      const int r = idx / (D / 4), c4 = idx % (D / 4);
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f), le = e, dz = e;
+      if (r0 + r < n) {
+        const int64_t off = (r0 + r) * D;
+        e = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
+        le = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
+        const float4 en = __ldg(reinterpret_cast<const float4*>(Enext + off) + c4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(Gnext + off) + c4);
+        dz.x = en.x > 0.f ? g.x : g.x * slope; dz.y = en.y > 0.f ? g.y : g.y * slope;
+        dz.z = en.z > 0.f ? g.z : g.z * slope; dz.w = en.w > 0.f ? g.w : g.w * slope;
+      }
+      reinterpret_cast<float4*>(Es)[idx] = e;
+      reinterpret_cast<float4*>(LEs)[idx] = le;
+      reinterpret_cast<float4*>(dZs)[idx] = dz;
+    }
+    __syncthreads();
+
+    // ---- dS, dP: rows ty*4.., cols tx*4.. ; k = o ----
+    float ds[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ds[i][j] = 0.f; dp[i][j] = 0.f; }
+#pragma unroll 4
+    for (int o = 0; o < D; ++o) {
+      const float4 w1 = *reinterpret_cast<const float4*>(W1s + o * D + tx * 4);
+      const float4 w2 = *reinterpret_cast<const float4*>(W2s + o * D + tx * 4);
+      const float w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+      const float w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = dZs[(ty * 4 + i) * D + o];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ds[i][j] = fmaf(a, w1v[j], ds[i][j]);
+          dp[i][j] = fmaf(a, w2v[j], dp[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = ty * 4 + i;
+      const int64_t r = r0 + rl;
+      if (r < n) {
+        const float4 e = *reinterpret_cast<const float4*>(Es + rl * D + tx * 4);
+        const float4 le = *reinterpret_cast<const float4*>(LEs + rl * D + tx * 4);
+        float4 t, dd;
+        t.x = fmaf(dp[i][0], e.x, ds[i][0]); t.y = fmaf(dp[i][1], e.y, ds[i][1]);
+        t.z = fmaf(dp[i][2], e.z, ds[i][2]); t.w = fmaf(dp[i][3], e.w, ds[i][3]);
+        dd.x = fmaf(dp[i][0], le.x, ds[i][0]); dd.y = fmaf(dp[i][1], le.y, ds[i][1]);
+        dd.z = fmaf(dp[i][2], le.z, ds[i][2]); dd.w = fmaf(dp[i][3], le.w, ds[i][3]);
+        reinterpret_cast<float4*>(T + r * D)[tx] = t;
+        float4* gp = reinterpret_cast<float4*>(G + r * D) + tx;
+        float4 g = *gp;
+        g.x += dd.x; g.y += dd.y; g.z += dd.z; g.w += dd.w;
+        *gp = g;
+      }
+    }
+
+    // ---- dW1[o,i], dW2[o,i]: o = ty*4.., i = tx*4.. ; k = row (rows past n hold dZ = 0) ----
+#pragma unroll 4
+    for (int r = 0; r < TM; ++r) {
+      const float4 dz = *reinterpret_cast<const float4*>(dZs + r * D + ty * 4);
+      const float4 e = *reinterpret_cast<const float4*>(Es + r * D + tx * 4);
+      const float4 le = *reinterpret_cast<const float4*>(LEs + r * D + tx * 4);
+      const float dzv[4] = {dz.x, dz.y, dz.z, dz.w};
+      const float sv[4] = {le.x + e.x, le.y + e.y, le.z + e.z, le.w + e.w};
+      const float pv[4] = {e.x * le.x, e.y * le.y, e.z * le.z, e.w * le.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dw1[i][j] = fmaf(dzv[i], sv[j], dw1[i][j]);
+          dw2[i][j] = fmaf(dzv[i], pv[j], dw2[i][j]);
+        }
+    }
+  }
+  float* my = ws + (size_t)blockIdx.x * 2 * D * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = ty * 4 + i;
+    reinterpret_cast<float4*>(my + o * D)[tx] = make_float4(dw1[i][0], dw1[i][1], dw1[i][2], dw1[i][3]);
+    reinterpret_cast<float4*>(my + D * D + o * D)[tx] = make_float4(dw2[i][0], dw2[i][1], dw2[i][2], dw2[i][3]);
+  }
+}
+
+// dW[idx] = sum over CTA partials in CTA order (deterministic).
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, int n_parts, int len,
+                                       float* __restrict__ out1, float* __restrict__ out2, int half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= len) return;
+  float acc = 0.f;
+  for (int p = 0; p < n_parts; ++p) acc += ws[(size_t)p * len + idx];
+  if (idx < half) out1[idx] = acc; else out2[idx - half] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail: warp per triple, all layers.
+// ---------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ngcf_tail_kernel(const float* const* __restrict__ E_layers, float* const* __restrict__ G_layers,
+                 int n_layers, int64_t nU, int64_t nI, const int64_t* __restrict__ uid,
+                 const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t B,
+                 float* __restrict__ pos_out, float* __restrict__ neg_out, double* loss_acc,
+                 int32_t* err) {
+  constexpr int D = VPL * 32;
+  constexpr int kMaxL = 8;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ double s_part[8];
+  double wl = 0.0;
+  const float inv_b = 1.f / (float)B;
+  for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += nwarps) {
+    const int64_t u = uid[b], p = pos[b], n = neg[b];
+    if (u < 0 || u >= nU || p < 0 || p >= nI || n < 0 || n >= nI) {
+      if (lane == 0 && err) atomicExch(err, 1);
+      continue;
+    }
+    float dp = 0.f, dn = 0.f;
+    for (int l = 0; l <= n_layers && l < kMaxL; ++l) {
+      const float* El = E_layers[l];
+      const Row<VPL> ur = ld_row<VPL>(El + u * D, lane);
+      const Row<VPL> pr = ld_row<VPL>(El + (nU + p) * D, lane);
+      const Row<VPL> nr = ld_row<VPL>(El + (nU + n) * D, lane);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) { dp = fmaf(ur.x[j], pr.x[j], dp); dn = fmaf(ur.x[j], nr.x[j], dn); }
+    }
+    dp = warp_sum(dp);
+    dn = warp_sum(dn);
+    const float x = dp - dn;
+    if (lane == 0) {
+      if (pos_out) pos_out[b] = dp;
+      if (neg_out) neg_out[b] = dn;
+    }
+    wl += (double)neg_logsigmoid(x);
+    if (G_layers) {
+      const float g = neg_logsigmoid_grad(x) * inv_b;
+      for (int l = 0; l <= n_layers && l < kMaxL; ++l) {
+        const float* El = E_layers[l];
+        float* Gl = G_layers[l];
+        const Row<VPL> ur = ld_row<VPL>(El + u * D, lane);
+        const Row<VPL> pr = ld_row<VPL>(El + (nU + p) * D, lane);
+        const Row<VPL> nr = ld_row<VPL>(El + (nU + n) * D, lane);
+        Row<VPL> gu, gp, gn;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          gu.x[j] = g * pr.x[j] - g * nr.x[j];
+          gp.x[j] = g * ur.x[j];
+          gn.x[j] = -gp.x[j];
+        }
+        red_row<VPL>(Gl + u * D, lane, gu);
+        red_row<VPL>(Gl + (nU + p) * D, lane, gp);
+        red_row<VPL>(Gl + (nU + n) * D, lane, gn);
+      }
+    }
+  }
+  if (lane == 0) s_part[wib] = wl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_part[i];
+    if (t != 0.0) atomicAdd(loss_acc, t);
+  }
+}
+
+__global__ void tail_finish_kernel(double* loss_acc, int64_t B, double* loss_sum, float* step_loss) {
+  const float mean = (float)(*loss_acc / (double)B);
+  if (step_loss) *step_loss = mean;
+  if (loss_sum) *loss_sum += (double)mean;
+  *loss_acc = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense optimizer step, float4 vectorised with scalar tail.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dense_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                 float* __restrict__ v, int64_t n, yr_opt opt) {
+  OptScalars os;
+  opt_scalars_for_step(os, opt, opt.step);
+  const bool adam = opt.kind != YR_OPT_SGD;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
+    if (adam) { mv = reinterpret_cast<float4*>(m)[i]; vv = reinterpret_cast<float4*>(v)[i]; }
+    opt_update(os, pv.x, gv.x, mv.x, vv.x);
+    opt_update(os, pv.y, gv.y, mv.y, vv.y);
+    opt_update(os, pv.z, gv.z, mv.z, vv.z);
+    opt_update(os, pv.w, gv.w, mv.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    if (adam) { reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv; }
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float mv = 0.f, vv = 0.f, pv = p[i];
+    if (adam) { mv = m[i]; vv = v[i]; }
+    opt_update(os, pv, g[i], mv, vv);
+    p[i] = pv;
+    if (adam) { m[i] = mv; v[i] = vv; }
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+constexpr int kBwdCtasPerSm = 2;
+
+}  // namespace yr
+
+using namespace yr;
+
+extern "C" int yr_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
+                           int d, const float* X, float* Y, int accumulate, yr_stream stream) {
+  if (!rowptr || !col || !val || !X || !Y || n_rows < 0) return YR_ERR_BAD_ARG;
+  if (n_rows == 0) return YR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 256;
+  int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  const unsigned g = (unsigned)blocks;
+#define YR_SPMM(V)                                                                              \
+  if (accumulate) spmm_csr_kernel<V, true><<<g, threads, 0, s>>>(rowptr, col, val, n_rows, X, Y); \
+  else spmm_csr_kernel<V, false><<<g, threads, 0, s>>>(rowptr, col, val, n_rows, X, Y);
+  switch (dim_vpl(d)) {
+    case 1: YR_SPMM(1); break;
+    case 2: YR_SPMM(2); break;
+    case 4: YR_SPMM(4); break;
+    case 8: YR_SPMM(8); break;
+    default: return YR_ERR_BAD_DIM;
+  }
+#undef YR_SPMM
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n,
+                                 int d, const float* E, const float* W1, const float* W2, float slope,
+                                 float* E_next, float* LE_save, yr_stream stream) {
+  if (!rowptr || !col || !val || !E || !W1 || !W2 || !E_next || !LE_save || n <= 0) return YR_ERR_BAD_ARG;
+  if (d != 64) return YR_ERR_BAD_DIM;
+  int rc = yr_spmm_csr(rowptr, col, val, n, d, E, LE_save, 0, stream);
+  if (rc) return rc;
+  using C = DenseCfg<64>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)C::kSmemFwd));
+    attr_set = true;
+  }
+  const int64_t n_tiles = (n + C::TM - 1) / C::TM;
+  int64_t grid = (int64_t)sm_count() * 3;
+  if (grid > n_tiles) grid = n_tiles;
+  ngcf_dense_fwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemFwd, (cudaStream_t)stream>>>(
+      E, LE_save, W1, W2, slope, n, E_next);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
+  return (size_t)sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
+}
+
+extern "C" int yr_ngcf_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT,
+                                 int64_t n, int d, const float* E, const float* LE, const float* E_next,
+                                 const float* G_next, const float* W1, const float* W2, float slope,
+                                 float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
+                                 yr_stream stream) {
+  if (!rowptrT || !colT || !valT || !E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 ||
+      !dW2 || !ws || n <= 0)
+    return YR_ERR_BAD_ARG;
+  if (d != 64) return YR_ERR_BAD_DIM;
+  if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
+  using C = DenseCfg<64>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)C::kSmemBwd));
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_tiles = (n + C::TM - 1) / C::TM;
+  int64_t grid = (int64_t)sm_count() * kBwdCtasPerSm;
+  if (grid > n_tiles) grid = n_tiles;
+  ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
+      E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws);
+  YR_CHECK_LAUNCH();
+  const int len = 2 * d * d;
+  reduce_partials_kernel<<<(len + 255) / 256, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
+  YR_CHECK_LAUNCH();
+  return yr_spmm_csr(rowptrT, colT, valT, n, d, T, G, 1, stream);
+}
+
+extern "C" int yr_ngcf_tail(const float* const* E_layers, float* const* G_layers, int n_layers,
+                            int64_t nU, int64_t nI, int d, const int64_t* uid, const int64_t* pos,
+                            const int64_t* neg, int64_t B, float* pos_out, float* neg_out,
+                            double* loss_sum, float* step_loss, int32_t* err, yr_stream stream) {
+  // loss_sum doubles as [0] running sum (+= batch mean) and needs a private accumulator: callers pass a
+  // 2-double block: loss_sum[0] = running sum, loss_sum[1] = scratch accumulator (zero between calls).
+  if (!E_layers || !uid || !pos || !neg || !loss_sum || B <= 0 || n_layers < 0 || n_layers > 7)
+    return YR_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 256;
+  int64_t blocks = (B * 32 + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const unsigned g = (unsigned)blocks;
+  double* acc = loss_sum + 1;
+  switch (dim_vpl(d)) {
+    case 1: ngcf_tail_kernel<1><<<g, threads, 0, s>>>(E_layers, G_layers, n_layers, nU, nI, uid, pos, neg, B, pos_out, neg_out, acc, err); break;
+    case 2: ngcf_tail_kernel<2><<<g, threads, 0, s>>>(E_layers, G_layers, n_layers, nU, nI, uid, pos, neg, B, pos_out, neg_out, acc, err); break;
+    case 4: ngcf_tail_kernel<4><<<g, threads, 0, s>>>(E_layers, G_layers, n_layers, nU, nI, uid, pos, neg, B, pos_out, neg_out, acc, err); break;
+    case 8: ngcf_tail_kernel<8><<<g, threads, 0, s>>>(E_layers, G_layers, n_layers, nU, nI, uid, pos, neg, B, pos_out, neg_out, acc, err); break;
+    default: return YR_ERR_BAD_DIM;
+  }
+  YR_CHECK_LAUNCH();
+  tail_finish_kernel<<<1, 1, 0, s>>>(acc, B, loss_sum, step_loss);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" int yr_dense_opt_step(float* p, const float* g, float* m, float* v, int64_t n,
+                                 const yr_opt* opt, yr_stream stream) {
+  if (!p || !g || !opt || n < 0) return YR_ERR_BAD_ARG;
+  if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
+  if (opt->kind != YR_OPT_SGD && (!m || !v)) return YR_ERR_BAD_ARG;
+  if (n == 0) return YR_OK;
+  const int threads = 256;
+  int64_t blocks = ((n >> 2) + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  dense_opt_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, *opt);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Composite entry points: a whole propagate / train step per host call.
+// ---------------------------------------------------------------------------------------------
+namespace yr {
+__global__ void concat_layers_kernel(const float* const* __restrict__ E_layers, int n_layers, int64_t n,
+                                     int d, float* __restrict__ out) {
+  const int width = (n_layers + 1) * d;
+  const int64_t total4 = n * (width / 4);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / (width / 4);
+    const int c = (int)(idx % (width / 4)) * 4;
+    const int l = c / d, k = c % d;
+    reinterpret_cast<float4*>(out)[idx] = __ldg(reinterpret_cast<const float4*>(E_layers[l] + r * d + k));
+  }
+}
+}  // namespace yr
+
+static int ngcf_state_ok(const yr_ngcf_state* st) {
+  if (!st || st->n_layers < 1 || st->n_layers > YR_NGCF_MAX_LAYERS || st->nU <= 0 || st->nI <= 0)
+    return YR_ERR_BAD_ARG;
+  if (!st->rowptr || !st->col || !st->val || !st->E[0]) return YR_ERR_BAD_ARG;
+  for (int l = 0; l < st->n_layers; ++l)
+    if (!st->E[l + 1] || !st->LE[l] || !st->W1[l] || !st->W2[l]) return YR_ERR_BAD_ARG;
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream stream) {
+  int rc = ngcf_state_ok(st);
+  if (rc) return rc;
+  const int64_t n = st->nU + st->nI;
+  for (int l = 0; l < st->n_layers; ++l) {
+    rc = yr_ngcf_layer_fwd(st->rowptr, st->col, st->val, n, st->d, st->E[l], st->W1[l], st->W2[l], slope,
+                           st->E[l + 1], st->LE[l], stream);
+    if (rc) return rc;
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                                  const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                                  float* step_loss, yr_stream stream) {
+  int rc = ngcf_state_ok(st);
+  if (rc) return rc;
+  if (!opt || !uid || !pos || !neg || B <= 0 || !st->rowptrT || !st->colT || !st->valT || !st->T ||
+      !st->E_dev || !st->G_dev || !st->ws || !st->loss)
+    return YR_ERR_BAD_ARG;
+  if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
+  const int L = st->n_layers, d = st->d;
+  const int64_t n = st->nU + st->nI;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int l = 0; l <= L; ++l) {
+    if (!st->G[l]) return YR_ERR_BAD_ARG;
+    YR_CUDA(cudaMemsetAsync(st->G[l], 0, sizeof(float) * (size_t)n * d, s));
+  }
+  rc = yr_ngcf_propagate(st, slope, stream);
+  if (rc) return rc;
+  rc = yr_ngcf_tail(st->E_dev, st->G_dev, L, st->nU, st->nI, d, uid, pos, neg, B, nullptr, nullptr, st->loss,
+                    step_loss, st->err, stream);
+  if (rc) return rc;
+  for (int l = L - 1; l >= 0; --l) {
+    if (!st->dW1[l] || !st->dW2[l]) return YR_ERR_BAD_ARG;
+    rc = yr_ngcf_layer_bwd(st->rowptrT, st->colT, st->valT, n, d, st->E[l], st->LE[l], st->E[l + 1],
+                           st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l], st->T, st->dW1[l], st->dW2[l],
+                           st->ws, st->ws_bytes, stream);
+    if (rc) return rc;
+  }
+  rc = yr_dense_opt_step(st->E[0], st->G[0], st->mE, st->vE, n * d, opt, stream);
+  if (rc) return rc;
+  for (int l = 0; l < L; ++l) {
+    rc = yr_dense_opt_step(st->W1[l], st->dW1[l], st->mW1[l], st->vW1[l], (int64_t)d * d, opt, stream);
+    if (rc) return rc;
+    rc = yr_dense_opt_step(st->W2[l], st->dW2[l], st->mW2[l], st->vW2[l], (int64_t)d * d, opt, stream);
+    if (rc) return rc;
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out,
+                              yr_stream stream) {
+  if (!E_layers || !out || n <= 0 || d <= 0 || (d & 3) || n_layers < 0 || n_layers > YR_NGCF_MAX_LAYERS)
+    return YR_ERR_BAD_ARG;
+  const int64_t total4 = n * ((n_layers + 1) * d / 4);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  yr::concat_layers_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(E_layers, n_layers, n, d, out);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}

@@ -1,0 +1,4 @@
+from .mf import MatrixFactorization
+from .ngcf import NGCF
+
+__all__ = ["MatrixFactorization", "NGCF"]

@@ -1,0 +1,281 @@
+"""Tensor-level wrappers over the C ABI (include/yelprec_b200.h) + autograd glue.
+
+Every function here launches hand-written sm_100a kernels from libyelprec_b200.so on the current CUDA
+stream. CPU tensors are rejected: the product has no CPU path (the CPU restatement lives in oracle/ and is
+test infrastructure only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import YelprecError, check, dptr, stream_ptr
+
+F32, I64, I32, F64 = torch.float32, torch.int64, torch.int32, torch.float64
+
+
+def _ids(t: torch.Tensor, device) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    t = t.to(device=device, dtype=I64, non_blocking=True)
+    return t.contiguous()
+
+
+def _raise_if_err(err: torch.Tensor, what: str) -> None:
+    """reference behaviour: nn.Embedding raises IndexError on an out-of-range id."""
+    if int(err.item()) != 0:
+        err.zero_()
+        raise IndexError(f"{what}: index out of range in self")
+
+
+# ----------------------------------------------------------------------------------------------------
+# MF score / BPR loss (autograd-capable, so an unmodified reference trainer can call loss.backward())
+# ----------------------------------------------------------------------------------------------------
+class _MFScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, V, uid, iid):
+        lib = _cabi.load()
+        Uc, Vc = U.detach().contiguous(), V.detach().contiguous()
+        out = torch.empty(uid.numel(), device=U.device, dtype=F32)
+        err = torch.zeros(1, device=U.device, dtype=I32)
+        check(lib.yr_mf_score(dptr(Uc, F32), dptr(Vc, F32), Uc.shape[0], Vc.shape[0], Uc.shape[1],
+                              dptr(uid, I64), dptr(iid, I64), uid.numel(), dptr(out), dptr(err),
+                              stream_ptr(U.device)), "yr_mf_score")
+        _raise_if_err(err, "MatrixFactorization.forward")
+        ctx.save_for_backward(Uc, Vc, uid, iid)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _cabi.load()
+        U, V, uid, iid = ctx.saved_tensors
+        gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+        gout = gout.contiguous().to(F32)
+        check(lib.yr_mf_score_bwd(dptr(U), dptr(V), U.shape[0], V.shape[0], U.shape[1], dptr(uid), dptr(iid),
+                                  uid.numel(), dptr(gout), dptr(gU), dptr(gV), stream_ptr(U.device)),
+              "yr_mf_score_bwd")
+        return gU, gV, None, None
+
+
+def mf_score(U: torch.Tensor, V: torch.Tensor, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
+    uid, iid = _ids(uid, U.device), _ids(iid, U.device)
+    if uid.numel() != iid.numel():
+        raise RuntimeError(f"The size of tensor a ({uid.numel()}) must match the size of tensor b ({iid.numel()})")
+    return _MFScore.apply(U, V, uid, iid)
+
+
+class _BPRLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, neg):
+        lib = _cabi.load()
+        pos, neg = pos.contiguous().to(F32), neg.contiguous().to(F32)
+        loss = torch.empty((), device=pos.device, dtype=F32)
+        check(lib.yr_bpr_loss_fwd(dptr(pos), dptr(neg), pos.numel(), dptr(loss), stream_ptr(pos.device)),
+              "yr_bpr_loss_fwd")
+        ctx.save_for_backward(pos, neg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        lib = _cabi.load()
+        pos, neg = ctx.saved_tensors
+        gpos, gneg = torch.empty_like(pos), torch.empty_like(neg)
+        gloss = gloss.contiguous().to(F32)
+        check(lib.yr_bpr_loss_bwd(dptr(pos), dptr(neg), pos.numel(), dptr(gloss), dptr(gpos), dptr(gneg),
+                                  stream_ptr(pos.device)), "yr_bpr_loss_bwd")
+        return gpos, gneg
+
+
+def bpr_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    if not pos.is_cuda:
+        raise YelprecError("BPRLoss: expected CUDA tensors (no CPU fallback)")
+    return _BPRLoss.apply(pos, neg)
+
+
+# ----------------------------------------------------------------------------------------------------
+# SpMM / NGCF layer (autograd-capable)
+# ----------------------------------------------------------------------------------------------------
+def spmm_csr(rowptr, col, val, X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False):
+    lib = _cabi.load()
+    X = X.contiguous()
+    if out is None:
+        out = torch.empty_like(X)
+        accumulate = False
+    check(lib.yr_spmm_csr(dptr(rowptr, I32), dptr(col, I32), dptr(val, F32), X.shape[0], X.shape[1], dptr(X, F32),
+                          dptr(out, F32), 1 if accumulate else 0, stream_ptr(X.device)), "yr_spmm_csr")
+    return out
+
+
+def ngcf_layer_fwd(csr, E, W1, W2, slope=0.01):
+    lib = _cabi.load()
+    E, W1, W2 = E.contiguous(), W1.contiguous(), W2.contiguous()
+    En, LE = torch.empty_like(E), torch.empty_like(E)
+    check(lib.yr_ngcf_layer_fwd(dptr(csr.rowptr, I32), dptr(csr.col, I32), dptr(csr.val, F32), E.shape[0], E.shape[1],
+                                dptr(E, F32), dptr(W1, F32), dptr(W2, F32), float(slope), dptr(En), dptr(LE),
+                                stream_ptr(E.device)), "yr_ngcf_layer_fwd")
+    return En, LE
+
+
+def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01):
+    """G (accumulated in place) += dLoss/dE; returns (dW1, dW2)."""
+    lib = _cabi.load()
+    d = E.shape[1]
+    T = torch.empty_like(E)
+    dW1, dW2 = torch.empty_like(W1), torch.empty_like(W2)
+    nbytes = lib.yr_ngcf_layer_bwd_ws_bytes(d)
+    ws = torch.empty(nbytes, device=E.device, dtype=torch.uint8)
+    check(lib.yr_ngcf_layer_bwd(dptr(csr.rowptr_t, I32), dptr(csr.col_t, I32), dptr(csr.val_t, F32), E.shape[0], d,
+                                dptr(E.contiguous(), F32), dptr(LE, F32), dptr(En, F32), dptr(Gn.contiguous(), F32),
+                                dptr(W1.contiguous(), F32), dptr(W2.contiguous(), F32), float(slope), dptr(G, F32),
+                                dptr(T), dptr(dW1), dptr(dW2), dptr(ws), nbytes, stream_ptr(E.device)),
+          "yr_ngcf_layer_bwd")
+    return dW1, dW2
+
+
+class _NGCFLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, W1, W2, csr, slope):
+        Ed, W1d, W2d = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
+        En, LE = ngcf_layer_fwd(csr, Ed, W1d, W2d, slope)
+        ctx.save_for_backward(Ed, LE, En, W1d, W2d)
+        ctx.csr, ctx.slope = csr, slope
+        return En
+
+    @staticmethod
+    def backward(ctx, Gn):
+        E, LE, En, W1, W2 = ctx.saved_tensors
+        G = torch.zeros_like(E)
+        dW1, dW2 = ngcf_layer_bwd(ctx.csr, E, LE, En, Gn, W1, W2, G, ctx.slope)
+        return G, dW1, dW2, None, None
+
+
+def ngcf_layer(E, W1, W2, csr, slope=0.01):
+    return _NGCFLayer.apply(E, W1, W2, csr, slope)
+
+
+def dense_opt_step(p, g, m, v, opt: _cabi.YrOpt):
+    lib = _cabi.load()
+    check(lib.yr_dense_opt_step(dptr(p, F32), dptr(g.contiguous(), F32), dptr(m), dptr(v), p.numel(), C.byref(opt),
+                                stream_ptr(p.device)), "yr_dense_opt_step")
+
+
+def device_ptr_array(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """int64 device tensor holding the data pointers of `tensors` (a `float* const*` for the kernels)."""
+    dev = tensors[0].device
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=I64).to(dev)
+
+
+def ngcf_concat(E_layers: Sequence[torch.Tensor]) -> torch.Tensor:
+    lib = _cabi.load()
+    n, d = E_layers[0].shape
+    L = len(E_layers) - 1
+    ptrs = device_ptr_array([e.contiguous() for e in E_layers])
+    out = torch.empty(n, (L + 1) * d, device=E_layers[0].device, dtype=F32)
+    check(lib.yr_ngcf_concat(dptr(ptrs), L, n, d, dptr(out), stream_ptr(out.device)), "yr_ngcf_concat")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# evaluation
+# ----------------------------------------------------------------------------------------------------
+class DeviceEvalCSR:
+    """EvalCSR (data/graph.py) uploaded once; reused across epochs."""
+
+    def __init__(self, csr, device, K: int):
+        from .data.graph import inv_log2_table
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.n_eval = csr.n_eval
+        self.eval_uid = t(csr.eval_uid)
+        self.mask_ptr, self.mask_idx = t(csr.mask_ptr), t(csr.mask_idx if csr.mask_idx.size else np.zeros(1, np.int32))
+        self.act_ptr, self.act_idx = t(csr.act_ptr), t(csr.act_idx if csr.act_idx.size else np.zeros(1, np.int32))
+        self.act_nuniq = t(csr.act_nuniq if csr.act_nuniq.size else np.zeros(1, np.int32))
+        self.inv_log2 = t(inv_log2_table(K))
+        self.K = K
+
+    def slice(self, lo: int, hi: int) -> "DeviceEvalCSR":
+        """Rows [lo, hi) — user sharding across GPUs (no communication until the metric sums)."""
+        out = object.__new__(DeviceEvalCSR)
+        out.n_eval = hi - lo
+        out.eval_uid = self.eval_uid[lo:hi].contiguous()
+        for name in ("mask", "act"):
+            ptr = getattr(self, f"{name}_ptr")
+            idx = getattr(self, f"{name}_idx")
+            base, end = int(ptr[lo].item()), int(ptr[hi].item())
+            setattr(out, f"{name}_ptr", (ptr[lo:hi + 1] - base).contiguous())
+            sl = idx[base:end]
+            setattr(out, f"{name}_idx", sl.contiguous() if sl.numel() else torch.zeros(1, dtype=I32, device=idx.device))
+        nu = self.act_nuniq[lo:hi]
+        out.act_nuniq = nu.contiguous() if nu.numel() else torch.zeros(1, dtype=I32, device=nu.device)
+        out.inv_log2, out.K = self.inv_log2, self.K
+        return out
+
+
+def transpose_items(V: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """[nI x d] -> ([pad32(d) x ldt], ldt) with ldt = nI rounded up to the 128-item tile."""
+    lib = _cabi.load()
+    V = V.detach().contiguous()
+    nI, d = V.shape
+    ldt = (nI + 127) // 128 * 128
+    d_pad = (d + 31) // 32 * 32
+    Vt = torch.empty(d_pad, ldt, device=V.device, dtype=F32)
+    check(lib.yr_transpose_items(dptr(V, F32), nI, d, dptr(Vt), ldt, stream_ptr(V.device)), "yr_transpose_items")
+    return Vt, ldt
+
+
+def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None):
+    """Returns (topk [n_eval x K] int64, topk_score, user_metrics [n_eval x 4] f64, sums [6] f64) on device."""
+    lib = _cabi.load()
+    Uemb = Uemb.detach().contiguous()
+    dev = Uemb.device
+    nI, d = Vemb.shape
+    if Vt is None:
+        Vt, ldt = transpose_items(Vemb)
+    else:
+        ldt = Vt.shape[1]
+    n, K = ecsr.n_eval, ecsr.K
+    topk = torch.empty(max(n, 1), K, device=dev, dtype=I64)
+    tsc = torch.empty(max(n, 1), K, device=dev, dtype=F32)
+    um = torch.zeros(max(n, 1), 4, device=dev, dtype=F64)
+    sums = torch.zeros(6, device=dev, dtype=F64)
+    err = torch.zeros(1, device=dev, dtype=I32)
+    ws = torch.empty(lib.yr_eval_ws_bytes(n, d, K), device=dev, dtype=torch.uint8)
+    check(lib.yr_eval_topk_metrics(dptr(Uemb, F32), Uemb.shape[0], dptr(Vt, F32), ldt, nI, d, dptr(ecsr.eval_uid, I64), n,
+                                   dptr(ecsr.mask_ptr, I32), dptr(ecsr.mask_idx, I32), dptr(ecsr.act_ptr, I32),
+                                   dptr(ecsr.act_idx, I32), dptr(ecsr.act_nuniq, I32), dptr(ecsr.inv_log2, F64), K,
+                                   dptr(topk), dptr(tsc), dptr(um), dptr(sums), dptr(ws), ws.numel(), dptr(err),
+                                   stream_ptr(dev)), "yr_eval_topk_metrics")
+    return topk[:n], tsc[:n], um[:n], sums, err
+
+
+def metrics_from_sums(sums, n_eval: int):
+    """(precision, recall, map, ndcg) with the reference's divisors (metric.py:24,47,70,104 — quirk Q6)."""
+    s = [float(x) for x in sums]
+    if n_eval == 0:
+        raise ZeroDivisionError("division by zero")        # what metric.py does on an empty eval set
+    return (s[0] / n_eval, s[1] / s[4], s[2] / s[5], s[3] / s[4])
+
+
+def topk_masked_row(pred: torch.Tensor, mask_items, K: int) -> torch.Tensor:
+    lib = _cabi.load()
+    pred = pred.detach().contiguous().to(F32)
+    mask = torch.as_tensor(np.asarray(mask_items, dtype=np.int64).reshape(-1)).to(pred.device)
+    out = torch.empty(K, device=pred.device, dtype=I64)
+    check(lib.yr_topk_masked_row(dptr(pred), pred.numel(), dptr(mask) if mask.numel() else None, mask.numel(), K,
+                                 dptr(out), stream_ptr(pred.device)), "yr_topk_masked_row")
+    return out
+
+
+def topk_metrics(predicted: torch.Tensor, ecsr: DeviceEvalCSR):
+    lib = _cabi.load()
+    predicted = predicted.contiguous()
+    n = predicted.shape[0]
+    um = torch.zeros(max(n, 1), 4, device=predicted.device, dtype=F64)
+    sums = torch.zeros(6, device=predicted.device, dtype=F64)
+    check(lib.yr_topk_metrics(dptr(predicted, I64), predicted.shape[1], n, dptr(ecsr.act_ptr, I32),
+                              dptr(ecsr.act_idx, I32), dptr(ecsr.act_nuniq, I32), dptr(ecsr.inv_log2, F64), ecsr.K,
+                              dptr(um), dptr(sums), stream_ptr(predicted.device)), "yr_topk_metrics")
+    return um[:n], sums

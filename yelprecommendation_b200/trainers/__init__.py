@@ -1,0 +1,4 @@
+from .mf_trainer import MFTrainer
+from .ngcf_trainer import NGCFTrainer
+
+__all__ = ["MFTrainer", "NGCFTrainer"]
