@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the BPR-MF / NGCF train + full-catalog eval hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline (BASELINE.json configs[1]): NGCF 3-layer d=64 BPR training on the synthetic Yelp2018-shape graph
+(31,668 users x 38,048 items, 1,561,406 interactions), batch 2048, Adam lr 1e-4 — `value` = training triples/s
+with every input resident in HBM; `e2e` = the same metric through NGCFTrainer.train() with HOST batches (pinned
+H2D of the ids and a D2H read of the loss every step). The JSON line also carries, under "extra", the two other
+rows of the metric: BPR-MF training triples/s (configs[0]) and full-catalog top-10 eval users/s for the MF and
+NGCF embeddings (configs[2]), each with its own roofline fraction.
+
+N > 1 (one process per GPU under torchrun): NGCF/MF training at Yelp shape does not shard (17.8 MB of parameters,
+sequential step semantics — DESIGN.md "replicas only"), so every rank trains an independent replica and `value`
+is the sum over replicas (weak scaling); evaluation shards its rows across ranks with no data-path collective.
+
+`--impl reference`: the reference's own CPU implementation of the same step (oracle/torch_port.py, the torch-CPU
+restatement pinned to the real reference by tests/golden — /root/reference does not exist on the GPU box), on all
+host threads, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ngcf_bpr_train_triples_per_sec"
+UNIT = "triples/s"
+B = 2048
+D = 64
+LAYERS = 3
+M_BYTES = (31_668 + 38_048) * D * 4            # one N x d fp32 row matrix = 17.85 MB
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=float(j["hbm_gbs"]), bf16=float(j["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(seed=2018):
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr, build_laplacian
+    inter = syn.make_interactions(seed=seed)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tp_, tn = syn.sample_triples(split, inter.num_items, seed=42)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    uid, pos, mask = syn.eval_lists(split, "valid")
+    ecsr = build_eval_csr(uid, pos, mask, inter.num_items)
+    return SimpleNamespace(inter=inter, split=split, tri=(tu, tp_, tn), L=L, ecsr=ecsr)
+
+
+def cfg(**kw):
+    base = dict(device="cuda", model_dir=tempfile.mkdtemp(), embed_size=D, optimizer="adam", lr=1e-4, weight_decay=0.0,
+                top_n=10, wandb=False, num_orders=LAYERS, epochs=1, patience=1, best_metric="loss", batch_size=B)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def timed(fn, n, stream_sync=True):
+    """ms for n calls of fn, CUDA events on the current stream, synchronised on both sides."""
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.torch_port import NGCFPort
+    from yelprecommendation_b200.data import synthetic as syn
+    w = build_workload()
+    torch.manual_seed(42)
+    n = w.inter.num_users + w.inter.num_items
+    emb = torch.randn(n, D)
+    lin = lambda: torch.nn.Linear(D, D, bias=False).weight.detach()
+    port = NGCFPort(emb, [lin() for _ in range(LAYERS)], [lin() for _ in range(LAYERS)], w.inter.num_users, w.L,
+                    "adam", 1e-4, 0.0)
+    batches = syn.to_batches(*[a[: B * (args.steps + args.warmup)] for a in w.tri], B)
+    budget_s = float(os.environ.get("YR_REF_BUDGET_S", "170"))
+    t0 = time.perf_counter()
+    port.train(batches[:1])
+    t_first = time.perf_counter() - t0
+    warm = max(0, min(args.warmup - 1, int(budget_s * 0.2 / max(t_first, 1e-6))))
+    if warm:
+        port.train(batches[1:1 + warm])
+    steps = max(1, min(args.steps, int(budget_s * 0.8 / max(t_first, 1e-6))))
+    use = batches[1 + warm:1 + warm + steps]
+    t0 = time.perf_counter()
+    port.train(use)
+    dt = time.perf_counter() - t0
+    val = steps * B / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "steps_requested": args.steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NGCF 3-layer d=64 BPR train step, Yelp2018-shape graph, batch 2048, Adam lr 1e-4"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} full train steps of oracle/torch_port.NGCFPort (torch CPU ops of the "
+                                       "reference, N x N identity hoisted: (L+I)E = LE + E)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": {"cpu_count": os.cpu_count(), "torch_threads": cores}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the MF-train / eval sub-benchmarks")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", help="profiling aid: run only 'ngcf' | 'mf' | 'eval' steps, no JSON contract")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if not args.only else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    from yelprecommendation_b200 import _cabi, ops, parallel
+    if not os.path.exists(_cabi.lib_path()):
+        ge.build()
+    lib = _cabi.load()
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.trainers import MFTrainer, NGCFTrainer
+
+    pk = peaks()
+    w = build_workload()
+    K, W = args.steps, args.warmup
+    tu, tp_, tn = w.tri
+    n_need = B * (K + W)
+    reps = (n_need + len(tu) - 1) // len(tu)
+    # each replica (rank) walks the pre-sampled triples from a different offset
+    off = (rank * 7919 * B) % len(tu)
+    take = lambda a: np.roll(np.tile(a, reps), -off)[:n_need]
+    hu, hp, hn = take(tu), take(tp_), take(tn)
+    du, dp, dn = (torch.from_numpy(a).to(dev) for a in (hu, hp, hn))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ------------------------------------------------------------------ NGCF training (headline)
+    torch.manual_seed(42)
+    ntr = NGCFTrainer(cfg(), w.inter.num_items, w.inter.num_users, w.L)
+    st, _ = ntr._state()
+    sl = torch.zeros(K + W, device=dev)
+
+    def ngcf_step(i):
+        s = i * B
+        ntr.train_step_on_device(du[s:s + B], dp[s:s + B], dn[s:s + B], sl[i:i + 1], st)
+
+    for i in range(W):
+        ngcf_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(lambda i: ngcf_step(W + i), K)
+    clocks = sampler.stop()
+    barrier()
+    ms = max_over_ranks(ms)
+    ngcf_loss = ntr.loss_sum()
+    value = world * K * B / (ms * 1e-3)
+    if args.only == "ngcf":
+        print(f"ngcf only: {ms / K:.3f} ms/step", flush=True)
+        return 0
+
+    # per-kernel timing of the step's pieces, each through its own C-ABI entry (same stream, CUDA events)
+    import ctypes as C
+    csr = ntr.model.csr(w.L)
+    n = w.inter.num_users + w.inter.num_items
+    E0 = ntr.model.embedding.weight.data
+    X, Y, G, T = (torch.randn(n, D, device=dev) for _ in range(4))
+    W1, W2 = ntr.model.W1[0].weight.data, ntr.model.W2[0].weight.data
+    nnzL = csr.nnz
+    csr_bytes = nnzL * 8 + (n + 1) * 4
+    reps_k = 20
+    pieces = {}
+
+    def piece(name, fn, alg_bytes):
+        for _ in range(3):
+            fn(0)
+        t = timed(fn, reps_k) / reps_k
+        pieces[name] = {"ms": t, "alg_bytes": alg_bytes, "gbs": alg_bytes / (t * 1e-3) / 1e9}
+
+    piece("spmm_csr", lambda i: ops.spmm_csr(csr.fwd, X, out=Y), csr_bytes + 2 * M_BYTES)
+    piece("layer_fwd(spmm+dense)", lambda i: ops.ngcf_layer_fwd(csr, X, W1, W2), csr_bytes + 3 * M_BYTES)
+    piece("layer_bwd(dense+reduce+spmmT)", lambda i: ops.ngcf_layer_bwd(csr, X, Y, T, G, W1, W2, torch.zeros_like(X)),
+          csr_bytes + 7 * M_BYTES)
+    optst = _cabi.make_opt("adam", 1e-4, 0.0, 5)
+    m1, v1 = torch.zeros_like(X), torch.zeros_like(X)
+    piece("dense_adam", lambda i: ops.dense_opt_step(X, G, m1, v1, optst), 6 * M_BYTES)
+    step_alg_bytes = LAYERS * (csr_bytes + 3 * M_BYTES) + LAYERS * (csr_bytes + 7 * M_BYTES) + \
+        3 * B * (LAYERS + 1) * D * 4 * 2 + 6 * M_BYTES
+    dom = max(("layer_bwd(dense+reduce+spmmT)", "layer_fwd(spmm+dense)", "spmm_csr", "dense_adam"),
+              key=lambda k: pieces[k]["ms"] * (LAYERS if "layer" in k else 1))
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": pieces[dom]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": pieces[dom]["gbs"] / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                "launch_ms": pieces[dom]["ms"], "alg_bytes_per_launch": pieces[dom]["alg_bytes"],
+                "step": {"alg_bytes": step_alg_bytes, "achieved": step_alg_bytes / (ms / K * 1e-3) / 1e9,
+                         "frac": step_alg_bytes / (ms / K * 1e-3) / 1e9 / pk["hbm"]},
+                "pieces": {k: {"ms": round(v["ms"], 4), "GBps": round(v["gbs"], 1)} for k, v in pieces.items()}}
+    del X, Y, G, T, m1, v1
+
+    # ------------------------------------------------------------------ e2e through the public trainer API
+    host_batches = syn.to_batches(hu, hp, hn, B)
+    for b in host_batches[:W]:
+        ntr.train([b])
+    barrier()
+    t0 = time.perf_counter()
+    ms_e2e = timed(lambda i: ntr.train([host_batches[W + i]]), K)      # H2D ids + step + D2H loss, every step
+    ms_e2e = max_over_ranks(max(ms_e2e, (time.perf_counter() - t0) * 1e3))
+    e2e = {"value": world * K * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
+           "d2h_bytes_per_step": 8 + 4, "api": "NGCFTrainer.train([batch]) per step (host int64 batches in, float loss out)"}
+
+    extra = {}
+    if not args.no_extra:
+        # -------------------------------------------------------------- BPR-MF training (configs[0])
+        torch.manual_seed(42)
+        mtr = MFTrainer(cfg(), w.inter.num_items, w.inter.num_users)
+        for name, okw, bpt in (("adam", dict(optimizer="adam"), None), ("sgd", dict(optimizer="sgd"), 1560)):
+            torch.manual_seed(42)
+            mtr = MFTrainer(cfg(**okw), w.inter.num_items, w.inter.num_users)
+            steps_mf = max(K, 200)
+            nt = B * steps_mf
+            rp = (nt + len(tu) - 1) // len(tu)
+            mu, mp, mn = (torch.from_numpy(np.tile(a, rp)[:nt]).to(dev) for a in (tu, tp_, tn))
+            mtr.train_on_device(mu[: B * 8], mp[: B * 8], mn[: B * 8], B)
+            barrier()
+            ms_mf = max_over_ranks(timed(lambda i: mtr.train_on_device(mu, mp, mn, B), 1))
+            mtr.loss_sum()
+            tps = world * nt / (ms_mf * 1e-3)
+            alg = (107.1e6 / B + 792) if name == "adam" else 1560.0
+            extra[f"mf_train_{name}"] = {"value": tps, "unit": UNIT, "us_per_step": 1e3 * ms_mf / steps_mf,
+                                         "alg_bytes_per_triple": alg, "hbm_frac": tps / world * alg / 1e9 / pk["hbm"],
+                                         "note": "one persistent cooperative launch for all steps; tables (17.8 MB) are L2-resident"}
+            if name == "sgd":
+                hb = syn.to_batches(*[np.tile(a, rp)[:nt] for a in (tu, tp_, tn)], B)
+                mtr.train(hb[:8])
+                barrier()
+                t0 = time.perf_counter()
+                mtr.train(hb)
+                torch.cuda.synchronize()
+                extra["mf_train_sgd"]["e2e_value"] = world * nt / (time.perf_counter() - t0)
+        # -------------------------------------------------------------- full-catalog evaluation (configs[2])
+        lo, hi = parallel.shard_range(w.ecsr.n_eval, rank, world)
+        decsr_full = ops.DeviceEvalCSR(w.ecsr, dev, 10)
+        decsr = decsr_full.slice(lo, hi) if world > 1 else decsr_full
+        Up, Vp = syn.planted_embeddings(w.inter)
+        Ud, Vd = torch.from_numpy(Up).to(dev), torch.from_numpy(Vp).to(dev)
+        layers, _, _ = ntr.propagate()
+        cat = ops.ngcf_concat(layers)
+        for name, (Ue, Ve) in (("mf", (Ud, Vd)), ("ngcf", (cat[: w.inter.num_users], cat[w.inter.num_users:]))):
+            Vt, _ = ops.transpose_items(Ve.contiguous())
+            ops.eval_topk_metrics(Ue, Ve, decsr, Vt)
+            barrier()
+            reps_e = 3
+            res = []
+            ms_ev = timed(lambda i: res.append(ops.eval_topk_metrics(Ue, Ve, decsr, Vt)), reps_e) / reps_e
+            ms_ev = max_over_ranks(ms_ev)
+            sums = parallel.all_reduce_sums(res[-1][3])
+            d_eff = Ue.shape[1]
+            flops = 2.0 * w.ecsr.n_eval * w.inter.num_items * d_eff
+            ups = w.ecsr.n_eval / (ms_ev * 1e-3)
+            extra[f"eval_{name}"] = {"value": ups, "unit": "users/s", "ms": ms_ev, "d_eff": d_eff,
+                                     "tflops": flops / (ms_ev * 1e-3) / 1e12,
+                                     "tensor_frac_vs_bf16_peak": flops / (ms_ev * 1e-3) / 1e12 / pk["bf16"],
+                                     "metrics": [round(x, 6) for x in ops.metrics_from_sums(sums.cpu(), w.ecsr.n_eval)],
+                                     "note": "exact-fp32 FFMA scoring (one fma chain per score, bit-exact top-K)"}
+            # e2e: host lists -> CSR upload -> kernel -> metrics back
+        t0 = time.perf_counter()
+        mtr.evaluate(w.ecsr)
+        extra["eval_mf"]["e2e_users_per_s_first_call"] = w.ecsr.n_eval / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        mtr.evaluate(w.ecsr)
+        extra["eval_mf"]["e2e_users_per_s"] = w.ecsr.n_eval / (time.perf_counter() - t0)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.torch_port import NGCFPort
+        sd = {k: v.detach().cpu().clone() for k, v in ntr.model.state_dict().items()}
+        port = NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(LAYERS)],
+                        [sd[f"W2.{l}.weight"] for l in range(LAYERS)], w.inter.num_users, w.L, "adam", 1e-4, 0.0)
+        port.train(host_batches[:1])
+        t0 = time.perf_counter()
+        n_cpu = 0
+        while n_cpu < 3 or (time.perf_counter() - t0 < 12 and n_cpu < 10):
+            port.train(host_batches[1 + n_cpu:2 + n_cpu])
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n_cpu * B / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n_cpu} full NGCF train steps (batch 2048) of oracle/torch_port.NGCFPort on the host",
+                        "ms_per_step": 1e3 * dt / n_cpu}
+
+    if rank == 0:
+        launches_per_step = LAYERS * 2 + 2 + LAYERS * 3 + 1 + 2 * LAYERS
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "NGCF 3-layer d=64 BPR train step, Yelp2018-shape graph (31,668u x 38,048i, "
+                                       "1,561,406 interactions), batch 2048, Adam lr 1e-4 (BASELINE.json configs[1])",
+                           "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (replicas only)",
+                           "l2": "per-step working set (~0.4 GB of E/LE/G/T/CSR/Adam state) exceeds the 126 MB L2; no flush"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "extra": extra, "loss_sum": ngcf_loss,
+                "lib": os.path.relpath(_cabi.lib_path(), ROOT)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,28 +108,52 @@ int yr_bpr_mf_validate(const float* U, const float* V, int64_t nU, int64_t nI, i
  * NGCF  (models/ngcf.py, trainers/ngcf_trainer.py)
  * ---------------------------------------------------------------------------------------------- */
 
-/* Y = A X (accumulate == 0) or Y += A X (accumulate != 0) for a CSR matrix with int32 indices and
- * fp32 values, X/Y row-major [n_rows x d]; row sums run in CSR order as one fma chain.
+/* CSR matrix (int32 indices, fp32 values) plus its load-balancing plan. Rows longer than YR_SPMM_CHUNK
+ * non-zeros are cut into chunks of YR_SPMM_CHUNK consecutive non-zeros so that one warp never walks more than
+ * that (the Yelp-shape graph has item rows with > 10,000 non-zeros). The plan is built once per graph on the
+ * host (yr_spmm_plan_*_h) and uploaded by the caller.
+ * Canonical summation order (the oracle restates it): a row with <= YR_SPMM_CHUNK non-zeros is ONE fma chain in
+ * CSR order (starting from Y's old value when accumulating); a longer row is the left-to-right sum of its chunk
+ * partials, each chunk one fma chain from 0 (and Y_old + that sum when accumulating). */
+#define YR_SPMM_CHUNK 128
+typedef struct yr_csr {
+  int64_t n_rows, nnz;
+  const int32_t *rowptr, *col;
+  const float* val;
+  int32_t n_chunks;               /* work items: one per short row, ceil(len/CHUNK) per long row */
+  const int32_t *chunk_row;       /* [n_chunks] row of the chunk */
+  const int32_t *chunk_start;     /* [n_chunks] first non-zero of the chunk */
+  const int32_t *chunk_slot;      /* [n_chunks] -1 = whole row (direct store), else slot in `partials` */
+  int32_t n_split_rows;           /* rows that were cut */
+  const int32_t *split_row;       /* [n_split_rows] */
+  const int32_t *split_ptr;       /* [n_split_rows+1] range of partial slots of each split row */
+  float* partials;                /* [split_ptr[n_split_rows] x d] scratch */
+} yr_csr;
+
+/* Host-side plan builder (host pointers). Call _size_h first, allocate, then _fill_h. */
+int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chunks_h, int32_t* n_split_rows_h,
+                        int32_t* n_partials_h);
+int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_row_h, int32_t* chunk_start_h,
+                        int32_t* chunk_slot_h, int32_t* split_row_h, int32_t* split_ptr_h);
+
+/* Y = A X (accumulate == 0) or Y += A X (accumulate != 0), X/Y row-major [n_rows x d].
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */
-int yr_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, int d,
-                const float* X, float* Y, int accumulate, yr_stream stream);
+int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream);
 
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
  *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
  * W1, W2 are nn.Linear weights [d x d] (out x in). LE_save [n x d] receives L E (kept for backward). */
-int yr_ngcf_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n, int d,
-                      const float* E, const float* W1, const float* W2, float slope,
+int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2, float slope,
                       float* E_next, float* LE_save, yr_stream stream);
 
-/* Backward of one layer. G_next = dLoss/dE_next. (rowptrT,colT,valT) is the CSR of L^T.
+/* Backward of one layer. G_next = dLoss/dE_next. LT is the CSR of L^T.
  *   dZ = G_next * leaky'(E_next); dS = dZ W1; dP = dZ W2;
- *   G += dS + dP*LE + L^T (dS + dP*E);   dW1 += dZ^T (LE+E);  dW2 += dZ^T (E*LE)
+ *   G += dS + dP*LE + L^T (dS + dP*E);   dW1 = dZ^T (LE+E);  dW2 = dZ^T (E*LE)
  * T [n x d] is scratch for the transposed SpMM operand; ws holds per-CTA dW partials
  * (yr_ngcf_layer_bwd_ws_bytes). dW1/dW2 are OVERWRITTEN with this layer's weight gradient. */
 size_t yr_ngcf_layer_bwd_ws_bytes(int d);
-int yr_ngcf_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int64_t n, int d,
-                      const float* E, const float* LE, const float* E_next, const float* G_next,
-                      const float* W1, const float* W2, float slope,
+int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
+                      const float* G_next, const float* W1, const float* W2, float slope,
                       float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
                       yr_stream stream);
 
@@ -156,8 +180,7 @@ int yr_dense_opt_step(float* p, const float* g, float* m, float* v, int64_t n, c
 typedef struct yr_ngcf_state {
   int64_t nU, nI;
   int32_t d, n_layers;
-  const int32_t *rowptr, *col;   const float* val;    /* CSR of L   */
-  const int32_t *rowptrT, *colT; const float* valT;   /* CSR of L^T */
+  yr_csr L, LT;                       /* CSR (+plan) of L and of L^T */
   float* E[YR_NGCF_MAX_LAYERS + 1];   /* [n x d] each, n = nU + nI */
   float* LE[YR_NGCF_MAX_LAYERS];      /* saved L E_l */
   float* G[YR_NGCF_MAX_LAYERS + 1];   /* dLoss/dE_l */

@@ -111,19 +111,41 @@ float orc_mf_train_step(float* U, float* V, int64_t nU, int64_t nI, int d, float
   return (float)(lacc / (double)B);
 }
 
-/* ---- torch.sparse.mm(L, E), models/ngcf.py:64,67: CSR rows, fma chain in column order -------------- */
+/* ---- torch.sparse.mm(L, E), models/ngcf.py:64,67 ------------------------------------------------------
+ * Canonical order (include/yelprec_b200.h, yr_csr): rows with <= 128 non-zeros are one fma chain in column
+ * order (seeded with Y's old value when accumulating); longer rows are the left-to-right sum of the partial
+ * chains of their 128-non-zero chunks (plus Y_old when accumulating). */
+#define ORC_SPMM_CHUNK 128
 void orc_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n, int d, const float* X,
                   float* Y, int accumulate) {
+  float* part = (float*)malloc(sizeof(float) * (size_t)d);
+  float* tot = (float*)malloc(sizeof(float) * (size_t)d);
   for (int64_t r = 0; r < n; ++r) {
     float* y = Y + r * d;
-    if (!accumulate)
-      for (int k = 0; k < d; ++k) y[k] = 0.f;
-    for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
-      const float a = val[j];
-      const float* x = X + (int64_t)col[j] * d;
-      for (int k = 0; k < d; ++k) y[k] = fmaf(a, x[k], y[k]);
+    const int32_t s = rowptr[r], e = rowptr[r + 1];
+    if (e - s <= ORC_SPMM_CHUNK) {
+      if (!accumulate)
+        for (int k = 0; k < d; ++k) y[k] = 0.f;
+      for (int32_t j = s; j < e; ++j) {
+        const float a = val[j];
+        const float* x = X + (int64_t)col[j] * d;
+        for (int k = 0; k < d; ++k) y[k] = fmaf(a, x[k], y[k]);
+      }
+      continue;
     }
+    for (int32_t c = s; c < e; c += ORC_SPMM_CHUNK) {
+      const int32_t ce = c + ORC_SPMM_CHUNK < e ? c + ORC_SPMM_CHUNK : e;
+      for (int k = 0; k < d; ++k) part[k] = 0.f;
+      for (int32_t j = c; j < ce; ++j) {
+        const float a = val[j];
+        const float* x = X + (int64_t)col[j] * d;
+        for (int k = 0; k < d; ++k) part[k] = fmaf(a, x[k], part[k]);
+      }
+      for (int k = 0; k < d; ++k) tot[k] = (c == s) ? part[k] : tot[k] + part[k];
+    }
+    for (int k = 0; k < d; ++k) y[k] = accumulate ? y[k] + tot[k] : tot[k];
   }
+  free(part); free(tot);
 }
 
 /* ---- NGCF.embedding_propagation, models/ngcf.py:60-72 (identity hoisted: (L+I)E = LE + E) ---------- */

@@ -36,7 +36,7 @@ def test_eval_golden_small(prefix):
     from yelprecommendation_b200.data.graph import build_eval_csr
     from yelprecommendation_b200 import ops
     g = load_npz("mf_small.npz")
-    U, V = g["eval_U"], g["eval_V"]
+    U, V = g["eval_U"].astype(np.float32), g["eval_V"].astype(np.float32)
     uid = g[f"{prefix}_uid"]
     csr = build_eval_csr(uid, lists_from(g, prefix, "pos_items"), lists_from(g, prefix, "mask_items"), int(g["num_items"]))
     topk, sums = check_vs_oracle(U, V, csr)
@@ -108,7 +108,7 @@ def test_trainer_evaluate_dataframe_interface():
     g = load_npz("mf_small.npz")
     tr = MFTrainer(cfg(), int(g["num_items"]), int(g["num_users"]))
     with torch.no_grad():
-        tr.model.user_embedding.weight.copy_(torch.from_numpy(g["eval_U"]))
+        tr.model.user_embedding.weight.copy_(torch.from_numpy(g["eval_U"].astype(np.float32)))
         tr.model.item_embedding.weight.copy_(torch.from_numpy(g["eval_V"]))
     uid = g["valid_eval_uid"]
     ev = pd.DataFrame({"pos_items": lists_from(g, "valid_eval", "pos_items"),

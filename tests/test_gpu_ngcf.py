@@ -43,12 +43,13 @@ def test_spmm_bit_exact_vs_oracle():
     for d in (32, 64, 128, 256):
         X = rng.standard_normal((1600, d)).astype(np.float32)
         Y0 = rng.standard_normal((1600, d)).astype(np.float32)
-        c = (csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(), csr.val.cpu().numpy())
-        y = ops.spmm_csr(csr.rowptr, csr.col, csr.val, torch.from_numpy(X).cuda())
+        assert csr.fwd.n_split_rows > 0 and not csr.symmetric        # long rows are cut into 128-nnz chunks
+        c = (csr.fwd.rowptr.cpu().numpy(), csr.fwd.col.cpu().numpy(), csr.fwd.val.cpu().numpy())
+        y = ops.spmm_csr(csr.fwd, torch.from_numpy(X).cuda())
         assert np.array_equal(y.cpu().numpy(), cport.spmm_csr(*c, X))
         ya = torch.from_numpy(Y0).cuda()
-        ops.spmm_csr(csr.rowptr_t, csr.col_t, csr.val_t, torch.from_numpy(X).cuda(), out=ya, accumulate=True)
-        ct = (csr.rowptr_t.cpu().numpy(), csr.col_t.cpu().numpy(), csr.val_t.cpu().numpy())
+        ops.spmm_csr(csr.bwd, torch.from_numpy(X).cuda(), out=ya, accumulate=True)
+        ct = (csr.bwd.rowptr.cpu().numpy(), csr.bwd.col.cpu().numpy(), csr.bwd.val.cpu().numpy())
         assert np.array_equal(ya.cpu().numpy(), cport.spmm_csr(*ct, X, Y0))
 
 

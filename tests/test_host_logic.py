@@ -66,12 +66,12 @@ def test_laplacian_csr_roundtrip_and_transpose():
     L = build_laplacian(inter.user, inter.item, inter.rating, 120, 90)
     csr = laplacian_to_csr(L, "cpu")
     dense = L.to_dense().numpy()
-    rp, ci, va = csr.rowptr.numpy(), csr.col.numpy(), csr.val.numpy()
+    rp, ci, va = csr.fwd.rowptr.numpy(), csr.fwd.col.numpy(), csr.fwd.val.numpy()
     rec = np.zeros_like(dense)
     for r in range(210):
         rec[r, ci[rp[r]:rp[r + 1]]] = va[rp[r]:rp[r + 1]]
     assert np.array_equal(rec, dense)
-    rpt, cit, vat = csr.rowptr_t.numpy(), csr.col_t.numpy(), csr.val_t.numpy()
+    rpt, cit, vat = csr.bwd.rowptr.numpy(), csr.bwd.col.numpy(), csr.bwd.val.numpy()
     rect = np.zeros_like(dense)
     for r in range(210):
         rect[r, cit[rpt[r]:rpt[r + 1]]] = vat[rpt[r]:rpt[r + 1]]

@@ -20,7 +20,7 @@ SYMBOLS = (
     "yr_version", "yr_device_sm_count",
     "yr_mf_score", "yr_mf_score_bwd", "yr_bpr_loss_fwd", "yr_bpr_loss_bwd",
     "yr_bpr_mf_train", "yr_bpr_mf_validate",
-    "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
+    "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
 )
@@ -48,6 +48,18 @@ class YrMfState(C.Structure):
                 ("nU", C.c_int64), ("nI", C.c_int64), ("d", C.c_int32)]
 
 
+YR_SPMM_CHUNK = 128
+
+
+class YrCsr(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64),
+                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
+                ("n_chunks", C.c_int32),
+                ("chunk_row", C.c_void_p), ("chunk_start", C.c_void_p), ("chunk_slot", C.c_void_p),
+                ("n_split_rows", C.c_int32),
+                ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p)]
+
+
 YR_NGCF_MAX_LAYERS = 7
 _PL = C.c_void_p * YR_NGCF_MAX_LAYERS
 _PL1 = C.c_void_p * (YR_NGCF_MAX_LAYERS + 1)
@@ -55,8 +67,7 @@ _PL1 = C.c_void_p * (YR_NGCF_MAX_LAYERS + 1)
 
 class YrNgcfState(C.Structure):
     _fields_ = [("nU", C.c_int64), ("nI", C.c_int64), ("d", C.c_int32), ("n_layers", C.c_int32),
-                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
-                ("rowptrT", C.c_void_p), ("colT", C.c_void_p), ("valT", C.c_void_p),
+                ("L", YrCsr), ("LT", YrCsr),
                 ("E", _PL1), ("LE", _PL), ("G", _PL1), ("T", C.c_void_p),
                 ("W1", _PL), ("W2", _PL), ("dW1", _PL), ("dW2", _PL),
                 ("mE", C.c_void_p), ("vE", C.c_void_p),
@@ -97,10 +108,12 @@ def load() -> C.CDLL:
         "yr_bpr_loss_bwd": (C.c_int, [p, p, i64, p, p, p, p]),
         "yr_bpr_mf_train": (C.c_int, [C.POINTER(YrMfState), C.POINTER(YrOpt), p, p, p, i64, i32, p, p, p]),
         "yr_bpr_mf_validate": (C.c_int, [p, p, i64, i64, i32, p, p, p, i64, i32, p, p, p, p]),
-        "yr_spmm_csr": (C.c_int, [p, p, p, i64, i32, p, p, i32, p]),
-        "yr_ngcf_layer_fwd": (C.c_int, [p, p, p, i64, i32, p, p, p, f32, p, p, p]),
+        "yr_spmm_plan_size_h": (C.c_int, [p, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "yr_spmm_plan_fill_h": (C.c_int, [p, i64, p, p, p, p, p]),
+        "yr_spmm_csr": (C.c_int, [C.POINTER(YrCsr), i32, p, p, i32, p]),
+        "yr_ngcf_layer_fwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, f32, p, p, p]),
         "yr_ngcf_layer_bwd_ws_bytes": (sz, [i32]),
-        "yr_ngcf_layer_bwd": (C.c_int, [p, p, p, i64, i32, p, p, p, p, p, p, f32, p, p, p, p, p, sz, p]),
+        "yr_ngcf_layer_bwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, p, p, p, f32, p, p, p, p, p, sz, p]),
         "yr_ngcf_tail": (C.c_int, [p, p, i32, i64, i64, i32, p, p, p, i64, p, p, p, p, p, p]),
         "yr_dense_opt_step": (C.c_int, [p, p, p, p, i64, C.POINTER(YrOpt), p]),
         "yr_ngcf_propagate": (C.c_int, [C.POINTER(YrNgcfState), f32, p]),

@@ -165,7 +165,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         // user row is gathered twice by the reference (pos call + neg call, Q2): g*p + (-g)*n
-        gu.x[j] = g * pr.x[j] - g * nr.x[j];
+        gu.x[j] = __fsub_rn(__fmul_rn(g, pr.x[j]), __fmul_rn(g, nr.x[j]));   // two rounded products, like autograd
         gp.x[j] = g * ur.x[j];
         gn.x[j] = -gp.x[j];
       }

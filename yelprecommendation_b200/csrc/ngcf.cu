@@ -10,58 +10,83 @@
 namespace yr {
 
 // ---------------------------------------------------------------------------------------------
-// CSR SpMM, warp per row, lanes across the embedding width, fma chain in CSR order.
+// CSR SpMM, one warp per CHUNK (<= YR_SPMM_CHUNK consecutive non-zeros of one row), lanes across the
+// embedding width, fma chain in CSR order inside the chunk. Whole-row chunks store (or accumulate into) Y
+// directly; chunks of split rows store a partial that spmm_fixup_kernel sums left to right.
+// Gathers of X rows are L2 hits at Yelp shape (X = 17.85 MB): 8 independent row loads are kept in flight.
 // ---------------------------------------------------------------------------------------------
 template <int VPL, bool ACC>
 __global__ void __launch_bounds__(256)
-spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                const float* __restrict__ val, int64_t n_rows, const float* __restrict__ X,
-                float* __restrict__ Y) {
+spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) {
   constexpr int D = VPL * 32;
   const int lane = threadIdx.x & 31;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += nwarps) {
-    const int s = rowptr[row], e = rowptr[row + 1];
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < A.n_chunks; c += nwarps) {
+    const int row = __ldg(A.chunk_row + c);
+    const int s = __ldg(A.chunk_start + c);
+    const int slot = __ldg(A.chunk_slot + c);
+    const int e = min(s + YR_SPMM_CHUNK, __ldg(A.rowptr + row + 1));
     Row<VPL> acc;
-    if constexpr (ACC) {
-      acc = ld_row<VPL>(Y + row * D, lane);
+    if (ACC && slot < 0) {
+      acc = ld_row<VPL>(Y + (int64_t)row * D, lane);
     } else {
 #pragma unroll
       for (int j = 0; j < VPL; ++j) acc.x[j] = 0.f;
     }
     for (int j0 = s; j0 < e; j0 += 32) {
       const int j = j0 + lane;
-      const int c = (j < e) ? __ldg(col + j) : 0;
-      const float a = (j < e) ? __ldg(val + j) : 0.f;
+      const int cc = (j < e) ? __ldg(A.col + j) : 0;
+      const float aa = (j < e) ? __ldg(A.val + j) : 0.f;
       const int cnt = min(32, e - j0);
       int t = 0;
-      for (; t + 4 <= cnt; t += 4) {
-        const int c0 = __shfl_sync(kFull, c, t), c1 = __shfl_sync(kFull, c, t + 1);
-        const int c2 = __shfl_sync(kFull, c, t + 2), c3 = __shfl_sync(kFull, c, t + 3);
-        const float a0 = __shfl_sync(kFull, a, t), a1 = __shfl_sync(kFull, a, t + 1);
-        const float a2 = __shfl_sync(kFull, a, t + 2), a3 = __shfl_sync(kFull, a, t + 3);
-        const Row<VPL> x0 = ld_row<VPL>(X + (int64_t)c0 * D, lane);
-        const Row<VPL> x1 = ld_row<VPL>(X + (int64_t)c1 * D, lane);
-        const Row<VPL> x2 = ld_row<VPL>(X + (int64_t)c2 * D, lane);
-        const Row<VPL> x3 = ld_row<VPL>(X + (int64_t)c3 * D, lane);
+      for (; t + 8 <= cnt; t += 8) {
+        Row<VPL> x[8];
+        float a[8];
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-          acc.x[q] = fmaf(a0, x0.x[q], acc.x[q]);
-          acc.x[q] = fmaf(a1, x1.x[q], acc.x[q]);
-          acc.x[q] = fmaf(a2, x2.x[q], acc.x[q]);
-          acc.x[q] = fmaf(a3, x3.x[q], acc.x[q]);
+        for (int q = 0; q < 8; ++q) {
+          const int cq = __shfl_sync(kFull, cc, t + q);
+          a[q] = __shfl_sync(kFull, aa, t + q);
+          x[q] = ld_row<VPL>(X + (int64_t)cq * D, lane);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) acc.x[v] = fmaf(a[q], x[q].x[v], acc.x[v]);
       }
       for (; t < cnt; ++t) {
-        const int c0 = __shfl_sync(kFull, c, t);
-        const float a0 = __shfl_sync(kFull, a, t);
+        const int c0 = __shfl_sync(kFull, cc, t);
+        const float a0 = __shfl_sync(kFull, aa, t);
         const Row<VPL> x0 = ld_row<VPL>(X + (int64_t)c0 * D, lane);
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) acc.x[q] = fmaf(a0, x0.x[q], acc.x[q]);
+        for (int v = 0; v < VPL; ++v) acc.x[v] = fmaf(a0, x0.x[v], acc.x[v]);
       }
     }
-    st_row<VPL>(Y + row * D, lane, acc);
+    if (slot < 0) st_row<VPL>(Y + (int64_t)row * D, lane, acc);
+    else st_row<VPL>(A.partials + (int64_t)slot * D, lane, acc);
   }
+}
+
+template <int VPL, bool ACC>
+__global__ void __launch_bounds__(256)
+spmm_fixup_kernel(yr_csr A, float* __restrict__ Y) {
+  constexpr int D = VPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= A.n_split_rows) return;
+  const int row = A.split_row[w];
+  const int p0 = A.split_ptr[w], p1 = A.split_ptr[w + 1];
+  Row<VPL> acc = ld_row<VPL>(A.partials + (int64_t)p0 * D, lane);
+  for (int p = p0 + 1; p < p1; ++p) {
+    const Row<VPL> x = ld_row<VPL>(A.partials + (int64_t)p * D, lane);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc.x[v] += x.x[v];
+  }
+  if (ACC) {
+    const Row<VPL> y = ld_row<VPL>(Y + (int64_t)row * D, lane);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc.x[v] = y.x[v] + acc.x[v];
+  }
+  st_row<VPL>(Y + (int64_t)row * D, lane, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,7 +359,7 @@ ngcf_tail_kernel(const float* const* __restrict__ E_layers, float* const* __rest
         Row<VPL> gu, gp, gn;
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
-          gu.x[j] = g * pr.x[j] - g * nr.x[j];
+          gu.x[j] = __fsub_rn(__fmul_rn(g, pr.x[j]), __fmul_rn(g, nr.x[j]));   // two rounded products, like autograd
           gp.x[j] = g * ur.x[j];
           gn.x[j] = -gp.x[j];
         }
@@ -409,19 +434,75 @@ constexpr int kBwdCtasPerSm = 2;
 
 using namespace yr;
 
-extern "C" int yr_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
-                           int d, const float* X, float* Y, int accumulate, yr_stream stream) {
-  if (!rowptr || !col || !val || !X || !Y || n_rows < 0) return YR_ERR_BAD_ARG;
-  if (n_rows == 0) return YR_OK;
+static int csr_ok(const yr_csr* A) {
+  if (!A || !A->rowptr || !A->col || !A->val || A->n_rows < 0 || A->n_chunks < 0) return YR_ERR_BAD_ARG;
+  if (A->n_chunks > 0 && (!A->chunk_row || !A->chunk_start || !A->chunk_slot)) return YR_ERR_BAD_ARG;
+  if (A->n_split_rows > 0 && (!A->split_row || !A->split_ptr || !A->partials)) return YR_ERR_BAD_ARG;
+  return YR_OK;
+}
+
+extern "C" int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chunks_h,
+                                   int32_t* n_split_rows_h, int32_t* n_partials_h) {
+  if (!rowptr_h || n_rows < 0 || !n_chunks_h || !n_split_rows_h || !n_partials_h) return YR_ERR_BAD_ARG;
+  int64_t chunks = 0, split = 0, parts = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    const int64_t c = len <= YR_SPMM_CHUNK ? 1 : (len + YR_SPMM_CHUNK - 1) / YR_SPMM_CHUNK;
+    chunks += c;
+    if (c > 1) { ++split; parts += c; }
+  }
+  if (chunks >= (1LL << 31)) return YR_ERR_BAD_DIM;
+  *n_chunks_h = (int32_t)chunks; *n_split_rows_h = (int32_t)split; *n_partials_h = (int32_t)parts;
+  return YR_OK;
+}
+
+// Long rows' chunks first (they are the longest work items), then one chunk per short row.
+extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_row_h,
+                                   int32_t* chunk_start_h, int32_t* chunk_slot_h, int32_t* split_row_h,
+                                   int32_t* split_ptr_h) {
+  if (!rowptr_h || n_rows < 0 || !chunk_row_h || !chunk_start_h || !chunk_slot_h || !split_ptr_h) return YR_ERR_BAD_ARG;
+  int64_t c = 0, sr = 0, slot = 0;
+  split_ptr_h[0] = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    if (len <= YR_SPMM_CHUNK) continue;
+    if (!split_row_h) return YR_ERR_BAD_ARG;
+    for (int64_t s = rowptr_h[r]; s < rowptr_h[r + 1]; s += YR_SPMM_CHUNK) {
+      chunk_row_h[c] = (int32_t)r; chunk_start_h[c] = (int32_t)s; chunk_slot_h[c] = (int32_t)slot;
+      ++c; ++slot;
+    }
+    split_row_h[sr] = (int32_t)r;
+    split_ptr_h[++sr] = (int32_t)slot;
+  }
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    if (len > YR_SPMM_CHUNK) continue;
+    chunk_row_h[c] = (int32_t)r; chunk_start_h[c] = rowptr_h[r]; chunk_slot_h[c] = -1;
+    ++c;
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream) {
+  int rc = csr_ok(A);
+  if (rc) return rc;
+  if (!X || !Y) return YR_ERR_BAD_ARG;
+  if (A->n_rows == 0 || A->n_chunks == 0) return YR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int threads = 256;
-  int64_t blocks = (n_rows * 32 + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count() * 8 * 4;
+  int64_t blocks = ((int64_t)A->n_chunks * 32 + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 8 * 8;
   if (blocks > cap) blocks = cap;
   const unsigned g = (unsigned)blocks;
-#define YR_SPMM(V)                                                                              \
-  if (accumulate) spmm_csr_kernel<V, true><<<g, threads, 0, s>>>(rowptr, col, val, n_rows, X, Y); \
-  else spmm_csr_kernel<V, false><<<g, threads, 0, s>>>(rowptr, col, val, n_rows, X, Y);
+  const unsigned gf = (unsigned)(((int64_t)A->n_split_rows * 32 + threads - 1) / threads);
+#define YR_SPMM(V)                                                                      \
+  if (accumulate) {                                                                     \
+    spmm_chunk_kernel<V, true><<<g, threads, 0, s>>>(*A, X, Y);                         \
+    if (gf) spmm_fixup_kernel<V, true><<<gf, threads, 0, s>>>(*A, Y);                   \
+  } else {                                                                              \
+    spmm_chunk_kernel<V, false><<<g, threads, 0, s>>>(*A, X, Y);                        \
+    if (gf) spmm_fixup_kernel<V, false><<<gf, threads, 0, s>>>(*A, Y);                  \
+  }
   switch (dim_vpl(d)) {
     case 1: YR_SPMM(1); break;
     case 2: YR_SPMM(2); break;
@@ -434,12 +515,12 @@ extern "C" int yr_spmm_csr(const int32_t* rowptr, const int32_t* col, const floa
   return YR_OK;
 }
 
-extern "C" int yr_ngcf_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n,
-                                 int d, const float* E, const float* W1, const float* W2, float slope,
-                                 float* E_next, float* LE_save, yr_stream stream) {
-  if (!rowptr || !col || !val || !E || !W1 || !W2 || !E_next || !LE_save || n <= 0) return YR_ERR_BAD_ARG;
+extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
+                                 float slope, float* E_next, float* LE_save, yr_stream stream) {
+  if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
   if (d != 64) return YR_ERR_BAD_DIM;
-  int rc = yr_spmm_csr(rowptr, col, val, n, d, E, LE_save, 0, stream);
+  const int64_t n = L->n_rows;
+  int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
   if (rc) return rc;
   using C = DenseCfg<64>;
   static bool attr_set = false;
@@ -461,16 +542,15 @@ extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
   return (size_t)sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
 }
 
-extern "C" int yr_ngcf_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT,
-                                 int64_t n, int d, const float* E, const float* LE, const float* E_next,
+extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
                                  const float* G_next, const float* W1, const float* W2, float slope,
                                  float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
                                  yr_stream stream) {
-  if (!rowptrT || !colT || !valT || !E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 ||
-      !dW2 || !ws || n <= 0)
+  if (!LT || !E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 || !dW2 || !ws || LT->n_rows <= 0)
     return YR_ERR_BAD_ARG;
   if (d != 64) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
+  const int64_t n = LT->n_rows;
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -488,7 +568,7 @@ extern "C" int yr_ngcf_layer_bwd(const int32_t* rowptrT, const int32_t* colT, co
   const int len = 2 * d * d;
   reduce_partials_kernel<<<(len + 255) / 256, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
   YR_CHECK_LAUNCH();
-  return yr_spmm_csr(rowptrT, colT, valT, n, d, T, G, 1, stream);
+  return yr_spmm_csr(LT, d, T, G, 1, stream);
 }
 
 extern "C" int yr_ngcf_tail(const float* const* E_layers, float* const* G_layers, int n_layers,
@@ -556,7 +636,7 @@ __global__ void concat_layers_kernel(const float* const* __restrict__ E_layers, 
 static int ngcf_state_ok(const yr_ngcf_state* st) {
   if (!st || st->n_layers < 1 || st->n_layers > YR_NGCF_MAX_LAYERS || st->nU <= 0 || st->nI <= 0)
     return YR_ERR_BAD_ARG;
-  if (!st->rowptr || !st->col || !st->val || !st->E[0]) return YR_ERR_BAD_ARG;
+  if (csr_ok(&st->L) || !st->E[0]) return YR_ERR_BAD_ARG;
   for (int l = 0; l < st->n_layers; ++l)
     if (!st->E[l + 1] || !st->LE[l] || !st->W1[l] || !st->W2[l]) return YR_ERR_BAD_ARG;
   return YR_OK;
@@ -565,9 +645,8 @@ static int ngcf_state_ok(const yr_ngcf_state* st) {
 extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream stream) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
-  const int64_t n = st->nU + st->nI;
   for (int l = 0; l < st->n_layers; ++l) {
-    rc = yr_ngcf_layer_fwd(st->rowptr, st->col, st->val, n, st->d, st->E[l], st->W1[l], st->W2[l], slope,
+    rc = yr_ngcf_layer_fwd(&st->L, st->d, st->E[l], st->W1[l], st->W2[l], slope,
                            st->E[l + 1], st->LE[l], stream);
     if (rc) return rc;
   }
@@ -579,7 +658,7 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
                                   float* step_loss, yr_stream stream) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
-  if (!opt || !uid || !pos || !neg || B <= 0 || !st->rowptrT || !st->colT || !st->valT || !st->T ||
+  if (!opt || !uid || !pos || !neg || B <= 0 || csr_ok(&st->LT) || !st->T ||
       !st->E_dev || !st->G_dev || !st->ws || !st->loss)
     return YR_ERR_BAD_ARG;
   if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
@@ -597,7 +676,7 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
   if (rc) return rc;
   for (int l = L - 1; l >= 0; --l) {
     if (!st->dW1[l] || !st->dW2[l]) return YR_ERR_BAD_ARG;
-    rc = yr_ngcf_layer_bwd(st->rowptrT, st->colT, st->valT, n, d, st->E[l], st->LE[l], st->E[l + 1],
+    rc = yr_ngcf_layer_bwd(&st->LT, d, st->E[l], st->LE[l], st->E[l + 1],
                            st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l], st->T, st->dW1[l], st->dW2[l],
                            st->ws, st->ws_bytes, stream);
     if (rc) return rc;

@@ -56,20 +56,58 @@ def coo_to_csr(rows: np.ndarray, cols: np.ndarray, vals: np.ndarray, n: int):
     return rowptr.astype(np.int32), cols.astype(np.int32), vals.astype(np.float32)
 
 
-@dataclass
-class LaplacianCSR:
-    n: int
-    rowptr: torch.Tensor
-    col: torch.Tensor
-    val: torch.Tensor
-    rowptr_t: torch.Tensor
-    col_t: torch.Tensor
-    val_t: torch.Tensor
-    symmetric: bool
+class CSRMatrix:
+    """Device CSR (int32 / fp32) + the SpMM load-balancing plan of include/yelprec_b200.h (yr_csr).
+    On CPU (tests of the host logic) the plan is still built, only the struct() call needs CUDA."""
+
+    def __init__(self, rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, device):
+        import ctypes as C
+        from .. import _cabi
+        lib = _cabi.load()
+        self.n_rows = int(rowptr.shape[0] - 1)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        nc, ns, npart = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _cabi.check(lib.yr_spmm_plan_size_h(rowptr.ctypes.data, self.n_rows, C.byref(nc), C.byref(ns), C.byref(npart)),
+                    "yr_spmm_plan_size_h")
+        self.n_chunks, self.n_split_rows, self.n_partials = nc.value, ns.value, npart.value
+        crow, cstart, cslot = (np.empty(max(nc.value, 1), np.int32) for _ in range(3))
+        srow, sptr = np.empty(max(ns.value, 1), np.int32), np.zeros(ns.value + 1, np.int32)
+        _cabi.check(lib.yr_spmm_plan_fill_h(rowptr.ctypes.data, self.n_rows, crow.ctypes.data, cstart.ctypes.data,
+                                            cslot.ctypes.data, srow.ctypes.data, sptr.ctypes.data), "yr_spmm_plan_fill_h")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.device = torch.device(device)
+        self.rowptr, self.col, self.val = t(rowptr), t(col.astype(np.int32)), t(val.astype(np.float32))
+        self.chunk_row, self.chunk_start, self.chunk_slot = t(crow), t(cstart), t(cslot)
+        self.split_row, self.split_ptr = t(srow), t(sptr)
+        self._partials = {}
 
     @property
     def nnz(self) -> int:
         return int(self.col.numel())
+
+    def struct(self, d: int):
+        """yr_csr for embedding width d (allocates the partials scratch for that width once)."""
+        from .. import _cabi
+        part = self._partials.get(d)
+        if part is None:
+            part = torch.empty(max(self.n_partials, 1) * d, device=self.device, dtype=torch.float32)
+            self._partials[d] = part
+        p = _cabi.dptr
+        return _cabi.YrCsr(self.n_rows, self.nnz, p(self.rowptr), p(self.col), p(self.val), self.n_chunks,
+                           p(self.chunk_row), p(self.chunk_start), p(self.chunk_slot), self.n_split_rows,
+                           p(self.split_row), p(self.split_ptr), p(part))
+
+
+@dataclass
+class LaplacianCSR:
+    n: int
+    fwd: CSRMatrix          # L
+    bwd: CSRMatrix          # L^T (the same object when L is bit-wise symmetric, e.g. binary ratings)
+    symmetric: bool
+
+    @property
+    def nnz(self) -> int:
+        return self.fwd.nnz
 
 
 def laplacian_to_csr(L: torch.Tensor, device) -> LaplacianCSR:
@@ -81,11 +119,9 @@ def laplacian_to_csr(L: torch.Tensor, device) -> LaplacianCSR:
     rp, ci, va = coo_to_csr(idx[0], idx[1], val, n)
     rpt, cit, vat = coo_to_csr(idx[1], idx[0], val, n)
     sym = bool(np.array_equal(rp, rpt) and np.array_equal(ci, cit) and np.array_equal(va, vat))
-    t = lambda a: torch.from_numpy(a).to(device)
-    if sym:
-        a, b, c = t(rp), t(ci), t(va)
-        return LaplacianCSR(n, a, b, c, a, b, c, True)
-    return LaplacianCSR(n, t(rp), t(ci), t(va), t(rpt), t(cit), t(vat), False)
+    fwd = CSRMatrix(rp, ci, va, device)
+    bwd = fwd if sym else CSRMatrix(rpt, cit, vat, device)
+    return LaplacianCSR(n, fwd, bwd, sym)
 
 
 @dataclass

@@ -221,9 +221,9 @@ def planted_embeddings(inter: Interactions, d=64, seed=7, noise=0.05):
     top-10 lists recover planted preferences and the eval metrics are non-zero."""
     rng = np.random.default_rng(seed)
     C = inter.cluster_item_logit.shape[0]
-    code = rng.standard_normal((C, d)).astype(np.float32) / np.sqrt(d)
+    code = rng.standard_normal((C, d)).astype(np.float32) / np.float32(np.sqrt(d))
     U = code[inter.user_cluster] + noise * rng.standard_normal((inter.num_users, d)).astype(np.float32)
     logit = inter.cluster_item_logit - inter.cluster_item_logit.mean(axis=0, keepdims=True)
     V = (np.linalg.pinv(code.astype(np.float64)) @ logit.astype(np.float64)).T.astype(np.float32)
     V += noise * rng.standard_normal(V.shape).astype(np.float32)
-    return np.ascontiguousarray(U), np.ascontiguousarray(V)
+    return np.ascontiguousarray(U, dtype=np.float32), np.ascontiguousarray(V, dtype=np.float32)

@@ -99,24 +99,27 @@ def bpr_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------
 # SpMM / NGCF layer (autograd-capable)
 # ----------------------------------------------------------------------------------------------------
-def spmm_csr(rowptr, col, val, X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False):
+def spmm_csr(A, X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False):
+    """A: data.graph.CSRMatrix. Returns A @ X (or out += A @ X)."""
     lib = _cabi.load()
     X = X.contiguous()
     if out is None:
         out = torch.empty_like(X)
         accumulate = False
-    check(lib.yr_spmm_csr(dptr(rowptr, I32), dptr(col, I32), dptr(val, F32), X.shape[0], X.shape[1], dptr(X, F32),
-                          dptr(out, F32), 1 if accumulate else 0, stream_ptr(X.device)), "yr_spmm_csr")
+    st = A.struct(X.shape[1])
+    check(lib.yr_spmm_csr(C.byref(st), X.shape[1], dptr(X, F32), dptr(out, F32), 1 if accumulate else 0,
+                          stream_ptr(X.device)), "yr_spmm_csr")
     return out
 
 
 def ngcf_layer_fwd(csr, E, W1, W2, slope=0.01):
+    """csr: data.graph.LaplacianCSR."""
     lib = _cabi.load()
     E, W1, W2 = E.contiguous(), W1.contiguous(), W2.contiguous()
     En, LE = torch.empty_like(E), torch.empty_like(E)
-    check(lib.yr_ngcf_layer_fwd(dptr(csr.rowptr, I32), dptr(csr.col, I32), dptr(csr.val, F32), E.shape[0], E.shape[1],
-                                dptr(E, F32), dptr(W1, F32), dptr(W2, F32), float(slope), dptr(En), dptr(LE),
-                                stream_ptr(E.device)), "yr_ngcf_layer_fwd")
+    st = csr.fwd.struct(E.shape[1])
+    check(lib.yr_ngcf_layer_fwd(C.byref(st), E.shape[1], dptr(E, F32), dptr(W1, F32), dptr(W2, F32), float(slope),
+                                dptr(En), dptr(LE), stream_ptr(E.device)), "yr_ngcf_layer_fwd")
     return En, LE
 
 
@@ -128,11 +131,11 @@ def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01):
     dW1, dW2 = torch.empty_like(W1), torch.empty_like(W2)
     nbytes = lib.yr_ngcf_layer_bwd_ws_bytes(d)
     ws = torch.empty(nbytes, device=E.device, dtype=torch.uint8)
-    check(lib.yr_ngcf_layer_bwd(dptr(csr.rowptr_t, I32), dptr(csr.col_t, I32), dptr(csr.val_t, F32), E.shape[0], d,
-                                dptr(E.contiguous(), F32), dptr(LE, F32), dptr(En, F32), dptr(Gn.contiguous(), F32),
-                                dptr(W1.contiguous(), F32), dptr(W2.contiguous(), F32), float(slope), dptr(G, F32),
-                                dptr(T), dptr(dW1), dptr(dW2), dptr(ws), nbytes, stream_ptr(E.device)),
-          "yr_ngcf_layer_bwd")
+    st = csr.bwd.struct(d)
+    check(lib.yr_ngcf_layer_bwd(C.byref(st), d, dptr(E.contiguous(), F32), dptr(LE, F32), dptr(En, F32),
+                                dptr(Gn.contiguous(), F32), dptr(W1.contiguous(), F32), dptr(W2.contiguous(), F32),
+                                float(slope), dptr(G, F32), dptr(T), dptr(dW1), dptr(dW2), dptr(ws), nbytes,
+                                stream_ptr(E.device)), "yr_ngcf_layer_bwd")
     return dW1, dW2
 
 

@@ -76,8 +76,7 @@ class NGCFTrainer(BaseTrainer):
         st = _cabi.YrNgcfState()
         st.nU, st.nI, st.d, st.n_layers = self.num_users, self.num_items, d, L
         p = _cabi.dptr
-        st.rowptr, st.col, st.val = p(csr.rowptr, I32), p(csr.col, I32), p(csr.val, F32)
-        st.rowptrT, st.colT, st.valT = p(csr.rowptr_t, I32), p(csr.col_t, I32), p(csr.val_t, F32)
+        st.L, st.LT = csr.fwd.struct(d), csr.bwd.struct(d)
         st.E[0] = p(E0, F32)
         st.G[0] = p(b["G"][0])
         for l in range(L):
