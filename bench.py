@@ -215,6 +215,24 @@ def main():
             return float(t.item())
         return ms
 
+    if args.only == "eval":      # profiling aid: K fused evaluations of the planted MF tables, nothing else
+        decsr = ops.DeviceEvalCSR(w.ecsr, dev, 10)
+        Up, Vp = syn.planted_embeddings(w.inter)
+        Ud, Vd = torch.from_numpy(Up).to(dev), torch.from_numpy(Vp).to(dev)
+        Vt, _ = ops.transpose_items(Vd)
+        for _ in range(W):
+            ops.eval_topk_metrics(Ud, Vd, decsr, Vt)
+        ms = timed(lambda i: ops.eval_topk_metrics(Ud, Vd, decsr, Vt), K)
+        print(f"eval only: {ms / K:.3f} ms/eval  {w.ecsr.n_eval / (ms / K * 1e-3):.0f} users/s", flush=True)
+        return 0
+    if args.only == "mf":        # profiling aid: one persistent launch of K SGD steps
+        torch.manual_seed(42)
+        mtr = MFTrainer(cfg(optimizer=os.environ.get("YR_BENCH_MF_OPT", "sgd")), w.inter.num_items, w.inter.num_users)
+        mtr.train_on_device(du[: B * W], dp[: B * W], dn[: B * W], B)
+        ms = timed(lambda i: mtr.train_on_device(du[: B * K], dp[: B * K], dn[: B * K], B), 1)
+        print(f"mf only: {1e3 * ms / K:.2f} us/step", flush=True)
+        return 0
+
     # ------------------------------------------------------------------ NGCF training (headline)
     torch.manual_seed(42)
     ntr = NGCFTrainer(cfg(), w.inter.num_items, w.inter.num_users, w.L)
