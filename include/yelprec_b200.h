@@ -121,9 +121,8 @@ typedef struct yr_csr {
   const int32_t *rowptr, *col;
   const float* val;
   int32_t n_chunks;               /* work items: one per short row, ceil(len/CHUNK) per long row */
-  const int32_t *chunk_row;       /* [n_chunks] row of the chunk */
-  const int32_t *chunk_start;     /* [n_chunks] first non-zero of the chunk */
-  const int32_t *chunk_slot;      /* [n_chunks] -1 = whole row (direct store), else slot in `partials` */
+  const int32_t *chunk_desc;      /* [n_chunks x 4], 16-byte aligned: {row, first non-zero, length,
+                                     slot} — slot -1 = whole row (direct store), else index into `partials` */
   int32_t n_split_rows;           /* rows that were cut */
   const int32_t *split_row;       /* [n_split_rows] */
   const int32_t *split_ptr;       /* [n_split_rows+1] range of partial slots of each split row */
@@ -133,8 +132,8 @@ typedef struct yr_csr {
 /* Host-side plan builder (host pointers). Call _size_h first, allocate, then _fill_h. */
 int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chunks_h, int32_t* n_split_rows_h,
                         int32_t* n_partials_h);
-int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_row_h, int32_t* chunk_start_h,
-                        int32_t* chunk_slot_h, int32_t* split_row_h, int32_t* split_ptr_h);
+int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_desc_h, int32_t* split_row_h,
+                        int32_t* split_ptr_h);
 
 /* Y = A X (accumulate == 0) or Y += A X (accumulate != 0), X/Y row-major [n_rows x d].
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */

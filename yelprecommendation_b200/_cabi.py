@@ -55,7 +55,7 @@ class YrCsr(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("n_chunks", C.c_int32),
-                ("chunk_row", C.c_void_p), ("chunk_start", C.c_void_p), ("chunk_slot", C.c_void_p),
+                ("chunk_desc", C.c_void_p),
                 ("n_split_rows", C.c_int32),
                 ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p)]
 
@@ -109,7 +109,7 @@ def load() -> C.CDLL:
         "yr_bpr_mf_train": (C.c_int, [C.POINTER(YrMfState), C.POINTER(YrOpt), p, p, p, i64, i32, p, p, p]),
         "yr_bpr_mf_validate": (C.c_int, [p, p, i64, i64, i32, p, p, p, i64, i32, p, p, p, p]),
         "yr_spmm_plan_size_h": (C.c_int, [p, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
-        "yr_spmm_plan_fill_h": (C.c_int, [p, i64, p, p, p, p, p]),
+        "yr_spmm_plan_fill_h": (C.c_int, [p, i64, p, p, p]),
         "yr_spmm_csr": (C.c_int, [C.POINTER(YrCsr), i32, p, p, i32, p]),
         "yr_ngcf_layer_fwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, f32, p, p, p]),
         "yr_ngcf_layer_bwd_ws_bytes": (sz, [i32]),

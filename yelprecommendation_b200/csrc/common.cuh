@@ -150,6 +150,24 @@ __device__ __forceinline__ void opt_update(const OptScalars& s, float& p, float 
   p = p + (-s.step_size * m) / denom;                 // param.addcdiv_(m, denom, value=-step_size)
 }
 
+inline int yr_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+inline int yr_csr_ok(const yr_csr* A) {
+  if (!A || !A->rowptr || !A->col || !A->val || A->n_rows < 0 || A->n_chunks < 0) return YR_ERR_BAD_ARG;
+  if (A->n_chunks > 0 && !A->chunk_desc) return YR_ERR_BAD_ARG;
+  if (A->n_split_rows > 0 && (!A->split_row || !A->split_ptr || !A->partials)) return YR_ERR_BAD_ARG;
+  return YR_OK;
+}
+
 inline int dim_vpl(int d) {
   switch (d) { case 32: return 1; case 64: return 2; case 128: return 4; case 256: return 8; default: return 0; }
 }

@@ -380,16 +380,6 @@ __global__ void transpose_items_kernel(const float* __restrict__ V, int64_t nI, 
   }
 }
 
-static int eval_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
 
 }  // namespace yr
 
@@ -435,7 +425,7 @@ extern "C" int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* 
     if (smem > 227 * 1024) return YR_ERR_BAD_DIM;
     YR_CUDA(cudaFuncSetAttribute(eval_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_utiles = (n_eval + kTU - 1) / kTU;
-    int64_t grid = eval_sm_count();
+    int64_t grid = yr_sm_count();
     if (grid > n_utiles) grid = n_utiles;
     eval_topk_kernel<<<(unsigned)grid, kEvalThreads, smem, s>>>(
         Uemb, nU, Vt, ldt, nI, d, d_pad, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq,

@@ -1,5 +1,5 @@
 // NGCF propagation kernels (sm_100a).
-//   yr_spmm_csr          — torch.sparse.mm(L, E) (reference models/ngcf.py:64,67)
+//   (the CSR SpMM lives in spmm.cu)
 //   yr_ngcf_layer_fwd    — NGCF.embedding_propagation (reference models/ngcf.py:60-72)
 //   yr_ngcf_layer_bwd    — its gradient (autograd through the two SpMMs / two Linear layers)
 //   yr_ngcf_tail         — gather/concat/dot tail of bpr_forward + BPRLoss and its scatter backward
@@ -8,86 +8,6 @@
 #include "common.cuh"
 
 namespace yr {
-
-// ---------------------------------------------------------------------------------------------
-// CSR SpMM, one warp per CHUNK (<= YR_SPMM_CHUNK consecutive non-zeros of one row), lanes across the
-// embedding width, fma chain in CSR order inside the chunk. Whole-row chunks store (or accumulate into) Y
-// directly; chunks of split rows store a partial that spmm_fixup_kernel sums left to right.
-// Gathers of X rows are L2 hits at Yelp shape (X = 17.85 MB): 8 independent row loads are kept in flight.
-// ---------------------------------------------------------------------------------------------
-template <int VPL, bool ACC>
-__global__ void __launch_bounds__(256)
-spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) {
-  constexpr int D = VPL * 32;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < A.n_chunks; c += nwarps) {
-    const int row = __ldg(A.chunk_row + c);
-    const int s = __ldg(A.chunk_start + c);
-    const int slot = __ldg(A.chunk_slot + c);
-    const int e = min(s + YR_SPMM_CHUNK, __ldg(A.rowptr + row + 1));
-    Row<VPL> acc;
-    if (ACC && slot < 0) {
-      acc = ld_row<VPL>(Y + (int64_t)row * D, lane);
-    } else {
-#pragma unroll
-      for (int j = 0; j < VPL; ++j) acc.x[j] = 0.f;
-    }
-    for (int j0 = s; j0 < e; j0 += 32) {
-      const int j = j0 + lane;
-      const int cc = (j < e) ? __ldg(A.col + j) : 0;
-      const float aa = (j < e) ? __ldg(A.val + j) : 0.f;
-      const int cnt = min(32, e - j0);
-      int t = 0;
-      for (; t + 8 <= cnt; t += 8) {
-        Row<VPL> x[8];
-        float a[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int cq = __shfl_sync(kFull, cc, t + q);
-          a[q] = __shfl_sync(kFull, aa, t + q);
-          x[q] = ld_row<VPL>(X + (int64_t)cq * D, lane);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) acc.x[v] = fmaf(a[q], x[q].x[v], acc.x[v]);
-      }
-      for (; t < cnt; ++t) {
-        const int c0 = __shfl_sync(kFull, cc, t);
-        const float a0 = __shfl_sync(kFull, aa, t);
-        const Row<VPL> x0 = ld_row<VPL>(X + (int64_t)c0 * D, lane);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) acc.x[v] = fmaf(a0, x0.x[v], acc.x[v]);
-      }
-    }
-    if (slot < 0) st_row<VPL>(Y + (int64_t)row * D, lane, acc);
-    else st_row<VPL>(A.partials + (int64_t)slot * D, lane, acc);
-  }
-}
-
-template <int VPL, bool ACC>
-__global__ void __launch_bounds__(256)
-spmm_fixup_kernel(yr_csr A, float* __restrict__ Y) {
-  constexpr int D = VPL * 32;
-  const int lane = threadIdx.x & 31;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= A.n_split_rows) return;
-  const int row = A.split_row[w];
-  const int p0 = A.split_ptr[w], p1 = A.split_ptr[w + 1];
-  Row<VPL> acc = ld_row<VPL>(A.partials + (int64_t)p0 * D, lane);
-  for (int p = p0 + 1; p < p1; ++p) {
-    const Row<VPL> x = ld_row<VPL>(A.partials + (int64_t)p * D, lane);
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) acc.x[v] += x.x[v];
-  }
-  if (ACC) {
-    const Row<VPL> y = ld_row<VPL>(Y + (int64_t)row * D, lane);
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) acc.x[v] = y.x[v] + acc.x[v];
-  }
-  st_row<VPL>(Y + (int64_t)row * D, lane, acc);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Dense part of one layer, forward: out = leaky( [LE+E | E*LE] . [W1^T ; W2^T] ).
@@ -299,13 +219,34 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
 }
 
 // dW[idx] = sum over CTA partials in CTA order (deterministic).
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, int n_parts, int len,
-                                       float* __restrict__ out1, float* __restrict__ out2, int half) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= len) return;
+// Block = 32 outputs x 8 partial-groups: group g sums partials g, g+8, ... (8 loads in flight), then the 8 group
+// sums are added in group order.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ ws, int n_parts, int len,
+                       float* __restrict__ out1, float* __restrict__ out2, int half) {
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int p = 0; p < n_parts; ++p) acc += ws[(size_t)p * len + idx];
-  if (idx < half) out1[idx] = acc; else out2[idx - half] = acc;
+  if (idx < len) {
+    int p = grp;
+    for (; p + 56 < n_parts; p += 64) {
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = ws[(size_t)(p + 8 * q) * len + idx];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += x[q];
+    }
+    for (; p < n_parts; p += 8) acc += ws[(size_t)p * len + idx];
+  }
+  sh[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && idx < len) {
+    float t = sh[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) t += sh[g][lane];
+    if (idx < half) out1[idx] = t; else out2[idx - half] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -417,103 +358,11 @@ dense_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
-
 constexpr int kBwdCtasPerSm = 2;
 
 }  // namespace yr
 
 using namespace yr;
-
-static int csr_ok(const yr_csr* A) {
-  if (!A || !A->rowptr || !A->col || !A->val || A->n_rows < 0 || A->n_chunks < 0) return YR_ERR_BAD_ARG;
-  if (A->n_chunks > 0 && (!A->chunk_row || !A->chunk_start || !A->chunk_slot)) return YR_ERR_BAD_ARG;
-  if (A->n_split_rows > 0 && (!A->split_row || !A->split_ptr || !A->partials)) return YR_ERR_BAD_ARG;
-  return YR_OK;
-}
-
-extern "C" int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chunks_h,
-                                   int32_t* n_split_rows_h, int32_t* n_partials_h) {
-  if (!rowptr_h || n_rows < 0 || !n_chunks_h || !n_split_rows_h || !n_partials_h) return YR_ERR_BAD_ARG;
-  int64_t chunks = 0, split = 0, parts = 0;
-  for (int64_t r = 0; r < n_rows; ++r) {
-    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
-    const int64_t c = len <= YR_SPMM_CHUNK ? 1 : (len + YR_SPMM_CHUNK - 1) / YR_SPMM_CHUNK;
-    chunks += c;
-    if (c > 1) { ++split; parts += c; }
-  }
-  if (chunks >= (1LL << 31)) return YR_ERR_BAD_DIM;
-  *n_chunks_h = (int32_t)chunks; *n_split_rows_h = (int32_t)split; *n_partials_h = (int32_t)parts;
-  return YR_OK;
-}
-
-// Long rows' chunks first (they are the longest work items), then one chunk per short row.
-extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_row_h,
-                                   int32_t* chunk_start_h, int32_t* chunk_slot_h, int32_t* split_row_h,
-                                   int32_t* split_ptr_h) {
-  if (!rowptr_h || n_rows < 0 || !chunk_row_h || !chunk_start_h || !chunk_slot_h || !split_ptr_h) return YR_ERR_BAD_ARG;
-  int64_t c = 0, sr = 0, slot = 0;
-  split_ptr_h[0] = 0;
-  for (int64_t r = 0; r < n_rows; ++r) {
-    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
-    if (len <= YR_SPMM_CHUNK) continue;
-    if (!split_row_h) return YR_ERR_BAD_ARG;
-    for (int64_t s = rowptr_h[r]; s < rowptr_h[r + 1]; s += YR_SPMM_CHUNK) {
-      chunk_row_h[c] = (int32_t)r; chunk_start_h[c] = (int32_t)s; chunk_slot_h[c] = (int32_t)slot;
-      ++c; ++slot;
-    }
-    split_row_h[sr] = (int32_t)r;
-    split_ptr_h[++sr] = (int32_t)slot;
-  }
-  for (int64_t r = 0; r < n_rows; ++r) {
-    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
-    if (len > YR_SPMM_CHUNK) continue;
-    chunk_row_h[c] = (int32_t)r; chunk_start_h[c] = rowptr_h[r]; chunk_slot_h[c] = -1;
-    ++c;
-  }
-  return YR_OK;
-}
-
-extern "C" int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream) {
-  int rc = csr_ok(A);
-  if (rc) return rc;
-  if (!X || !Y) return YR_ERR_BAD_ARG;
-  if (A->n_rows == 0 || A->n_chunks == 0) return YR_OK;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int threads = 256;
-  int64_t blocks = ((int64_t)A->n_chunks * 32 + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count() * 8 * 8;
-  if (blocks > cap) blocks = cap;
-  const unsigned g = (unsigned)blocks;
-  const unsigned gf = (unsigned)(((int64_t)A->n_split_rows * 32 + threads - 1) / threads);
-#define YR_SPMM(V)                                                                      \
-  if (accumulate) {                                                                     \
-    spmm_chunk_kernel<V, true><<<g, threads, 0, s>>>(*A, X, Y);                         \
-    if (gf) spmm_fixup_kernel<V, true><<<gf, threads, 0, s>>>(*A, Y);                   \
-  } else {                                                                              \
-    spmm_chunk_kernel<V, false><<<g, threads, 0, s>>>(*A, X, Y);                        \
-    if (gf) spmm_fixup_kernel<V, false><<<gf, threads, 0, s>>>(*A, Y);                  \
-  }
-  switch (dim_vpl(d)) {
-    case 1: YR_SPMM(1); break;
-    case 2: YR_SPMM(2); break;
-    case 4: YR_SPMM(4); break;
-    case 8: YR_SPMM(8); break;
-    default: return YR_ERR_BAD_DIM;
-  }
-#undef YR_SPMM
-  YR_CHECK_LAUNCH();
-  return YR_OK;
-}
 
 extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
                                  float slope, float* E_next, float* LE_save, yr_stream stream) {
@@ -530,7 +379,7 @@ extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const f
     attr_set = true;
   }
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
-  int64_t grid = (int64_t)sm_count() * 3;
+  int64_t grid = (int64_t)yr_sm_count() * 3;
   if (grid > n_tiles) grid = n_tiles;
   ngcf_dense_fwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemFwd, (cudaStream_t)stream>>>(
       E, LE_save, W1, W2, slope, n, E_next);
@@ -539,7 +388,7 @@ extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const f
 }
 
 extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
-  return (size_t)sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
+  return (size_t)yr_sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
 }
 
 extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
@@ -560,13 +409,13 @@ extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const 
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
-  int64_t grid = (int64_t)sm_count() * kBwdCtasPerSm;
+  int64_t grid = (int64_t)yr_sm_count() * kBwdCtasPerSm;
   if (grid > n_tiles) grid = n_tiles;
   ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
       E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws);
   YR_CHECK_LAUNCH();
   const int len = 2 * d * d;
-  reduce_partials_kernel<<<(len + 255) / 256, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
+  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
   YR_CHECK_LAUNCH();
   return yr_spmm_csr(LT, d, T, G, 1, stream);
 }
@@ -582,7 +431,7 @@ extern "C" int yr_ngcf_tail(const float* const* E_layers, float* const* G_layers
   cudaStream_t s = (cudaStream_t)stream;
   const int threads = 256;
   int64_t blocks = (B * 32 + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)yr_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   const unsigned g = (unsigned)blocks;
   double* acc = loss_sum + 1;
@@ -608,7 +457,7 @@ extern "C" int yr_dense_opt_step(float* p, const float* g, float* m, float* v, i
   const int threads = 256;
   int64_t blocks = ((n >> 2) + threads - 1) / threads;
   if (blocks < 1) blocks = 1;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)yr_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   dense_opt_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, *opt);
   YR_CHECK_LAUNCH();
@@ -636,7 +485,7 @@ __global__ void concat_layers_kernel(const float* const* __restrict__ E_layers, 
 static int ngcf_state_ok(const yr_ngcf_state* st) {
   if (!st || st->n_layers < 1 || st->n_layers > YR_NGCF_MAX_LAYERS || st->nU <= 0 || st->nI <= 0)
     return YR_ERR_BAD_ARG;
-  if (csr_ok(&st->L) || !st->E[0]) return YR_ERR_BAD_ARG;
+  if (yr_csr_ok(&st->L) || !st->E[0]) return YR_ERR_BAD_ARG;
   for (int l = 0; l < st->n_layers; ++l)
     if (!st->E[l + 1] || !st->LE[l] || !st->W1[l] || !st->W2[l]) return YR_ERR_BAD_ARG;
   return YR_OK;
@@ -658,7 +507,7 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
                                   float* step_loss, yr_stream stream) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
-  if (!opt || !uid || !pos || !neg || B <= 0 || csr_ok(&st->LT) || !st->T ||
+  if (!opt || !uid || !pos || !neg || B <= 0 || yr_csr_ok(&st->LT) || !st->T ||
       !st->E_dev || !st->G_dev || !st->ws || !st->loss)
     return YR_ERR_BAD_ARG;
   if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;

@@ -1,0 +1,223 @@
+// CSR SpMM for the NGCF propagation (sm_100a): Y = A X / Y += A X, replacing torch.sparse.mm(L, E)
+// (reference models/ngcf.py:64,67) and its transpose in the backward pass.
+//
+// Work decomposition (yr_csr plan): one CHUNK = <= YR_SPMM_CHUNK consecutive non-zeros of one row. A group of
+// LPR = d/4 lanes owns a chunk (d = 64: half a warp, two chunks per warp), every lane carries one float4 of the
+// row, so a neighbour row is ONE 256-byte request per group and 8 of them are kept in flight per group. Chunk
+// descriptors are one 16-byte load. fma chain in CSR order inside a chunk; chunks of split rows store a partial
+// that spmm_fixup_kernel adds left to right (the oracle restates exactly this order -> bit-exact).
+//
+// At Yelp shape X (17.85 MB) is L2-resident; the 3.12 M gathered rows are 800 MB of L2->SM traffic per SpMM
+// against 61 MB of algorithmic HBM traffic, so this kernel lives on L2 latency / bandwidth, not on HBM.
+#include "common.cuh"
+
+namespace yr {
+
+template <int D> struct SpmmCfg {
+  static constexpr int kVec = D / 4;                       // float4 per row
+  static constexpr int LPR = kVec >= 32 ? 32 : kVec;       // lanes per row (group width)
+  static constexpr int VPT = kVec / LPR;                   // float4 per lane
+  static constexpr int CPW = 32 / LPR;                     // chunks per warp
+};
+
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
+  acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y);
+  acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+}
+
+template <int D, bool ACC>
+__global__ void __launch_bounds__(256, D <= 64 ? 3 : 2)
+spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) {
+  using C = SpmmCfg<D>;
+  constexpr int LPR = C::LPR, VPT = C::VPT, CPW = C::CPW;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int4* __restrict__ desc = reinterpret_cast<const int4*>(A.chunk_desc);
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+
+  for (int cb = gwarp * CPW; cb < A.n_chunks; cb += nwarps * CPW) {
+    const int c = cb + sub;
+    int4 dsc = make_int4(0, 0, 0, -1);
+    if (c < A.n_chunks) dsc = __ldg(desc + c);
+    const int row = dsc.x, s = dsc.y, len = dsc.z, slot = dsc.w;
+    float4 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ACC && slot < 0 && len >= 0 && c < A.n_chunks) {
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) acc[v] = reinterpret_cast<const float4*>(Y + (int64_t)row * D)[sl * VPT + v];
+    }
+    int maxlen = len;
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, o));
+    for (int j0 = 0; j0 < maxlen; j0 += LPR) {
+      const int j = j0 + sl;
+      const int cc = (j < len) ? __ldg(A.col + s + j) : -1;
+      const float aa = (j < len) ? __ldg(A.val + s + j) : 0.f;
+#pragma unroll
+      for (int t = 0; t < LPR; t += 8) {
+        if (j0 + t >= maxlen) break;
+        float4 x[8][VPT];
+        float a[8];
+        int cq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          cq[q] = __shfl_sync(kFull, cc, t + q, LPR);
+          a[q] = __shfl_sync(kFull, aa, t + q, LPR);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (cq[q] >= 0) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) x[q][v] = __ldg(X4 + (int64_t)cq[q] * C::kVec + sl * VPT + v);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (cq[q] >= 0) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) fma4(acc[v], a[q], x[q][v]);
+          }
+        }
+      }
+    }
+    if (c < A.n_chunks) {
+      float4* dst = (slot < 0) ? reinterpret_cast<float4*>(Y + (int64_t)row * D)
+                               : reinterpret_cast<float4*>(A.partials + (int64_t)slot * D);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) dst[sl * VPT + v] = acc[v];
+    }
+  }
+}
+
+// One lane group per split row: sum the chunk partials left to right (8 loads in flight), add Y_old if accumulating.
+template <int D, bool ACC>
+__global__ void __launch_bounds__(256)
+spmm_fixup_kernel(yr_csr A, float* __restrict__ Y) {
+  using C = SpmmCfg<D>;
+  constexpr int LPR = C::LPR, VPT = C::VPT, CPW = C::CPW;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int w = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * CPW + sub;
+  if (w >= A.n_split_rows) return;
+  const int row = A.split_row[w];
+  const int p0 = A.split_ptr[w], p1 = A.split_ptr[w + 1];
+  const float4* __restrict__ P4 = reinterpret_cast<const float4*>(A.partials);
+  float4 acc[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) acc[v] = P4[(int64_t)p0 * C::kVec + sl * VPT + v];
+  int p = p0 + 1;
+  for (; p + 8 <= p1; p += 8) {
+    float4 x[8][VPT];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) x[q][v] = P4[(int64_t)(p + q) * C::kVec + sl * VPT + v];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        acc[v].x += x[q][v].x; acc[v].y += x[q][v].y; acc[v].z += x[q][v].z; acc[v].w += x[q][v].w;
+      }
+  }
+  for (; p < p1; ++p) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const float4 x = P4[(int64_t)p * C::kVec + sl * VPT + v];
+      acc[v].x += x.x; acc[v].y += x.y; acc[v].z += x.z; acc[v].w += x.w;
+    }
+  }
+  float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D);
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    if (ACC) {
+      const float4 y = y4[sl * VPT + v];
+      acc[v].x = y.x + acc[v].x; acc[v].y = y.y + acc[v].y; acc[v].z = y.z + acc[v].z; acc[v].w = y.w + acc[v].w;
+    }
+    y4[sl * VPT + v] = acc[v];
+  }
+}
+
+template <int D>
+static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s) {
+  using C = SpmmCfg<D>;
+  const int threads = 256, wpb = threads / 32;
+  int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
+  const int64_t cap = (int64_t)yr_sm_count() * 8 * 16;
+  if (blocks > cap) blocks = cap;
+  const int64_t fb = ((int64_t)A->n_split_rows + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
+  if (accumulate) {
+    spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
+    if (fb) spmm_fixup_kernel<D, true><<<(unsigned)fb, threads, 0, s>>>(*A, Y);
+  } else {
+    spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
+    if (fb) spmm_fixup_kernel<D, false><<<(unsigned)fb, threads, 0, s>>>(*A, Y);
+  }
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+}  // namespace yr
+
+using namespace yr;
+
+extern "C" int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chunks_h,
+                                   int32_t* n_split_rows_h, int32_t* n_partials_h) {
+  if (!rowptr_h || n_rows < 0 || !n_chunks_h || !n_split_rows_h || !n_partials_h) return YR_ERR_BAD_ARG;
+  int64_t chunks = 0, split = 0, parts = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    const int64_t c = len <= YR_SPMM_CHUNK ? 1 : (len + YR_SPMM_CHUNK - 1) / YR_SPMM_CHUNK;
+    chunks += c;
+    if (c > 1) { ++split; parts += c; }
+  }
+  if (chunks >= (1LL << 31)) return YR_ERR_BAD_DIM;
+  *n_chunks_h = (int32_t)chunks; *n_split_rows_h = (int32_t)split; *n_partials_h = (int32_t)parts;
+  return YR_OK;
+}
+
+// Long rows' chunks first (they are the longest work items), then one chunk per short row.
+extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_desc_h,
+                                   int32_t* split_row_h, int32_t* split_ptr_h) {
+  if (!rowptr_h || n_rows < 0 || !chunk_desc_h || !split_ptr_h) return YR_ERR_BAD_ARG;
+  int64_t c = 0, sr = 0, slot = 0;
+  split_ptr_h[0] = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    if (len <= YR_SPMM_CHUNK) continue;
+    if (!split_row_h) return YR_ERR_BAD_ARG;
+    for (int64_t s = rowptr_h[r]; s < rowptr_h[r + 1]; s += YR_SPMM_CHUNK) {
+      const int64_t e = s + YR_SPMM_CHUNK < rowptr_h[r + 1] ? s + YR_SPMM_CHUNK : rowptr_h[r + 1];
+      int32_t* d = chunk_desc_h + 4 * c;
+      d[0] = (int32_t)r; d[1] = (int32_t)s; d[2] = (int32_t)(e - s); d[3] = (int32_t)slot;
+      ++c; ++slot;
+    }
+    split_row_h[sr] = (int32_t)r;
+    split_ptr_h[++sr] = (int32_t)slot;
+  }
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    if (len > YR_SPMM_CHUNK) continue;
+    int32_t* d = chunk_desc_h + 4 * c;
+    d[0] = (int32_t)r; d[1] = rowptr_h[r]; d[2] = (int32_t)len; d[3] = -1;
+    ++c;
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream) {
+  int rc = yr_csr_ok(A);
+  if (rc) return rc;
+  if (!X || !Y) return YR_ERR_BAD_ARG;
+  if (A->n_rows == 0 || A->n_chunks == 0) return YR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (d) {
+    case 32: return launch_spmm<32>(A, X, Y, accumulate, s);
+    case 64: return launch_spmm<64>(A, X, Y, accumulate, s);
+    case 128: return launch_spmm<128>(A, X, Y, accumulate, s);
+    case 256: return launch_spmm<256>(A, X, Y, accumulate, s);
+    default: return YR_ERR_BAD_DIM;
+  }
+}

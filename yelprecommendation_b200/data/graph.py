@@ -70,14 +70,14 @@ class CSRMatrix:
         _cabi.check(lib.yr_spmm_plan_size_h(rowptr.ctypes.data, self.n_rows, C.byref(nc), C.byref(ns), C.byref(npart)),
                     "yr_spmm_plan_size_h")
         self.n_chunks, self.n_split_rows, self.n_partials = nc.value, ns.value, npart.value
-        crow, cstart, cslot = (np.empty(max(nc.value, 1), np.int32) for _ in range(3))
+        cdesc = np.zeros((max(nc.value, 1), 4), np.int32)
         srow, sptr = np.empty(max(ns.value, 1), np.int32), np.zeros(ns.value + 1, np.int32)
-        _cabi.check(lib.yr_spmm_plan_fill_h(rowptr.ctypes.data, self.n_rows, crow.ctypes.data, cstart.ctypes.data,
-                                            cslot.ctypes.data, srow.ctypes.data, sptr.ctypes.data), "yr_spmm_plan_fill_h")
+        _cabi.check(lib.yr_spmm_plan_fill_h(rowptr.ctypes.data, self.n_rows, cdesc.ctypes.data, srow.ctypes.data,
+                                            sptr.ctypes.data), "yr_spmm_plan_fill_h")
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.device = torch.device(device)
         self.rowptr, self.col, self.val = t(rowptr), t(col.astype(np.int32)), t(val.astype(np.float32))
-        self.chunk_row, self.chunk_start, self.chunk_slot = t(crow), t(cstart), t(cslot)
+        self.chunk_desc = t(cdesc)
         self.split_row, self.split_ptr = t(srow), t(sptr)
         self._partials = {}
 
@@ -94,7 +94,7 @@ class CSRMatrix:
             self._partials[d] = part
         p = _cabi.dptr
         return _cabi.YrCsr(self.n_rows, self.nnz, p(self.rowptr), p(self.col), p(self.val), self.n_chunks,
-                           p(self.chunk_row), p(self.chunk_start), p(self.chunk_slot), self.n_split_rows,
+                           p(self.chunk_desc), self.n_split_rows,
                            p(self.split_row), p(self.split_ptr), p(part))
 
 
