@@ -231,6 +231,23 @@ int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* Vt, int64_t
                          int64_t* topk_out, float* topk_score, double* user_metrics, double* metric_sums,
                          void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
 
+/* Same contract and BIT-IDENTICAL outputs as yr_eval_topk_metrics, on the tensor cores: TF32 tcgen05.mma scores
+ * act as a candidate filter with a proven error bound (|s_tf32 - s_fp32| <= c * ||u|| * max||v||), the few survivors
+ * per row are re-scored with the canonical fp32 fma chain, and rows the filter cannot decide (more than 32 items
+ * inside the window, or fewer than K unmasked items) are evaluated by the exact kernel. Needs both layouts of the
+ * item table: Vemb [nI x d] row-major (TMA source, exact re-score) and Vt (yr_transpose_items, for the fallback).
+ * Supported when yr_eval_tc_supported(d, K) != 0 (d % 32 == 0, 32 <= d <= 256, K <= 16); otherwise YR_ERR_BAD_DIM
+ * and the caller uses yr_eval_topk_metrics. ws: yr_eval_tc_ws_bytes(n_eval) bytes. */
+int yr_eval_tc_supported(int d, int K);
+size_t yr_eval_tc_ws_bytes(int64_t n_eval);
+int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt, int64_t ldt,
+                            int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
+                            const int32_t* mask_ptr, const int32_t* mask_idx,
+                            const int32_t* act_ptr, const int32_t* act_idx, const int32_t* act_nuniq,
+                            const double* inv_log2, int K,
+                            int64_t* topk_out, float* topk_score, double* user_metrics, double* metric_sums,
+                            void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+
 /* MFTrainer._generate_top_k_recommendation (trainers/mf_trainer.py:163-178) for ONE score row:
  * mask_idx (int64, any order, n_mask entries) positions get -3.40282e+38, then the K best by
  * (score desc, item id asc) are written best-first. `pred` is not modified. */

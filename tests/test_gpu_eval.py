@@ -11,17 +11,33 @@ from util import RTOL, cfg, lists_from, load_npz, metric_cases, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def run_gpu(U, V, csr, K=10):
+MODES = ["exact", "tc"]      # FP32-pipe kernel / tensor-core filter + exact re-score: identical outputs required
+
+
+def tc_ok(d, K):
+    from yelprecommendation_b200 import _cabi
+    return _cabi.load().yr_eval_tc_supported(d, K) != 0
+
+
+def run_gpu(U, V, csr, K=10, mode="exact"):
     from yelprecommendation_b200 import ops
     dev = torch.device("cuda")
     ecsr = ops.DeviceEvalCSR(csr, dev, K)
-    topk, tsc, um, sums, err = ops.eval_topk_metrics(torch.from_numpy(U).to(dev), torch.from_numpy(V).to(dev), ecsr)
+    topk, tsc, um, sums, err = ops.eval_topk_metrics(torch.from_numpy(U).to(dev), torch.from_numpy(V).to(dev), ecsr,
+                                                     mode=mode)
     assert int(err.item()) == 0
     return topk.cpu().numpy(), tsc.cpu().numpy(), um.cpu().numpy(), sums.cpu().numpy()
 
 
-def check_vs_oracle(U, V, csr, K=10):
-    topk, tsc, um, sums = run_gpu(U, V, csr, K)
+def fallback_rows():
+    from yelprecommendation_b200 import ops
+    return int(ops.eval_topk_metrics.last_fallback_rows.item())
+
+
+def check_vs_oracle(U, V, csr, K=10, mode="exact"):
+    if mode == "tc" and not tc_ok(U.shape[1], K):
+        pytest.skip("tensor-core filter needs d % 32 == 0, d <= 256, K <= 16")
+    topk, tsc, um, sums = run_gpu(U, V, csr, K, mode)
     otopk, otsc, oum, osums = cport.eval_topk_metrics(U, V, csr.eval_uid, csr.mask_ptr, csr.mask_idx, csr.act_ptr,
                                                       csr.act_idx, K)
     assert np.array_equal(topk, otopk), "top-K ids must be bit-exact under (score desc, id asc)"
@@ -31,15 +47,16 @@ def check_vs_oracle(U, V, csr, K=10):
     return topk, sums
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("prefix", ["valid_eval", "test_eval"])
-def test_eval_golden_small(prefix):
+def test_eval_golden_small(prefix, mode):
     from yelprecommendation_b200.data.graph import build_eval_csr
     from yelprecommendation_b200 import ops
     g = load_npz("mf_small.npz")
     U, V = g["eval_U"].astype(np.float32), g["eval_V"].astype(np.float32)
     uid = g[f"{prefix}_uid"]
     csr = build_eval_csr(uid, lists_from(g, prefix, "pos_items"), lists_from(g, prefix, "mask_items"), int(g["num_items"]))
-    topk, sums = check_vs_oracle(U, V, csr)
+    topk, sums = check_vs_oracle(U, V, csr, 10, mode)
     ref = g[f"{prefix}_topk"]
     diff = [r for r in range(len(uid)) if not np.array_equal(topk[r], ref[r])]
     for r in diff:   # only fp32-noise ties against the reference's NumPy order (Q5)
@@ -74,17 +91,21 @@ def _random_problem(rng, nU, nI, d, n_eval, heavy=False, ties=False):
 
 @pytest.mark.parametrize("nU,nI,d,n_eval,K", [(64, 100, 64, 1, 10), (300, 1000, 64, 129, 10), (500, 3001, 64, 400, 20),
                                                (200, 777, 256, 130, 10), (128, 640, 32, 128, 1), (90, 512, 128, 77, 32),
-                                               (50, 33, 20, 40, 10)])
-def test_eval_random_vs_oracle(nU, nI, d, n_eval, K):
+                                               (50, 33, 20, 40, 10), (400, 5000, 64, 300, 16)])
+@pytest.mark.parametrize("mode", MODES)
+def test_eval_random_vs_oracle(nU, nI, d, n_eval, K, mode):
     rng = np.random.default_rng(nI + d)
     U, V, csr = _random_problem(rng, nU, nI, d, n_eval)
-    check_vs_oracle(U, V, csr, K)
+    check_vs_oracle(U, V, csr, K, mode)
+    if mode == "tc":
+        assert fallback_rows() <= max(1, n_eval // 50)       # the filter decides (almost) every row itself
 
 
-def test_eval_heavy_masks_and_ties():
+@pytest.mark.parametrize("mode", MODES)
+def test_eval_heavy_masks_and_ties(mode):
     rng = np.random.default_rng(5)
     U, V, csr = _random_problem(rng, 100, 2000, 64, 150, heavy=True, ties=True)
-    topk, _ = check_vs_oracle(U, V, csr, 10)
+    topk, _ = check_vs_oracle(U, V, csr, 10, mode)
     # masked items never appear unless fewer than K unmasked items exist
     for e in range(csr.n_eval):
         m = set(csr.mask_idx[csr.mask_ptr[e]:csr.mask_ptr[e + 1]].tolist())
@@ -98,7 +119,28 @@ def test_eval_more_masked_than_catalog_minus_k():
     rng = np.random.default_rng(9)
     U, V = rng.standard_normal((4, 64)).astype(np.float32), rng.standard_normal((40, 64)).astype(np.float32)
     csr = build_eval_csr([0, 1], [[1, 2], [3]], [list(range(35)), list(range(40))], 40)
-    check_vs_oracle(U, V, csr, 10)
+    check_vs_oracle(U, V, csr, 10, "exact")
+    check_vs_oracle(U, V, csr, 10, "tc")
+    assert fallback_rows() == 2          # fewer than K unmasked items -> both rows go to the exact kernel
+
+
+def test_tc_filter_adversarial_near_ties():
+    """Scores packed inside the TF32 error window: hundreds of items within 2*eps of the K-th best. The filter must
+    hand those rows to the exact kernel (candidate overflow) and the result must still be bit-exact."""
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    rng = np.random.default_rng(3)
+    d, nI = 64, 3000
+    base = rng.standard_normal(d).astype(np.float32)
+    V = (base[None, :] + 1e-4 * rng.standard_normal((nI, d))).astype(np.float32)     # near-identical items
+    V[::7] = V[3]                                                                     # plus exact duplicates
+    U = rng.standard_normal((64, d)).astype(np.float32)
+    csr = build_eval_csr(np.arange(64), [[1, 5, 9]] * 64, [[2, 3]] * 64, nI)
+    check_vs_oracle(U, V, csr, 10, "tc")
+    assert fallback_rows() > 0
+    # moderately close scores: the window holds a few extra candidates, no fallback needed
+    V2 = (base[None, :] * 0.1 + rng.standard_normal((nI, d))).astype(np.float32)
+    check_vs_oracle(U, V2, csr, 10, "tc")
+    assert fallback_rows() == 0
 
 
 def test_trainer_evaluate_dataframe_interface():
@@ -146,7 +188,12 @@ def test_full_catalog_yelp_shape_properties():
     uid, pos, mask = syn.eval_lists(split, "valid")
     csr = build_eval_csr(uid, pos, mask, inter.num_items)
     U, V = syn.planted_embeddings(inter)
-    topk, tsc, um, sums = run_gpu(U, V, csr, 10)
+    topk, tsc, um, sums = run_gpu(U, V, csr, 10, "tc")
+    n_fb = fallback_rows()
+    topk_x, tsc_x, um_x, sums_x = run_gpu(U, V, csr, 10, "exact")
+    assert np.array_equal(topk, topk_x) and np.array_equal(tsc, tsc_x) and np.array_equal(um, um_x)   # all 31,668 rows
+    assert np.array_equal(sums, sums_x)
+    assert n_fb <= len(uid) // 100
     assert topk.shape == (len(uid), 10) and topk.min() >= 0 and topk.max() < inter.num_items
     assert np.all(np.diff(tsc, axis=1) <= 0)                                  # best first
     assert np.all(np.sort(topk, axis=1)[:, 1:] != np.sort(topk, axis=1)[:, :-1])   # distinct ids

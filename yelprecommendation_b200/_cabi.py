@@ -23,6 +23,7 @@ SYMBOLS = (
     "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
+    "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -125,6 +126,10 @@ def load() -> C.CDLL:
         "yr_eval_ws_bytes": (sz, [i64, i32, i32]),
         "yr_eval_topk_metrics": (C.c_int, [p, i64, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
                                            p, p, p, p, p, sz, p, p]),
+        "yr_eval_tc_supported": (C.c_int, [i32, i32]),
+        "yr_eval_tc_ws_bytes": (sz, [i64]),
+        "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
+                                              p, p, p, p, p, sz, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

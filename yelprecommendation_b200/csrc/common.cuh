@@ -19,6 +19,16 @@ namespace cg = cooperative_groups;
     if (e__ != cudaSuccess) return (int)e__;                \
   } while (0)
 
+// library-internal launchers (eval.cu), shared with eval_tc.cu; not part of the C ABI
+int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t ldt, int64_t nI, int d,
+                         const int64_t* eval_uid, int64_t n_eval, const int32_t* mask_ptr,
+                         const int32_t* mask_idx, const int32_t* act_ptr, const int32_t* act_idx,
+                         const int32_t* act_nuniq, const double* inv_log2, int K, int64_t* topk_out,
+                         float* topk_score, double* user_metrics, int32_t* err, const int32_t* row_list,
+                         const int32_t* n_rows_dev, yr_stream stream);
+int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, const int32_t* act_nuniq,
+                          int64_t n_eval, double* metric_sums, yr_stream stream);
+
 namespace yr {
 
 constexpr int kWarp = 32;

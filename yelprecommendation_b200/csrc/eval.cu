@@ -77,7 +77,11 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
                  const int32_t* __restrict__ act_ptr, const int32_t* __restrict__ act_idx,
                  const int32_t* __restrict__ act_nuniq, const double* __restrict__ inv_log2, int K,
                  int64_t* __restrict__ topk_out, float* __restrict__ topk_score,
-                 double* __restrict__ user_metrics, int32_t* err) {
+                 double* __restrict__ user_metrics, int32_t* err, const int32_t* __restrict__ row_list,
+                 const int32_t* __restrict__ n_rows_dev) {
+  // optional indirection: evaluate only rows row_list[0 .. *n_rows_dev) (the tensor-core path's undecided rows)
+  if (row_list) n_eval = *n_rows_dev;
+  auto ROW = [&](int64_t t) -> int64_t { return row_list ? (int64_t)row_list[t] : t; };
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* Us = reinterpret_cast<float*>(smem_raw);
   float* Vs = Us + (size_t)d_pad * kTU;
@@ -134,7 +138,7 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int64_t e = e0 + u;
       if (e < n_eval && c4 * 4 < d) {
-        const int64_t uid = eval_uid[e];
+        const int64_t uid = eval_uid[ROW(e)];
         if (uid >= 0 && uid < nU) v = __ldg(reinterpret_cast<const float4*>(Uemb + uid * d) + c4);
         else if (err) atomicExch(err, 1);
       }
@@ -146,7 +150,7 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
       const int64_t e = e0 + tid;
       thr[tid] = -INFINITY;
       int c = 0, en = 0;
-      if (e < n_eval) { c = mask_ptr[e]; en = mask_ptr[e + 1]; }
+      if (e < n_eval) { const int64_t er = ROW(e); c = mask_ptr[er]; en = mask_ptr[er + 1]; }
       mcur[tid] = c; mend[tid] = en;
       mnext[tid] = (c < en) ? mask_idx[c] : 0x7fffffff;
     }
@@ -208,7 +212,7 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
             if (tmask[m] == key) return true;
           return false;
         }
-        const int64_t e = e0 + ul;   // rare: more than kMCap masked pairs in one tile -> search the CSR
+        const int64_t e = ROW(e0 + ul);   // rare: more than kMCap masked pairs in one tile -> search the CSR
         int lo = mask_ptr[e], hi = mask_ptr[e + 1];
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
@@ -292,8 +296,8 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
     // ---- finalize this user tile: top-K out + metric terms (metric.py quirks Q6-Q8) ----
     for (int uu = 0; uu < 16; ++uu) {
       const int ul = warp * 16 + uu;
-      const int64_t e = e0 + ul;
-      if (e >= n_eval) break;
+      if (e0 + ul >= n_eval) break;
+      const int64_t e = ROW(e0 + ul);
       int pi = -1; float ps = 0.f;
       if (lane < K) {
         pi = topI[ul * K + lane]; ps = topS[ul * K + lane];
@@ -412,27 +416,46 @@ extern "C" int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* 
                                     double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
                                     yr_stream stream) {
   (void)ws; (void)ws_bytes;
+  int rc = yr_eval_exact_launch(Uemb, nU, Vt, ldt, nI, d, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx,
+                                act_nuniq, inv_log2, K, topk_out, topk_score, user_metrics, err, nullptr, nullptr,
+                                stream);
+  if (rc) return rc;
+  return yr_eval_reduce_launch(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums, stream);
+}
+
+// Internal launchers shared with the tensor-core path (eval_tc.cu): the exact kernel over all rows, or over
+// row_list[0 .. *n_rows_dev) when a list is given (n_eval then only bounds the grid).
+int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t ldt, int64_t nI, int d,
+                         const int64_t* eval_uid, int64_t n_eval, const int32_t* mask_ptr,
+                         const int32_t* mask_idx, const int32_t* act_ptr, const int32_t* act_idx,
+                         const int32_t* act_nuniq, const double* inv_log2, int K, int64_t* topk_out,
+                         float* topk_score, double* user_metrics, int32_t* err, const int32_t* row_list,
+                         const int32_t* n_rows_dev, yr_stream stream) {
   if (!Uemb || !Vt || !eval_uid || !mask_ptr || !mask_idx || !act_ptr || !act_idx || !act_nuniq ||
-      !inv_log2 || !topk_out || !user_metrics || !metric_sums)
+      !inv_log2 || !topk_out || !user_metrics)
     return YR_ERR_BAD_ARG;
   if (n_eval < 0 || nI <= 0 || d <= 0 || K <= 0 || K > kMaxK) return YR_ERR_BAD_ARG;
   if ((d & 3) != 0 || nI >= (1 << 24)) return YR_ERR_BAD_DIM;
   if (ldt % kTI != 0 || ldt < nI || (ldt & 3) != 0) return YR_ERR_BAD_ARG;   // tiles must not run off Vt
-  cudaStream_t s = (cudaStream_t)stream;
-  if (n_eval > 0) {
-    const int d_pad = pad32(d);
-    const size_t smem = eval_smem_bytes(d_pad, K);
-    if (smem > 227 * 1024) return YR_ERR_BAD_DIM;
-    YR_CUDA(cudaFuncSetAttribute(eval_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_utiles = (n_eval + kTU - 1) / kTU;
-    int64_t grid = yr_sm_count();
-    if (grid > n_utiles) grid = n_utiles;
-    eval_topk_kernel<<<(unsigned)grid, kEvalThreads, smem, s>>>(
-        Uemb, nU, Vt, ldt, nI, d, d_pad, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq,
-        inv_log2, K, topk_out, topk_score, user_metrics, err);
-    YR_CHECK_LAUNCH();
-  }
-  eval_reduce_kernel<<<1, 1024, 0, s>>>(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums);
+  if (n_eval == 0) return YR_OK;
+  const int d_pad = pad32(d);
+  const size_t smem = eval_smem_bytes(d_pad, K);
+  if (smem > 227 * 1024) return YR_ERR_BAD_DIM;
+  YR_CUDA(cudaFuncSetAttribute(eval_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_utiles = (n_eval + kTU - 1) / kTU;
+  int64_t grid = yr_sm_count();
+  if (grid > n_utiles) grid = n_utiles;
+  eval_topk_kernel<<<(unsigned)grid, kEvalThreads, smem, (cudaStream_t)stream>>>(
+      Uemb, nU, Vt, ldt, nI, d, d_pad, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq,
+      inv_log2, K, topk_out, topk_score, user_metrics, err, row_list, n_rows_dev);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, const int32_t* act_nuniq,
+                          int64_t n_eval, double* metric_sums, yr_stream stream) {
+  if (!user_metrics || !act_ptr || !act_nuniq || !metric_sums) return YR_ERR_BAD_ARG;
+  eval_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }

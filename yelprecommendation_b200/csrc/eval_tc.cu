@@ -1,0 +1,482 @@
+// Full-catalog evaluation on the 5th-gen tensor cores (sm_100a): same contract and BIT-IDENTICAL outputs as
+// eval.cu (reference trainers/mf_trainer.py:134-178, metric.py:7-109), ~30x fewer FP32-pipe flops.
+//
+// Idea: TF32 tcgen05.mma scores are only a FILTER. For user u and item i let s be the canonical fp32 fma-chain
+// score and s~ the tensor-core score; |s~ - s| <= eps_u := c * ||u||_2 * max_i ||v_i||_2 (c covers TF32 operand
+// truncation 2*2^-10, the MMA accumulation and the chain's own rounding). If tau~ is the K-th largest s~ among the
+// unmasked items seen so far, every true top-K item satisfies s~ >= tau~_final - 2 eps >= tau~_running - 2 eps.
+// So one thread per user (= one TMEM lane) scans its row of the accumulator, keeps the K best s~ values and
+// appends every unmasked item with s~ >= tau~ - 2 eps to a small candidate buffer (compacted in place when full).
+// After the last item tile the few survivors (~K + a handful) are re-scored with the exact fp32 chain, ordered by
+// (score desc, item id asc), and fed to the same metric code. Rows the filter cannot decide (candidate overflow, or
+// fewer than K unmasked items) are appended to a fallback list that the exact kernel of eval.cu evaluates.
+//
+// Pipeline per CTA (one per SM, persistent over 128-user tiles):
+//   warp 0  : TMA producer  — item tiles [TN x 32 floats] boxes, 128B swizzle, mbarrier expect_tx
+//   warp 1  : MMA issuer    — tcgen05.mma.kind::tf32, M=128, N=TN, K=8 per instruction, A/B from shared memory
+//   warp 2  : TMEM allocator (2 accumulator stages of TN columns)
+//   warps 4-7: epilogue     — tcgen05.ld 32x32b.x32, filter, candidate buffers, final exact re-score + metrics
+// The user tile (gathered rows of eval_uid) is written to shared memory by all threads in the 128B-swizzled K-major
+// layout the UMMA descriptor expects.
+#include <cuda.h>
+#include <float.h>
+#include "common.cuh"
+
+namespace yr {
+
+constexpr int kTcTM = 128;
+constexpr int kTcThreads = 256;
+constexpr int kTcCap = 32;          // candidate buffer entries per user
+constexpr int kTcMaxK = 16;
+constexpr float kTcMaskValue = -3.40282e+38f;
+constexpr float kTcErrCoef = 0.0025f;   // > 2*2^-10 (TF32 operands) + accumulation + fp32-chain rounding
+
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE;\n\t"
+      "bra TC_WAIT;\n\t"
+      "TC_DONE:\n\t}" ::"r"(s2u(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;               // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+  return d;
+}
+
+struct TcParams {
+  const float* Uemb; int64_t nU;
+  const float* Vemb; int64_t nI; int d;
+  const int64_t* eval_uid; int64_t n_eval;
+  const int32_t* mask_ptr; const int32_t* mask_idx;
+  const int32_t* act_ptr; const int32_t* act_idx; const int32_t* act_nuniq;
+  const double* inv_log2; int K;
+  int64_t* topk_out; float* topk_score; double* user_metrics;
+  int32_t* err;
+  const float* vmax;             // device scalar: max item row norm
+  int32_t* fb_count; int32_t* fb_rows;
+  int TN, SPS, NST;              // item tile width, 32-float slabs per stage, pipeline stages
+};
+
+__device__ __forceinline__ float exact_score(const float* __restrict__ u, const float* __restrict__ v, int d) {
+  float acc = 0.f;
+  const float4* u4 = reinterpret_cast<const float4*>(u);
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  for (int k = 0; k < d / 4; ++k) {
+    const float4 a = __ldg(u4 + k), c = __ldg(v4 + k);
+    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc);
+    acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // the swizzled tiles need 1024-byte alignment in the shared window; the launch adds 1 KB of slack for this
+  unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
+  const int d = P.d, K = P.K, TN = P.TN, SPS = P.SPS, NST = P.NST;
+  const int n_slabs = d / 32;
+  const int n_kc = n_slabs / SPS;                       // stages per item tile
+  const uint32_t stage_bytes = (uint32_t)SPS * TN * 128;
+  unsigned char* Us = smem;                             // [n_slabs][128 rows][128 B] swizzled
+  unsigned char* Vs = Us + (size_t)n_slabs * 16384;     // [NST][SPS][TN rows][128 B] swizzled (TMA)
+  float* tk = reinterpret_cast<float*>(Vs + (size_t)NST * stage_bytes);   // [K][128] approx top-K values
+  int* cid = reinterpret_cast<int*>(tk + kTcMaxK * kTcTM);                // [kTcCap][128]
+  float* csc = reinterpret_cast<float*>(cid + kTcCap * kTcTM);            // [kTcCap][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(csc + kTcCap * kTcTM);     // full[4] empty[4] tfull[2] tempty[2]
+  uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_utiles = (P.n_eval + kTcTM - 1) / kTcTM;
+  const int n_itiles = (int)((P.nI + TN - 1) / TN);
+  const uint32_t tmem_cols = 2u * TN;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&vmap) : "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N=TN, M=128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  uint32_t st_p = 0, ph_p = 0;      // producer ring position / phase
+  uint32_t st_m = 0, ph_m = 0;      // MMA ring position / phase
+  uint32_t acc_m = 0, aph_m = 0;    // MMA accumulator stage / phase
+  uint32_t acc_e = 0, aph_e = 0;    // epilogue accumulator stage / phase
+
+  for (int64_t ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
+    const int64_t e0 = ut * kTcTM;
+    // ---- user tile -> shared memory, K-major SW128: byte = slab*16384 + (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)
+    for (int idx = tid; idx < kTcTM * (d / 4); idx += kTcThreads) {
+      const int r = idx / (d / 4), c4 = idx % (d / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t e = e0 + r;
+      if (e < P.n_eval) {
+        const int64_t uid = P.eval_uid[e];
+        if (uid >= 0 && uid < P.nU) v = __ldg(reinterpret_cast<const float4*>(P.Uemb + uid * d) + c4);
+        else if (P.err) atomicExch(P.err, 1);
+      }
+      const int slab = c4 >> 3, c = c4 & 7;
+      *reinterpret_cast<float4*>(Us + (size_t)slab * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+    __syncthreads();
+
+    if (warp == 0) {
+      // ================= TMA producer =================
+      if (lane == 0) {
+        for (int it = 0; it < n_itiles; ++it) {
+          for (int kc = 0; kc < n_kc; ++kc) {
+            mbar_wait(empty + st_p, ph_p ^ 1);
+            mbar_expect_tx(full + st_p, stage_bytes);
+            unsigned char* dst = Vs + (size_t)st_p * stage_bytes;
+            for (int sl = 0; sl < SPS; ++sl)
+              tma_load_2d(dst + (size_t)sl * TN * 128, &vmap, (kc * SPS + sl) * 32, it * TN, full + st_p);
+            if (++st_p == (uint32_t)NST) { st_p = 0; ph_p ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+        for (int it = 0; it < n_itiles; ++it) {
+          mbar_wait(tempty + acc_m, aph_m ^ 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + acc_m * TN;
+          for (int kc = 0; kc < n_kc; ++kc) {
+            mbar_wait(full + st_m, ph_m);
+            tc_fence_after();
+            const uint32_t bbase = s2u(Vs + (size_t)st_m * stage_bytes);
+            for (int sl = 0; sl < SPS; ++sl) {
+              const uint64_t ad = sw128_desc(s2u(Us + (size_t)(kc * SPS + sl) * 16384));
+              const uint64_t bd = sw128_desc(bbase + (uint32_t)sl * TN * 128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)       // 4 x (K = 8 tf32 = 32 B) per 128-byte slab
+                umma_tf32(tacc, ad + 2 * ks, bd + 2 * ks, idesc, (kc | sl | ks) != 0);
+            }
+            umma_commit(empty + st_m);             // smem stage free once these MMAs retire
+            if (++st_m == (uint32_t)NST) { st_m = 0; ph_m ^= 1; }
+          }
+          umma_commit(tfull + acc_m);              // accumulator ready for the epilogue
+          if (++acc_m == 2) { acc_m = 0; aph_m ^= 1; }
+        }
+      }
+    } else if (warp >= 4) {
+      // ================= epilogue: one thread per user row =================
+      const int r = (warp - 4) * 32 + lane;        // TMEM lane == user row of the tile
+      const int64_t e = e0 + r;
+      const bool live = e < P.n_eval;
+      int64_t uid = live ? P.eval_uid[e] : 0;
+      if (uid < 0 || uid >= P.nU) uid = 0;
+      const float* urow = P.Uemb + uid * d;
+      float eps2 = 0.f;
+      if (live) {
+        float nn = 0.f;
+        for (int k = 0; k < d; ++k) nn = fmaf(urow[k], urow[k], nn);
+        eps2 = 2.f * kTcErrCoef * sqrtf(nn) * (*P.vmax) * 1.0001f + FLT_MIN;
+      }
+      for (int j = 0; j < K; ++j) tk[j * kTcTM + r] = -INFINITY;
+      float tau = -INFINITY, theta = -INFINITY;
+      int cnt = 0;
+      bool overflow = false;
+      int mcur = live ? P.mask_ptr[e] : 0;
+      const int mend = live ? P.mask_ptr[e + 1] : 0;
+      int mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff;
+
+      auto compact = [&]() {        // keep candidates still inside the window
+        int w = 0;
+        for (int j = 0; j < cnt; ++j) {
+          const float s = csc[j * kTcTM + r];
+          if (s >= theta) { csc[w * kTcTM + r] = s; cid[w * kTcTM + r] = cid[j * kTcTM + r]; ++w; }
+        }
+        cnt = w;
+      };
+      auto handle = [&](int item, float s) {
+        if (item >= P.nI) return;                                   // zero-filled TMA rows past the catalog
+        while (mnext < item) { ++mcur; mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff; }
+        if (mnext == item) return;                                  // masked: never a candidate (see fallback rule)
+        if (cnt == kTcCap) { compact(); if (cnt == kTcCap) { overflow = true; return; } }
+        cid[cnt * kTcTM + r] = item; csc[cnt * kTcTM + r] = s; ++cnt;
+        if (s > tau) {                                              // insert into the sorted K best s~ values
+          int j = K - 1;
+          while (j > 0 && tk[(j - 1) * kTcTM + r] < s) { tk[j * kTcTM + r] = tk[(j - 1) * kTcTM + r]; --j; }
+          tk[j * kTcTM + r] = s;
+          tau = tk[(K - 1) * kTcTM + r];
+          theta = tau - eps2;
+        }
+      };
+
+      for (int it = 0; it < n_itiles; ++it) {
+        mbar_wait(tfull + acc_e, aph_e);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_e * TN;
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(trow + c0, v);
+          float m = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+          if (live && !overflow && m >= theta) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (v[j] >= theta) handle(it * TN + c0 + j, v[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty + acc_e);
+        if (++acc_e == 2) { acc_e = 0; aph_e ^= 1; }
+      }
+
+      // ---- final phase: exact re-score of the survivors, top-K, metrics ----
+      if (live) {
+        bool fallback = overflow || tau == -INFINITY;                // tau == -inf: fewer than K unmasked items
+        int topi[kTcMaxK];
+        float tops[kTcMaxK];
+        int nt = 0;
+        if (!fallback) {
+          for (int j = 0; j < cnt; ++j) {
+            if (csc[j * kTcTM + r] < theta) continue;
+            const int item = cid[j * kTcTM + r];
+            const float s = exact_score(urow, P.Vemb + (int64_t)item * d, d);
+            int pos = nt < K ? nt : K;                               // insertion by (score desc, id asc)
+            while (pos > 0 && (tops[pos - 1] < s || (tops[pos - 1] == s && topi[pos - 1] > item))) --pos;
+            if (pos < K) {
+              const int last = nt < K ? nt : K - 1;
+              for (int q = last; q > pos; --q) { tops[q] = tops[q - 1]; topi[q] = topi[q - 1]; }
+              tops[pos] = s; topi[pos] = item;
+              if (nt < K) ++nt;
+            }
+          }
+          if (nt < K) fallback = true;
+        }
+        if (fallback) {
+          P.fb_rows[atomicAdd(P.fb_count, 1)] = (int32_t)e;
+        } else {
+          for (int j = 0; j < K; ++j) {
+            P.topk_out[e * K + j] = topi[j];
+            if (P.topk_score) P.topk_score[e * K + j] = tops[j];
+          }
+          // metric terms, metric.py:7-109 (quirks Q6-Q8), Python's summation order
+          const int a0 = P.act_ptr[e], LA = P.act_ptr[e + 1] - a0;
+          int hits = 0;
+          double ap = 0.0, dcg = 0.0, idcg = 0.0;
+          int firstpos[kTcMaxK];
+          for (int j = 0; j < K; ++j) {
+            firstpos[j] = 0x7fffffff;
+            for (int a = 0; a < LA; ++a)
+              if (P.act_idx[a0 + a] == topi[j]) { firstpos[j] = a; break; }
+          }
+          for (int i = 1; i <= K; ++i) {
+            if (firstpos[i - 1] == 0x7fffffff) continue;
+            ++hits;
+            int c = 0;
+            for (int j = 0; j < i; ++j) c += (firstpos[j] < i) ? 1 : 0;
+            ap += (double)c / (double)i;
+            if (i <= LA) dcg += P.inv_log2[i - 1];
+          }
+          for (int i = 1; i <= K && i <= LA; ++i) idcg += P.inv_log2[i - 1];
+          const int nun = P.act_nuniq[e];
+          double* um = P.user_metrics + e * 4;
+          um[0] = (double)hits / (double)K;
+          um[1] = (nun > 0) ? (double)hits / (double)nun : 0.0;
+          um[2] = (LA > 0) ? ap / (double)LA : 0.0;
+          um[3] = (nun > 0 && idcg > 0.0) ? dcg / idcg : 0.0;
+        }
+      }
+    }
+    __syncthreads();     // user tile fully consumed before Us is overwritten
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// max_i ||V_i||_2 (device scalar, non-negative floats order like their bit patterns).
+__global__ void item_norm_max_kernel(const float* __restrict__ V, int64_t nI, int d, float* vmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int64_t i = w; i < nI; i += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < d; k += 32) { const float x = V[i * d + k]; acc = fmaf(x, x, acc); }
+    acc = warp_sum(acc);
+    best = fmaxf(best, sqrtf(acc));
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(vmax), __float_as_int(best * 1.0001f));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct TcConfig { int TN, SPS, NST; size_t smem; };
+
+static bool tc_config(int d, int K, TcConfig* c) {
+  if (d < 32 || d > 256 || (d % 32) != 0 || K < 1 || K > kTcMaxK) return false;
+  c->TN = d <= 64 ? 256 : 128;
+  c->SPS = (d % 64 == 0 && d <= 128) ? 2 : 1;
+  const size_t fixed = (size_t)(d / 32) * 16384 + (size_t)kTcMaxK * kTcTM * 4 + 2 * (size_t)kTcCap * kTcTM * 4 + 12 * 8 + 16;
+  const size_t stage = (size_t)c->SPS * c->TN * 128;
+  int nst = (int)((220 * 1024 - fixed) / stage);
+  if (nst > 4) nst = 4;
+  if (nst < 2) return false;
+  c->NST = nst;
+  c->smem = fixed + (size_t)nst * stage + 1024;     // + slack for the 1024-byte alignment of the swizzled tiles
+  return true;
+}
+
+}  // namespace yr
+
+using namespace yr;
+
+extern "C" size_t yr_eval_tc_ws_bytes(int64_t n_eval) {
+  return 64 + (size_t)(n_eval > 0 ? n_eval : 0) * sizeof(int32_t);
+}
+
+extern "C" int yr_eval_tc_supported(int d, int K) {
+  TcConfig c;
+  return tc_config(d, K, &c) && encode_tiled_fn() != nullptr;
+}
+
+extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt,
+                                       int64_t ldt, int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
+                                       const int32_t* mask_ptr, const int32_t* mask_idx, const int32_t* act_ptr,
+                                       const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2,
+                                       int K, int64_t* topk_out, float* topk_score, double* user_metrics,
+                                       double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
+                                       yr_stream stream) {
+  if (!Uemb || !Vemb || !Vt || !eval_uid || !mask_ptr || !mask_idx || !act_ptr || !act_idx || !act_nuniq ||
+      !inv_log2 || !topk_out || !user_metrics || !metric_sums || !ws)
+    return YR_ERR_BAD_ARG;
+  if (n_eval < 0 || nI <= 0 || nI >= (1 << 24)) return YR_ERR_BAD_ARG;
+  TcConfig cfg;
+  if (!tc_config(d, K, &cfg)) return YR_ERR_BAD_DIM;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return YR_ERR_BAD_DIM;
+  if (ws_bytes < yr_eval_tc_ws_bytes(n_eval)) return YR_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(Vemb) & 15) != 0) return YR_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* vmax = reinterpret_cast<float*>(ws);
+  int32_t* fb_count = reinterpret_cast<int32_t*>(ws) + 1;
+  int32_t* fb_rows = reinterpret_cast<int32_t*>(ws) + 16;
+  YR_CUDA(cudaMemsetAsync(ws, 0, 64, s));
+  if (n_eval > 0) {
+    item_norm_max_kernel<<<yr_sm_count() * 4, 256, 0, s>>>(Vemb, nI, d, vmax);
+    YR_CHECK_LAUNCH();
+    CUtensorMap vmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nI};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)cfg.TN};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = enc(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vemb), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return YR_ERR_BAD_ARG;
+    TcParams P;
+    P.Uemb = Uemb; P.nU = nU; P.Vemb = Vemb; P.nI = nI; P.d = d; P.eval_uid = eval_uid; P.n_eval = n_eval;
+    P.mask_ptr = mask_ptr; P.mask_idx = mask_idx; P.act_ptr = act_ptr; P.act_idx = act_idx; P.act_nuniq = act_nuniq;
+    P.inv_log2 = inv_log2; P.K = K; P.topk_out = topk_out; P.topk_score = topk_score; P.user_metrics = user_metrics;
+    P.err = err; P.vmax = vmax; P.fb_count = fb_count; P.fb_rows = fb_rows;
+    P.TN = cfg.TN; P.SPS = cfg.SPS; P.NST = cfg.NST;
+    YR_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    const int64_t n_utiles = (n_eval + kTcTM - 1) / kTcTM;
+    int64_t grid = yr_sm_count();
+    if (grid > n_utiles) grid = n_utiles;
+    eval_tc_kernel<<<(unsigned)grid, kTcThreads, cfg.smem, s>>>(vmap, P);
+    YR_CHECK_LAUNCH();
+    // rows the filter could not decide: exact FP32 kernel over the fallback list (usually empty)
+    int rc = yr_eval_exact_launch(Uemb, nU, Vt, ldt, nI, d, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx,
+                                  act_nuniq, inv_log2, K, topk_out, topk_score, user_metrics, err, fb_rows, fb_count,
+                                  stream);
+    if (rc) return rc;
+  }
+  return yr_eval_reduce_launch(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums, stream);
+}

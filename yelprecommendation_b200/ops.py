@@ -229,12 +229,39 @@ def transpose_items(V: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return Vt, ldt
 
 
-def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None):
-    """Returns (topk [n_eval x K] int64, topk_score, user_metrics [n_eval x 4] f64, sums [6] f64) on device."""
+def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None, mode: str = None):
+    """Returns (topk [n_eval x K] int64, topk_score, user_metrics [n_eval x 4] f64, sums [6] f64, err) on device.
+
+    mode 'tc'    : tensor-core filter + exact re-score (yr_eval_topk_metrics_tc) — bit-identical outputs;
+    mode 'exact' : FP32-pipe kernel (yr_eval_topk_metrics);
+    mode None    : env YR_EVAL_MODE, else 'tc' whenever the library supports (d, K), 'exact' otherwise."""
+    import os
     lib = _cabi.load()
     Uemb = Uemb.detach().contiguous()
+    Vemb = Vemb.detach().contiguous()
     dev = Uemb.device
     nI, d = Vemb.shape
+    mode = mode or os.environ.get("YR_EVAL_MODE") or "auto"
+    use_tc = mode == "tc" or (mode == "auto" and lib.yr_eval_tc_supported(d, ecsr.K) != 0)
+    if use_tc:
+        if Vt is None:
+            Vt, ldt = transpose_items(Vemb)
+        else:
+            ldt = Vt.shape[1]
+        n, K = ecsr.n_eval, ecsr.K
+        topk = torch.empty(max(n, 1), K, device=dev, dtype=I64)
+        tsc = torch.empty(max(n, 1), K, device=dev, dtype=F32)
+        um = torch.zeros(max(n, 1), 4, device=dev, dtype=F64)
+        sums = torch.zeros(6, device=dev, dtype=F64)
+        err = torch.zeros(1, device=dev, dtype=I32)
+        ws = torch.empty(lib.yr_eval_tc_ws_bytes(n), device=dev, dtype=torch.uint8)
+        check(lib.yr_eval_topk_metrics_tc(dptr(Uemb, F32), Uemb.shape[0], dptr(Vemb, F32), dptr(Vt, F32), ldt, nI, d,
+                                          dptr(ecsr.eval_uid, I64), n, dptr(ecsr.mask_ptr, I32), dptr(ecsr.mask_idx, I32),
+                                          dptr(ecsr.act_ptr, I32), dptr(ecsr.act_idx, I32), dptr(ecsr.act_nuniq, I32),
+                                          dptr(ecsr.inv_log2, F64), K, dptr(topk), dptr(tsc), dptr(um), dptr(sums),
+                                          dptr(ws), ws.numel(), dptr(err), stream_ptr(dev)), "yr_eval_topk_metrics_tc")
+        eval_topk_metrics.last_fallback_rows = ws[4:8].view(I32)      # device int32[1]: rows sent to the exact kernel
+        return topk[:n], tsc[:n], um[:n], sums, err
     if Vt is None:
         Vt, ldt = transpose_items(Vemb)
     else:
