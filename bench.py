@@ -223,7 +223,18 @@ def main():
         for _ in range(W):
             ops.eval_topk_metrics(Ud, Vd, decsr, Vt)
         ms = timed(lambda i: ops.eval_topk_metrics(Ud, Vd, decsr, Vt), K)
-        print(f"eval only: {ms / K:.3f} ms/eval  {w.ecsr.n_eval / (ms / K * 1e-3):.0f} users/s", flush=True)
+        fb = getattr(ops.eval_topk_metrics, "last_fallback_rows", None)
+        print(f"eval only: {ms / K:.3f} ms/eval  {w.ecsr.n_eval / (ms / K * 1e-3):.0f} users/s  "
+              f"fallback_rows={int(fb.item()) if fb is not None else 'n/a'}", flush=True)
+        rng = np.random.default_rng(0)
+        Ur = torch.from_numpy(rng.standard_normal(Up.shape).astype(np.float32)).to(dev)
+        Vr = torch.from_numpy(rng.standard_normal(Vp.shape).astype(np.float32)).to(dev)
+        Vtr, _ = ops.transpose_items(Vr)
+        ops.eval_topk_metrics(Ur, Vr, decsr, Vtr)
+        ms = timed(lambda i: ops.eval_topk_metrics(Ur, Vr, decsr, Vtr), K)
+        fb = getattr(ops.eval_topk_metrics, "last_fallback_rows", None)
+        print(f"eval only (random N(0,1) tables): {ms / K:.3f} ms/eval  fallback_rows={int(fb.item()) if fb is not None else 'n/a'}",
+              flush=True)
         return 0
     if args.only == "mf":        # profiling aid: one persistent launch of K SGD steps
         torch.manual_seed(42)

@@ -25,10 +25,12 @@
 namespace yr {
 
 constexpr int kTcTM = 128;
-constexpr int kTcThreads = 256;
-constexpr int kTcCap = 32;          // candidate buffer entries per user
+constexpr int kTcTN = 128;         // items per MMA tile (N)
+constexpr int kTcAcc = 4;          // TMEM accumulator stages (4 x 128 columns)
+constexpr int kTcThreads = 384;    // 4 control warps + 8 epilogue warps
+constexpr int kTcPend = 4;         // per-thread pending FIFO (deferred candidate handling)
 constexpr int kTcMaxK = 16;
-constexpr float kTcMaskValue = -3.40282e+38f;
+constexpr int kTcCap = 128;        // candidate buffer entries per half-stream (global scratch): compaction is rare
 constexpr float kTcErrCoef = 0.0025f;   // > 2*2^-10 (TF32 operands) + accumulation + fp32-chain rounding
 
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,7 +123,8 @@ struct TcParams {
   int32_t* err;
   const float* vmax;             // device scalar: max item row norm
   int32_t* fb_count; int32_t* fb_rows;
-  int TN, SPS, NST;              // item tile width, 32-float slabs per stage, pipeline stages
+  int* cand;                     // global scratch for the candidate buffers: [grid][2 arrays][2][CAP][128]
+  int SPS, NST, CAP;             // 32-float slabs per stage, pipeline stages, candidate buffer entries per half-stream
 };
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ u, const float* __restrict__ v, int d) {
@@ -136,32 +139,53 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ u, const 
   return acc;
 }
 
+// Select v[j] for a per-lane j without local memory: 5-level mux over the 32 registers.
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4], e[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) e[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? e[1] : e[0];
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // the swizzled tiles need 1024-byte alignment in the shared window; the launch adds 1 KB of slack for this
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
-  const int d = P.d, K = P.K, TN = P.TN, SPS = P.SPS, NST = P.NST;
+  const int d = P.d, K = P.K, SPS = P.SPS, NST = P.NST, CAP = P.CAP;
+  constexpr int TN = kTcTN;
   const int n_slabs = d / 32;
   const int n_kc = n_slabs / SPS;                       // stages per item tile
   const uint32_t stage_bytes = (uint32_t)SPS * TN * 128;
   unsigned char* Us = smem;                             // [n_slabs][128 rows][128 B] swizzled
   unsigned char* Vs = Us + (size_t)n_slabs * 16384;     // [NST][SPS][TN rows][128 B] swizzled (TMA)
-  float* tk = reinterpret_cast<float*>(Vs + (size_t)NST * stage_bytes);   // [K][128] approx top-K values
-  int* cid = reinterpret_cast<int*>(tk + kTcMaxK * kTcTM);                // [kTcCap][128]
-  float* csc = reinterpret_cast<float*>(cid + kTcCap * kTcTM);            // [kTcCap][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(csc + kTcCap * kTcTM);     // full[4] empty[4] tfull[2] tempty[2]
-  uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* tk = reinterpret_cast<float*>(Vs + (size_t)NST * stage_bytes);   // [2][K][128] approx top-K values
+  // candidate buffers live in global scratch (L2): touched ~100 times per user, and 64 KB of shared memory is
+  // worth more as pipeline stages
+  int* cid = P.cand + (size_t)blockIdx.x * 4 * CAP * kTcTM;               // [2][CAP][128] candidate item ids
+  float* csc = reinterpret_cast<float*>(cid + 2 * CAP * kTcTM);           // [2][CAP][128] candidate s~
+  int* pid = reinterpret_cast<int*>(tk + 2 * K * kTcTM);                  // [2][kTcPend][128] pending ids
+  float* psc = reinterpret_cast<float*>(pid + 2 * kTcPend * kTcTM);       // [2][kTcPend][128] pending s~
+  float* tauB = psc + 2 * kTcPend * kTcTM;                                // [128] tau of the second half-stream
+  int* cntB = reinterpret_cast<int*>(tauB + kTcTM);                       // [128] its candidate count (-1 = overflow)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cntB + kTcTM);             // full[4] empty[4] tfull[4] tempty[4]
+  uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_utiles = (P.n_eval + kTcTM - 1) / kTcTM;
   const int n_itiles = (int)((P.nI + TN - 1) / TN);
-  const uint32_t tmem_cols = 2u * TN;
+  constexpr uint32_t tmem_cols = kTcAcc * TN;           // 4 accumulator stages x 128 columns = all of TMEM
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < kTcAcc; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&vmap) : "memory");
   }
@@ -233,12 +257,13 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
             if (++st_m == (uint32_t)NST) { st_m = 0; ph_m ^= 1; }
           }
           umma_commit(tfull + acc_m);              // accumulator ready for the epilogue
-          if (++acc_m == 2) { acc_m = 0; aph_m ^= 1; }
+          if (++acc_m == kTcAcc) { acc_m = 0; aph_m ^= 1; }
         }
       }
     } else if (warp >= 4) {
-      // ================= epilogue: one thread per user row =================
-      const int r = (warp - 4) * 32 + lane;        // TMEM lane == user row of the tile
+      // ================= epilogue: two threads per user row (column halves of every tile) =================
+      const int half = (warp - 4) >> 2;            // 0: columns 0..63, 1: columns 64..127
+      const int r = (warp & 3) * 32 + lane;        // TMEM lane == user row of the tile
       const int64_t e = e0 + r;
       const bool live = e < P.n_eval;
       int64_t uid = live ? P.eval_uid[e] : 0;
@@ -250,76 +275,119 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         for (int k = 0; k < d; ++k) nn = fmaf(urow[k], urow[k], nn);
         eps2 = 2.f * kTcErrCoef * sqrtf(nn) * (*P.vmax) * 1.0001f + FLT_MIN;
       }
-      for (int j = 0; j < K; ++j) tk[j * kTcTM + r] = -INFINITY;
+      float* my_tk = tk + (size_t)half * K * kTcTM + r;
+      int* my_cid = cid + (size_t)half * CAP * kTcTM + r;
+      float* my_csc = csc + (size_t)half * CAP * kTcTM + r;
+      int* my_pid = pid + (size_t)half * kTcPend * kTcTM + r;
+      float* my_psc = psc + (size_t)half * kTcPend * kTcTM + r;
+      for (int j = 0; j < K; ++j) my_tk[j * kTcTM] = -INFINITY;
       float tau = -INFINITY, theta = -INFINITY;
-      int cnt = 0;
+      int cnt = 0, npend = 0;
       bool overflow = false;
       int mcur = live ? P.mask_ptr[e] : 0;
       const int mend = live ? P.mask_ptr[e + 1] : 0;
       int mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff;
 
-      auto compact = [&]() {        // keep candidates still inside the window
-        int w = 0;
-        for (int j = 0; j < cnt; ++j) {
-          const float s = csc[j * kTcTM + r];
-          if (s >= theta) { csc[w * kTcTM + r] = s; cid[w * kTcTM + r] = cid[j * kTcTM + r]; ++w; }
-        }
-        cnt = w;
-      };
-      auto handle = [&](int item, float s) {
-        if (item >= P.nI) return;                                   // zero-filled TMA rows past the catalog
+      auto handle = [&](int item, float s) {          // candidate -> buffer (+ the K best s~ values)
+        if (s < theta) return;                                      // theta may have risen since the scan
         while (mnext < item) { ++mcur; mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff; }
         if (mnext == item) return;                                  // masked: never a candidate (see fallback rule)
-        if (cnt == kTcCap) { compact(); if (cnt == kTcCap) { overflow = true; return; } }
-        cid[cnt * kTcTM + r] = item; csc[cnt * kTcTM + r] = s; ++cnt;
+        if (cnt == CAP) {                                           // compact: keep what is still inside the window
+          int w = 0;
+          for (int j = 0; j < CAP; ++j) {
+            const float sj = my_csc[j * kTcTM];
+            if (sj >= theta) { my_csc[w * kTcTM] = sj; my_cid[w * kTcTM] = my_cid[j * kTcTM]; ++w; }
+          }
+          cnt = w;
+          if (cnt == CAP) { overflow = true; return; }
+        }
+        my_cid[cnt * kTcTM] = item; my_csc[cnt * kTcTM] = s; ++cnt;
         if (s > tau) {                                              // insert into the sorted K best s~ values
           int j = K - 1;
-          while (j > 0 && tk[(j - 1) * kTcTM + r] < s) { tk[j * kTcTM + r] = tk[(j - 1) * kTcTM + r]; --j; }
-          tk[j * kTcTM + r] = s;
-          tau = tk[(K - 1) * kTcTM + r];
+          while (j > 0 && my_tk[(j - 1) * kTcTM] < s) { my_tk[j * kTcTM] = my_tk[(j - 1) * kTcTM]; --j; }
+          my_tk[j * kTcTM] = s;
+          tau = my_tk[(K - 1) * kTcTM];
           theta = tau - eps2;
         }
+      };
+      auto drain = [&]() {                            // warp-uniform loop: lanes pop their pending FIFO in lock step
+        int head = 0;
+        while (__any_sync(kFull, head < npend)) {
+          if (head < npend) { handle(my_pid[head * kTcTM], my_psc[head * kTcTM]); ++head; }
+        }
+        npend = 0;
       };
 
       for (int it = 0; it < n_itiles; ++it) {
         mbar_wait(tfull + acc_e, aph_e);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_e * TN;
-        for (int c0 = 0; c0 < TN; c0 += 32) {
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_e * TN + half * (TN / 2);
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN / 2; c0 += 32) {
           float v[32];
           tmem_ld32(trow + c0, v);
-          float m = v[0];
+          // tree max (depth 4) instead of a 31-deep chain: this warp is alone on its scheduler
+          float m8[8];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-          if (live && !overflow && m >= theta) {
+          for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+          const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          const bool need = live && !overflow && m >= theta;
+          if (__any_sync(kFull, need)) {
+            unsigned mask = 0;
+            if (need) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (v[j] >= theta) handle(it * TN + c0 + j, v[j]);
+              for (int j = 0; j < 32; ++j) mask |= (v[j] >= theta) ? (1u << j) : 0u;
+            }
+            const int item0 = it * TN + half * (TN / 2) + c0;
+            // columns past the catalog are zero-filled TMA rows (score 0): never candidates
+            if ((int64_t)item0 + 32 > P.nI) mask = (item0 < P.nI) ? (mask & ((1u << (int)(P.nI - item0)) - 1u)) : 0u;
+            while (__any_sync(kFull, mask != 0)) {
+              if (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                my_pid[npend * kTcTM] = item0 + j;
+                my_psc[npend * kTcTM] = select32(v, j);
+                ++npend;
+              }
+              if (__any_sync(kFull, npend == kTcPend)) drain();
+            }
           }
         }
         tc_fence_before();
         mbar_arrive(tempty + acc_e);
-        if (++acc_e == 2) { acc_e = 0; aph_e ^= 1; }
+        if (++acc_e == kTcAcc) { acc_e = 0; aph_e ^= 1; }
+        if (__any_sync(kFull, npend > 0)) drain();
       }
 
-      // ---- final phase: exact re-score of the survivors, top-K, metrics ----
-      if (live) {
-        bool fallback = overflow || tau == -INFINITY;                // tau == -inf: fewer than K unmasked items
+      // ---- hand the second half-stream's state to the first; first half finishes the row ----
+      if (half == 1) { tauB[r] = tau; cntB[r] = overflow ? -1 : cnt; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // epilogue warps only
+      if (half == 0 && live) {
+        const float tau_b = tauB[r];
+        const int cnt_b = cntB[r];
+        const float tau_f = fmaxf(tau, tau_b);                      // both are lower bounds of the K-th best s~
+        const float theta_f = tau_f - eps2;
+        bool fallback = overflow || cnt_b < 0 || tau_f == -INFINITY;
         int topi[kTcMaxK];
         float tops[kTcMaxK];
         int nt = 0;
         if (!fallback) {
-          for (int j = 0; j < cnt; ++j) {
-            if (csc[j * kTcTM + r] < theta) continue;
-            const int item = cid[j * kTcTM + r];
-            const float s = exact_score(urow, P.Vemb + (int64_t)item * d, d);
-            int pos = nt < K ? nt : K;                               // insertion by (score desc, id asc)
-            while (pos > 0 && (tops[pos - 1] < s || (tops[pos - 1] == s && topi[pos - 1] > item))) --pos;
-            if (pos < K) {
-              const int last = nt < K ? nt : K - 1;
-              for (int q = last; q > pos; --q) { tops[q] = tops[q - 1]; topi[q] = topi[q - 1]; }
-              tops[pos] = s; topi[pos] = item;
-              if (nt < K) ++nt;
+          for (int h = 0; h < 2; ++h) {
+            const int n_h = h == 0 ? cnt : cnt_b;
+            const int* b_id = cid + (size_t)h * CAP * kTcTM + r;
+            const float* b_sc = csc + (size_t)h * CAP * kTcTM + r;
+            for (int j = 0; j < n_h; ++j) {
+              if (b_sc[j * kTcTM] < theta_f) continue;
+              const int item = b_id[j * kTcTM];
+              const float s = exact_score(urow, P.Vemb + (int64_t)item * d, d);
+              int pos = nt < K ? nt : K;                             // insertion by (score desc, id asc)
+              while (pos > 0 && (tops[pos - 1] < s || (tops[pos - 1] == s && topi[pos - 1] > item))) --pos;
+              if (pos < K) {
+                const int last = nt < K ? nt : K - 1;
+                for (int q = last; q > pos; --q) { tops[q] = tops[q - 1]; topi[q] = topi[q - 1]; }
+                tops[pos] = s; topi[pos] = item;
+                if (nt < K) ++nt;
+              }
             }
           }
           if (nt < K) fallback = true;
@@ -359,7 +427,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         }
       }
     }
-    __syncthreads();     // user tile fully consumed before Us is overwritten
+    __syncthreads();     // user tile fully consumed before Us / the per-row state are overwritten
   }
   tc_fence_before();
   __syncthreads();
@@ -397,15 +465,16 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-struct TcConfig { int TN, SPS, NST; size_t smem; };
+struct TcConfig { int SPS, NST, CAP; size_t smem; };
 
 static bool tc_config(int d, int K, TcConfig* c) {
   if (d < 32 || d > 256 || (d % 32) != 0 || K < 1 || K > kTcMaxK) return false;
-  c->TN = d <= 64 ? 256 : 128;
   c->SPS = (d % 64 == 0 && d <= 128) ? 2 : 1;
-  const size_t fixed = (size_t)(d / 32) * 16384 + (size_t)kTcMaxK * kTcTM * 4 + 2 * (size_t)kTcCap * kTcTM * 4 + 12 * 8 + 16;
-  const size_t stage = (size_t)c->SPS * c->TN * 128;
-  int nst = (int)((220 * 1024 - fixed) / stage);
+  c->CAP = kTcCap;
+  const size_t fixed = (size_t)(d / 32) * 16384 + 2 * (size_t)K * kTcTM * 4 +
+                       4 * (size_t)kTcPend * kTcTM * 4 + 2 * kTcTM * 4 + 16 * 8 + 16;
+  const size_t stage = (size_t)c->SPS * kTcTN * 128;
+  int nst = (int)((224 * 1024 - fixed) / stage);
   if (nst > 4) nst = 4;
   if (nst < 2) return false;
   c->NST = nst;
@@ -417,8 +486,11 @@ static bool tc_config(int d, int K, TcConfig* c) {
 
 using namespace yr;
 
+static size_t tc_cand_bytes() { return (size_t)yr_sm_count() * 4 * kTcCap * kTcTM * sizeof(int); }
+
 extern "C" size_t yr_eval_tc_ws_bytes(int64_t n_eval) {
-  return 64 + (size_t)(n_eval > 0 ? n_eval : 0) * sizeof(int32_t);
+  const size_t rows = ((size_t)(n_eval > 0 ? n_eval : 0) * sizeof(int32_t) + 255) / 256 * 256;
+  return 256 + rows + tc_cand_bytes();
 }
 
 extern "C" int yr_eval_tc_supported(int d, int K) {
@@ -446,7 +518,8 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
   cudaStream_t s = (cudaStream_t)stream;
   float* vmax = reinterpret_cast<float*>(ws);
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws) + 1;
-  int32_t* fb_rows = reinterpret_cast<int32_t*>(ws) + 16;
+  int32_t* fb_rows = reinterpret_cast<int32_t*>(ws) + 64;
+  int* cand = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + yr_eval_tc_ws_bytes(n_eval) - tc_cand_bytes());
   YR_CUDA(cudaMemsetAsync(ws, 0, 64, s));
   if (n_eval > 0) {
     item_norm_max_kernel<<<yr_sm_count() * 4, 256, 0, s>>>(Vemb, nI, d, vmax);
@@ -454,7 +527,7 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
     CUtensorMap vmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nI};
     const cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(float)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)cfg.TN};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)kTcTN};
     const cuuint32_t estr[2] = {1u, 1u};
     CUresult cr = enc(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vemb), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -464,8 +537,8 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
     P.Uemb = Uemb; P.nU = nU; P.Vemb = Vemb; P.nI = nI; P.d = d; P.eval_uid = eval_uid; P.n_eval = n_eval;
     P.mask_ptr = mask_ptr; P.mask_idx = mask_idx; P.act_ptr = act_ptr; P.act_idx = act_idx; P.act_nuniq = act_nuniq;
     P.inv_log2 = inv_log2; P.K = K; P.topk_out = topk_out; P.topk_score = topk_score; P.user_metrics = user_metrics;
-    P.err = err; P.vmax = vmax; P.fb_count = fb_count; P.fb_rows = fb_rows;
-    P.TN = cfg.TN; P.SPS = cfg.SPS; P.NST = cfg.NST;
+    P.err = err; P.vmax = vmax; P.fb_count = fb_count; P.fb_rows = fb_rows; P.cand = cand;
+    P.SPS = cfg.SPS; P.NST = cfg.NST; P.CAP = cfg.CAP;
     YR_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     const int64_t n_utiles = (n_eval + kTcTM - 1) / kTcTM;
     int64_t grid = yr_sm_count();
