@@ -139,6 +139,12 @@ int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */
 int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream);
 
+/* Where the per-layer d x d transforms run: 1 (default) = tensor cores, tcgen05.mma.kind::tf32 with the 3xTF32 split
+ * (within the 1e-5 parity bar); 0 = FP32 pipe, one fma chain per output (bit-comparable with the oracle).
+ * Applies to the forward transform; process-wide. */
+int yr_ngcf_set_dense_mode(int mode);
+int yr_ngcf_get_dense_mode(void);
+
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
  *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
  * W1, W2 are nn.Linear weights [d x d] (out x in). LE_save [n x d] receives L E (kept for backward). */

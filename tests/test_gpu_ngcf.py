@@ -53,7 +53,18 @@ def test_spmm_bit_exact_vs_oracle():
         assert np.array_equal(ya.cpu().numpy(), cport.spmm_csr(*ct, X, Y0))
 
 
-def test_layer_forward_bit_exact_vs_oracle_and_golden():
+@pytest.fixture
+def fp32_dense():
+    """FP32-pipe dense transforms (bit-comparable with the oracle) for the duration of a test."""
+    from yelprecommendation_b200 import _cabi
+    lib = _cabi.load()
+    old = lib.yr_ngcf_get_dense_mode()
+    lib.yr_ngcf_set_dense_mode(0)
+    yield
+    lib.yr_ngcf_set_dense_mode(old)
+
+
+def test_layer_forward_bit_exact_vs_oracle_and_golden(fp32_dense):
     from yelprecommendation_b200 import ops
     from yelprecommendation_b200.data.graph import laplacian_to_csr
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
@@ -67,6 +78,35 @@ def test_layer_forward_bit_exact_vs_oracle_and_golden():
         assert np.array_equal(En.cpu().numpy(), Eo)                      # same fma chain order -> bit-exact
         assert rel_err(En.cpu().numpy(), g[f"ngcf_layer{l + 1}"]) < RTOL   # vs the reference (torch.eye and all)
         E, Ec = En, Eo
+
+
+def test_layer_forward_tensor_core_3xtf32():
+    """Default mode: tcgen05 TF32 MMAs with the hi/lo split. Must stay well inside the 1e-5 bar, on the golden graph
+    and on a 20k-row graph with a ragged last tile."""
+    from yelprecommendation_b200 import _cabi, ops
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian, laplacian_to_csr
+    assert _cabi.load().yr_ngcf_get_dense_mode() == 1
+    g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
+    dcsr = laplacian_to_csr(L, "cuda")
+    E, Ec = torch.from_numpy(E0).cuda(), E0
+    for l in range(3):
+        En, LE = ops.ngcf_layer_fwd(dcsr, E, torch.from_numpy(W1[l]).cuda(), torch.from_numpy(W2[l]).cuda())
+        Eo, LEo = cport.ngcf_layer_fwd(csr, Ec, W1[l], W2[l])
+        assert np.array_equal(LE.cpu().numpy(), LEo)
+        assert rel_err(En.cpu().numpy(), Eo) < 2e-6
+        assert rel_err(En.cpu().numpy(), g[f"ngcf_layer{l + 1}"]) < RTOL
+        E, Ec = torch.from_numpy(Eo).cuda(), Eo          # same input for both on the next layer
+    inter = syn.make_interactions(num_users=9000, num_items=11077, nnz=300_000, seed=12, n_clusters=8)
+    Lb = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    big = laplacian_to_csr(Lb, "cuda")
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((20077, 64)).astype(np.float32)
+    A, B = (rng.standard_normal((64, 64)).astype(np.float32) * 0.2 for _ in range(2))
+    En, _ = ops.ngcf_layer_fwd(big, torch.from_numpy(X).cuda(), torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    c = (big.fwd.rowptr.cpu().numpy(), big.fwd.col.cpu().numpy(), big.fwd.val.cpu().numpy())
+    Eo, _ = cport.ngcf_layer_fwd(c, X, A, B)
+    assert rel_err(En.cpu().numpy(), Eo) < 2e-6
 
 
 def test_layer_backward_vs_oracle_and_autograd_golden():

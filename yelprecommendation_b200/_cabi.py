@@ -24,6 +24,7 @@ SYMBOLS = (
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
+    "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -126,6 +127,8 @@ def load() -> C.CDLL:
         "yr_eval_ws_bytes": (sz, [i64, i32, i32]),
         "yr_eval_topk_metrics": (C.c_int, [p, i64, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
                                            p, p, p, p, p, sz, p, p]),
+        "yr_ngcf_set_dense_mode": (C.c_int, [i32]),
+        "yr_ngcf_get_dense_mode": (C.c_int, []),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),
         "yr_eval_tc_ws_bytes": (sz, [i64]),
         "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,

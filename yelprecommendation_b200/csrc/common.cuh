@@ -29,6 +29,9 @@ int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t
 int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, const int32_t* act_nuniq,
                           int64_t n_eval, double* metric_sums, yr_stream stream);
 
+int yr_ngcf_dense_fwd_tc_launch(const float* E, const float* LE, const float* W1, const float* W2, float slope,
+                                int64_t n, float* Eout, cudaStream_t s);
+
 namespace yr {
 
 constexpr int kWarp = 32;

@@ -364,6 +364,15 @@ constexpr int kBwdCtasPerSm = 2;
 
 using namespace yr;
 
+// 0 = FP32 pipe (one fma chain per output, bit-comparable with the oracle), 1 = tensor cores (3xTF32 split)
+static int g_dense_mode = 1;
+extern "C" int yr_ngcf_set_dense_mode(int mode) {
+  if (mode != 0 && mode != 1) return YR_ERR_BAD_ARG;
+  g_dense_mode = mode;
+  return YR_OK;
+}
+extern "C" int yr_ngcf_get_dense_mode(void) { return g_dense_mode; }
+
 extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
                                  float slope, float* E_next, float* LE_save, yr_stream stream) {
   if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
@@ -371,6 +380,8 @@ extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const f
   const int64_t n = L->n_rows;
   int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
   if (rc) return rc;
+  if (g_dense_mode == 1)      // tcgen05 3xTF32 (ngcf_tc.cu)
+    return yr_ngcf_dense_fwd_tc_launch(E, LE_save, W1, W2, slope, n, E_next, (cudaStream_t)stream);
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
