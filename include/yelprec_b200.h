@@ -121,12 +121,14 @@ typedef struct yr_csr {
   const int32_t *rowptr, *col;
   const float* val;
   int32_t n_chunks;               /* work items: one per short row, ceil(len/CHUNK) per long row */
-  const int32_t *chunk_desc;      /* [n_chunks x 4], 16-byte aligned: {row, first non-zero, length,
+  const int32_t *chunk_desc;      /* [n_chunks x 4], 16-byte aligned: {row, first non-zero, length | split_row_index << 8,
                                      slot} — slot -1 = whole row (direct store), else index into `partials` */
   int32_t n_split_rows;           /* rows that were cut */
   const int32_t *split_row;       /* [n_split_rows] */
   const int32_t *split_ptr;       /* [n_split_rows+1] range of partial slots of each split row */
   float* partials;                /* [split_ptr[n_split_rows] x d] scratch */
+  int32_t* split_count;           /* [n_split_rows] arrival counters, zero on first use; every call leaves them zero.
+                                     The chunk that arrives last at a split row sums that row's partials (in order). */
 } yr_csr;
 
 /* Host-side plan builder (host pointers). Call _size_h first, allocate, then _fill_h. */

@@ -59,7 +59,8 @@ class YrCsr(C.Structure):
                 ("n_chunks", C.c_int32),
                 ("chunk_desc", C.c_void_p),
                 ("n_split_rows", C.c_int32),
-                ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p)]
+                ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p),
+                ("split_count", C.c_void_p)]
 
 
 YR_NGCF_MAX_LAYERS = 7

@@ -177,7 +177,7 @@ inline int yr_sm_count() {
 inline int yr_csr_ok(const yr_csr* A) {
   if (!A || !A->rowptr || !A->col || !A->val || A->n_rows < 0 || A->n_chunks < 0) return YR_ERR_BAD_ARG;
   if (A->n_chunks > 0 && !A->chunk_desc) return YR_ERR_BAD_ARG;
-  if (A->n_split_rows > 0 && (!A->split_row || !A->split_ptr || !A->partials)) return YR_ERR_BAD_ARG;
+  if (A->n_split_rows > 0 && (!A->split_row || !A->split_ptr || !A->partials || !A->split_count)) return YR_ERR_BAD_ARG;
   return YR_OK;
 }
 

@@ -41,7 +41,8 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
     const int c = cb + sub;
     int4 dsc = make_int4(0, 0, 0, -1);
     if (c < A.n_chunks) dsc = __ldg(desc + c);
-    const int row = dsc.x, s = dsc.y, len = dsc.z, slot = dsc.w;
+    const int row = dsc.x, s = dsc.y, len = dsc.z & 0xff, slot = dsc.w;
+    const int split_idx = dsc.z >> 8;            // index into split_row / split_ptr / split_count (split chunks only)
     float4 acc[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -89,54 +90,58 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
 #pragma unroll
       for (int v = 0; v < VPT; ++v) dst[sl * VPT + v] = acc[v];
     }
-  }
-}
-
-// One lane group per split row: sum the chunk partials left to right (8 loads in flight), add Y_old if accumulating.
-template <int D, bool ACC>
-__global__ void __launch_bounds__(256)
-spmm_fixup_kernel(yr_csr A, float* __restrict__ Y) {
-  using C = SpmmCfg<D>;
-  constexpr int LPR = C::LPR, VPT = C::VPT, CPW = C::CPW;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / LPR, sl = lane % LPR;
-  const int w = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * CPW + sub;
-  if (w >= A.n_split_rows) return;
-  const int row = A.split_row[w];
-  const int p0 = A.split_ptr[w], p1 = A.split_ptr[w + 1];
-  const float4* __restrict__ P4 = reinterpret_cast<const float4*>(A.partials);
-  float4 acc[VPT];
-#pragma unroll
-  for (int v = 0; v < VPT; ++v) acc[v] = P4[(int64_t)p0 * C::kVec + sl * VPT + v];
-  int p = p0 + 1;
-  for (; p + 8 <= p1; p += 8) {
-    float4 x[8][VPT];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) x[q][v] = P4[(int64_t)(p + q) * C::kVec + sl * VPT + v];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        acc[v].x += x[q][v].x; acc[v].y += x[q][v].y; acc[v].z += x[q][v].z; acc[v].w += x[q][v].w;
+    // ---- split rows: the chunk that arrives LAST sums the row's partials left to right (deterministic order).
+    // Long rows' chunks are scheduled first (plan order), so this tail work overlaps the bulk of the kernel.
+    const bool is_split = (c < A.n_chunks) && slot >= 0;
+    if (__any_sync(kFull, is_split)) {
+      if (is_split) __threadfence();                       // my part of the partial is visible device-wide
+      __syncwarp();
+      int last = 0;
+      if (is_split && sl == 0) {
+        const int nparts = A.split_ptr[split_idx + 1] - A.split_ptr[split_idx];
+        last = (atomicAdd(A.split_count + split_idx, 1) == nparts - 1) ? 1 : 0;
       }
-  }
-  for (; p < p1; ++p) {
+      last = __shfl_sync(kFull, last, 0, LPR);
+      if (last) {
+        __threadfence();
+        const int p0 = A.split_ptr[split_idx], p1 = A.split_ptr[split_idx + 1];
+        const float4* P4 = reinterpret_cast<const float4*>(A.partials);
+        float4 tot[VPT];
 #pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      const float4 x = P4[(int64_t)p * C::kVec + sl * VPT + v];
-      acc[v].x += x.x; acc[v].y += x.y; acc[v].z += x.z; acc[v].w += x.w;
-    }
-  }
-  float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D);
+        for (int v = 0; v < VPT; ++v) tot[v] = __ldcg(P4 + (int64_t)p0 * C::kVec + sl * VPT + v);
+        int p = p0 + 1;
+        for (; p + 8 <= p1; p += 8) {
+          float4 x[8][VPT];
 #pragma unroll
-  for (int v = 0; v < VPT; ++v) {
-    if (ACC) {
-      const float4 y = y4[sl * VPT + v];
-      acc[v].x = y.x + acc[v].x; acc[v].y = y.y + acc[v].y; acc[v].z = y.z + acc[v].z; acc[v].w = y.w + acc[v].w;
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) x[q][v] = __ldcg(P4 + (int64_t)(p + q) * C::kVec + sl * VPT + v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+              tot[v].x += x[q][v].x; tot[v].y += x[q][v].y; tot[v].z += x[q][v].z; tot[v].w += x[q][v].w;
+            }
+        }
+        for (; p < p1; ++p) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            const float4 x = __ldcg(P4 + (int64_t)p * C::kVec + sl * VPT + v);
+            tot[v].x += x.x; tot[v].y += x.y; tot[v].z += x.z; tot[v].w += x.w;
+          }
+        }
+        float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          if (ACC) {
+            const float4 y = y4[sl * VPT + v];
+            tot[v].x = y.x + tot[v].x; tot[v].y = y.y + tot[v].y; tot[v].z = y.z + tot[v].z; tot[v].w = y.w + tot[v].w;
+          }
+          y4[sl * VPT + v] = tot[v];
+        }
+        if (sl == 0) A.split_count[split_idx] = 0;         // re-arm for the next call
+      }
     }
-    y4[sl * VPT + v] = acc[v];
   }
 }
 
@@ -147,14 +152,8 @@ static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate
   int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
   const int64_t cap = (int64_t)yr_sm_count() * 8 * 16;
   if (blocks > cap) blocks = cap;
-  const int64_t fb = ((int64_t)A->n_split_rows + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
-  if (accumulate) {
-    spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
-    if (fb) spmm_fixup_kernel<D, true><<<(unsigned)fb, threads, 0, s>>>(*A, Y);
-  } else {
-    spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
-    if (fb) spmm_fixup_kernel<D, false><<<(unsigned)fb, threads, 0, s>>>(*A, Y);
-  }
+  if (accumulate) spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
+  else spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }
@@ -191,7 +190,7 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     for (int64_t s = rowptr_h[r]; s < rowptr_h[r + 1]; s += YR_SPMM_CHUNK) {
       const int64_t e = s + YR_SPMM_CHUNK < rowptr_h[r + 1] ? s + YR_SPMM_CHUNK : rowptr_h[r + 1];
       int32_t* d = chunk_desc_h + 4 * c;
-      d[0] = (int32_t)r; d[1] = (int32_t)s; d[2] = (int32_t)(e - s); d[3] = (int32_t)slot;
+      d[0] = (int32_t)r; d[1] = (int32_t)s; d[2] = (int32_t)(e - s) | (int32_t)(sr << 8); d[3] = (int32_t)slot;
       ++c; ++slot;
     }
     split_row_h[sr] = (int32_t)r;

@@ -79,6 +79,7 @@ class CSRMatrix:
         self.rowptr, self.col, self.val = t(rowptr), t(col.astype(np.int32)), t(val.astype(np.float32))
         self.chunk_desc = t(cdesc)
         self.split_row, self.split_ptr = t(srow), t(sptr)
+        self.split_count = torch.zeros(max(ns.value, 1), dtype=torch.int32, device=device)
         self._partials = {}
 
     @property
@@ -95,7 +96,7 @@ class CSRMatrix:
         p = _cabi.dptr
         return _cabi.YrCsr(self.n_rows, self.nnz, p(self.rowptr), p(self.col), p(self.val), self.n_chunks,
                            p(self.chunk_desc), self.n_split_rows,
-                           p(self.split_row), p(self.split_ptr), p(part))
+                           p(self.split_row), p(self.split_ptr), p(part), p(self.split_count))
 
 
 @dataclass
