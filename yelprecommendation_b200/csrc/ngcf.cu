@@ -411,6 +411,7 @@ extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const 
   if (d != 64) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
   const int64_t n = LT->n_rows;
+  cudaStream_t s = (cudaStream_t)stream;
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -418,7 +419,6 @@ extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const 
                                  (int)C::kSmemBwd));
     attr_set = true;
   }
-  cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
   int64_t grid = (int64_t)yr_sm_count() * kBwdCtasPerSm;
   if (grid > n_tiles) grid = n_tiles;

@@ -19,21 +19,6 @@ namespace yr {
 constexpr int kFwdThreads = 416;   // 8 loader warps + 4 epilogue warps + 1 MMA/TMEM warp
 constexpr int kFwdTM = 128;
 
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = x - hi;     // exact in fp32
-}
-__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
-  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
-  split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-}
-// byte offset of 16-byte chunk c4 (4 floats) of row r inside a [rows x 64 floats] operand stored as
-// 2 slabs (32 floats each) of rows x 128 B, 128B-swizzled: slab*rows*128 + (r/8)*1024 + (r%8)*128 + ((c^(r%8))*16)
-__device__ __forceinline__ uint32_t sw_off(int rows, int r, int c4) {
-  const int slab = c4 >> 3, c = c4 & 7;
-  return (uint32_t)(slab * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-
 __global__ void __launch_bounds__(kFwdThreads, 1)
 ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ W1,
                          const float* __restrict__ W2, float slope, int64_t n, float* __restrict__ Eout, int n_pass) {

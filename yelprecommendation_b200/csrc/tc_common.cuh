@@ -86,4 +86,33 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, 128-byte-swizzled shared-memory matrix descriptor: the SAME physical tile as the K-major one above
+// ([mn-block of 32 floats][8-row groups of 1024 B][row][128 B swizzled]) read with MN contiguous and K = rows:
+// leading byte offset = distance between consecutive 32-float MN blocks, stride byte offset = 8 K-rows = 1024 B.
+__device__ __forceinline__ uint64_t sw128_desc_mn(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// 3xTF32 operand split: hi keeps the top 11 significand bits (exactly representable in TF32), lo = x - hi (exact).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+  split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+// byte offset of 16-byte chunk c4 (floats 4*c4 .. 4*c4+3) of row r inside a [rows x 32*n_slabs floats] operand stored
+// as slabs (32 floats each) of rows x 128 B, 128B-swizzled: slab*rows*128 + (r/8)*1024 + (r%8)*128 + ((c^(r%8))*16)
+__device__ __forceinline__ uint32_t sw_off(int rows, int r, int c4) {
+  const int slab = c4 >> 3, c = c4 & 7;
+  return (uint32_t)(slab * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
 }  // namespace yr
