@@ -212,6 +212,50 @@ int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
 int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * CDAE  (models/cdae.py, loss.py:7-16 NSBCELoss, trainers/cdae_trainer.py) — BASELINE config 4
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Parameters in the reference's own layouts (state_dict keys hidden_layer.{weight,bias}, user_nodes.weight,
+ * output_layer.{weight,bias}); the same struct describes gradients and Adam moments. */
+typedef struct yr_cdae_tensors {
+  float* Wh;   /* hidden_layer.weight [h x nI]  */
+  float* bh;   /* hidden_layer.bias   [h]       */
+  float* Vu;   /* user_nodes.weight   [nU x h]  */
+  float* Wo;   /* output_layer.weight [nI x h]  */
+  float* bo;   /* output_layer.bias   [nI]      */
+} yr_cdae_tensors;
+
+size_t yr_cdae_ws_bytes(int64_t B, int64_t nI);
+
+/* z[b,:] = sigmoid( Wh . (x[b,:] * keep[b,:]) + bh + Vu[uid[b]] )   (models/cdae.py:46-51; keep == NULL in eval
+ * mode, else the dropout multiplier 0 or 1/(1-p) the caller drew — nn.Dropout's mask is supplied, not re-drawn).
+ * x is the dense [B x nI] multi-hot `input_mask` exactly as the reference's DataLoader yields it.
+ * z_out is [B x ldz] (ldz >= h): columns h..ldz-1 are set to 1, 0, 0, ... so that [z | 1] . [Wo | bo]^T is the
+ * output logit (used to feed the full-catalog top-K kernels). */
+int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, const int64_t* uid, const float* x,
+                   const float* keep, int64_t B, float* z_out, int64_t ldz, void* ws, size_t ws_bytes,
+                   int32_t* err, yr_stream stream);
+
+/* pred[b,i] = sigmoid( z[b,:] . Wo[i,:] + bo[i] )  — CDAE.forward's dense output (models/cdae.py:52). */
+int yr_cdae_output(const yr_cdae_tensors* P, int64_t nI, int h, const float* z, int64_t ldz, int64_t B,
+                   float* pred, yr_stream stream);
+
+/* One CDAETrainer.train step (trainers/cdae_trainer.py:39-52) or, with opt == NULL, the loss-only pass of
+ * validate (:62-70): forward, NSBCELoss over the positions where target + negative_mask != 0 (loss.py:12-16, BCE
+ * mean, logs clamped at -100 like torch), backward restricted to those positions, dense optimizer step over all
+ * five tensors. grads must be all-zero on entry and are all-zero on exit. loss (device double[2]): [0] += batch
+ * loss, [1] scratch. step_loss may be NULL. `target` is input_mask for train, input_mask + valid_mask for validate. */
+int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                 const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h,
+                 const int64_t* uid, const float* x, const float* keep, const float* target,
+                 const float* negative_mask, int64_t B, double* loss, float* step_loss,
+                 void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+
+/* NSBCELoss.forward on dense tensors (loss.py:12-16): mean BCE over positions where target + negative_mask != 0. */
+int yr_nsbce_loss(const float* pred, const float* target, const float* negative_mask, int64_t n, float* loss,
+                  void* ws, size_t ws_bytes, yr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Full-catalog evaluation (trainers/mf_trainer.py:134-178, metric.py)
  * ---------------------------------------------------------------------------------------------- */
 

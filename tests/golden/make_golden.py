@@ -250,9 +250,92 @@ def golden_ngcf():
     print("ngcf_small: losses", out["ngcf_0_losses"])
 
 
+# ------------------------------------------------------------------------------------------------
+class _SuppliedDropout(torch.nn.Module):
+    """Stands in for model.dropout_layer so that the fixture records the exact nn.Dropout multipliers used."""
+
+    def __init__(self, keeps):
+        super().__init__()
+        self.keeps, self.i = keeps, 0
+
+    def forward(self, x):
+        if not self.training:
+            return x
+        k = self.keeps[self.i]
+        self.i += 1
+        return x * k
+
+
+def golden_cdae():
+    from trainers.cdae_trainer import CDAETrainer as RefCDAETrainer
+    rng = np.random.default_rng(21)
+    nU, nI, B, p = 80, 112, 16, 0.6
+    inter = syn.make_interactions(num_users=nU, num_items=nI, nnz=1400, seed=6, n_clusters=4)
+    dense = np.zeros((nU, nI), np.float32)
+    dense[inter.user, inter.item] = 1.0
+    # per-user split into train / valid / test masks in the spirit of cdae_data_pipeline.py:18-52
+    train_m, valid_m, test_m = np.zeros_like(dense), np.zeros_like(dense), np.zeros_like(dense)
+    for u in range(nU):
+        h = rng.permutation(np.nonzero(dense[u])[0])
+        tr, te = np.split(h, [int(0.8 * len(h))])
+        tr, va = np.split(tr, [int(0.75 * len(tr))])
+        train_m[u, tr], valid_m[u, va], test_m[u, te] = 1, 1, 1
+
+    def neg_mask(pos):
+        out = np.zeros_like(pos)
+        for u in range(pos.shape[0]):
+            cand = np.nonzero(1 - pos[u])[0]
+            out[u, rng.choice(cand, min(len(cand), int(pos[u].sum()) * 5), replace=False)] = 1.0
+        return out
+
+    users = np.arange(nU)
+    neg_train, neg_valid = neg_mask(train_m), neg_mask(train_m + valid_m)
+    n_steps = 3
+    keeps = [(rng.random((B, nI)) >= p).astype(np.float32) / np.float32(1 - p) for _ in range(n_steps)]
+    t = torch.from_numpy
+
+    def batches(masks, lo=0, hi=None):
+        hi = hi or nU
+        out = []
+        for s in range(lo, hi, B):
+            sl = slice(s, min(s + B, hi))
+            out.append({k: (t(users[sl].copy()) if k == "user_id" else t(v[sl].copy())) for k, v in masks.items()})
+        return out
+
+    out = dict(nU=nU, nI=nI, B=B, train_mask=train_m, valid_mask=valid_m, test_mask=test_m, neg_train=neg_train,
+               neg_valid=neg_valid, keeps=np.stack(keeps))
+    tb = batches({"user_id": None, "input_mask": train_m, "negative_mask": neg_train})[:n_steps]
+    vb = batches({"user_id": None, "input_mask": train_m, "valid_mask": valid_m, "negative_mask": neg_valid})
+    eb = batches({"user_id": None, "input_mask": train_m + valid_m, "test_mask": test_m})
+    for ci, (name, lr) in enumerate([("adam", 1e-2), ("sgd", 0.5)]):
+        torch.manual_seed(42)
+        tr = RefCDAETrainer(cfg(optimizer=name, lr=lr, hidden_size=64, corruption_level=p, hidden_activation="sigmoid",
+                                output_activation="sigmoid", negative_sampling=True, loss_name="bce"), nI, nU)
+        tr.model.dropout_layer = _SuppliedDropout([t(k) for k in keeps])
+        if ci == 0:
+            for k, v in tr.model.state_dict().items():
+                out["init_" + k] = v.detach().numpy().copy()
+            tr.model.eval()
+            out["pred_eval0"] = tr.model(t(users[:B].copy()), t(train_m[:B].copy())).detach().numpy()
+            out["valid0"] = np.array(tr.validate(vb))
+        losses = [tr.train([b]) for b in tb]
+        out[f"c{ci}_name"], out[f"c{ci}_lr"], out[f"c{ci}_losses"] = name, lr, np.array(losses)
+        for k, v in tr.model.state_dict().items():
+            out[f"c{ci}_final_" + k] = v.detach().numpy().copy()
+        if ci == 0:
+            out["valid_after"] = np.array(tr.validate(vb))
+            out["test_after"] = np.array(tr.evaluate(eb))
+    np.savez_compressed(os.path.join(HERE, "cdae_small.npz"), **out)
+    print("cdae_small: losses", out["c0_losses"], "valid", out["valid_after"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cdae":
+        golden_cdae()
+        sys.exit(0)
     golden_metrics()
     golden_split_and_mf()
     golden_ngcf()
+    golden_cdae()
     print("fixtures written to", HERE)
     os.system(f"ls -la {HERE}")

@@ -1,0 +1,122 @@
+"""CDAE (BASELINE config 4): the torch-CPU port is pinned to the real reference (CPU test); the CUDA path is checked
+against the reference fixture and the port (GPU tests)."""
+from math import isclose
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port as tp
+from util import RTOL, cfg, load_npz, rel_err
+
+KEYS = ["hidden_layer.weight", "hidden_layer.bias", "user_nodes.weight", "output_layer.weight", "output_layer.bias"]
+
+
+def _fixture():
+    g = load_npz("cdae_small.npz")
+    nU, nI, B = int(g["nU"]), int(g["nI"]), int(g["B"])
+    t = torch.from_numpy
+    users = np.arange(nU)
+
+    def batches(masks, n=None):
+        out = []
+        for s in range(0, nU, B):
+            sl = slice(s, min(s + B, nU))
+            out.append({k: (t(users[sl].copy()) if v is None else t(v[sl].copy())) for k, v in masks.items()})
+        return out[:n] if n else out
+
+    tb = batches({"user_id": None, "input_mask": g["train_mask"], "negative_mask": g["neg_train"]}, 3)
+    vb = batches({"user_id": None, "input_mask": g["train_mask"], "valid_mask": g["valid_mask"], "negative_mask": g["neg_valid"]})
+    eb = batches({"user_id": None, "input_mask": g["train_mask"] + g["valid_mask"], "test_mask": g["test_mask"]})
+    keeps = [t(k.copy()) for k in g["keeps"]]
+    init = {k: t(g["init_" + k].copy()) for k in KEYS}
+    return g, nU, nI, B, tb, vb, eb, keeps, init
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_port_matches_reference(ci):
+    g, nU, nI, B, tb, vb, eb, keeps, init = _fixture()
+    port = tp.CDAEPort(init, str(g[f"c{ci}_name"]), float(g[f"c{ci}_lr"]))
+    if ci == 0:
+        pred = port.forward(tb[0]["user_id"], tb[0]["input_mask"]).detach().numpy()
+        assert rel_err(pred, g["pred_eval0"]) < 1e-6
+        assert np.allclose(port.validate(vb), g["valid0"], rtol=1e-6)
+    _, steps = port.train(tb, keeps)
+    assert rel_err(steps, g[f"c{ci}_losses"]) < 1e-6
+    for k, v in port.state_dict().items():
+        assert rel_err(v.detach().numpy(), g[f"c{ci}_final_" + k]) < 1e-5, k
+    if ci == 0:
+        assert np.allclose(port.validate(vb), g["valid_after"], rtol=1e-5)
+        assert np.allclose(port.evaluate(eb), g["test_after"], rtol=1e-6)
+
+
+def _trainer(g, nU, nI, init, name, lr):
+    from yelprecommendation_b200.trainers import CDAETrainer
+    tr = CDAETrainer(cfg(optimizer=name, lr=lr, hidden_size=64, corruption_level=0.6, hidden_activation="sigmoid",
+                         output_activation="sigmoid", negative_sampling=True, loss_name="bce"), nI, nU)
+    assert sorted(tr.model.state_dict().keys()) == sorted(KEYS)
+    tr.model.load_state_dict(init)
+    return tr
+
+
+@pytest.mark.gpu
+def test_forward_and_loss_vs_reference():
+    from yelprecommendation_b200.loss import NSBCELoss
+    g, nU, nI, B, tb, vb, eb, keeps, init = _fixture()
+    tr = _trainer(g, nU, nI, init, "adam", 1e-2)
+    tr.model.eval()
+    pred = tr.model(tb[0]["user_id"], tb[0]["input_mask"])
+    assert rel_err(pred.cpu().numpy(), g["pred_eval0"]) < RTOL
+    ref = tp.nsbce_loss(torch.from_numpy(g["pred_eval0"]), tb[0]["input_mask"], tb[0]["negative_mask"]).item()
+    got = NSBCELoss()(pred, tb[0]["input_mask"].cuda(), tb[0]["negative_mask"].cuda()).item()
+    assert isclose(got, ref, rel_tol=RTOL)
+    # training mode with a supplied dropout multiplier
+    tr.model.train()
+    port = tp.CDAEPort(init)
+    want = port.forward(tb[0]["user_id"], tb[0]["input_mask"], keeps[0]).detach().numpy()
+    got = tr.model(tb[0]["user_id"], tb[0]["input_mask"], keep=keeps[0].cuda()).cpu().numpy()
+    assert rel_err(got, want) < RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", [0, 1])
+def test_train_validate_evaluate_vs_reference(ci):
+    g, nU, nI, B, tb, vb, eb, keeps, init = _fixture()
+    tr = _trainer(g, nU, nI, init, str(g[f"c{ci}_name"]), float(g[f"c{ci}_lr"]))
+    if ci == 0:
+        v0 = tr.validate(vb)
+        assert isclose(v0[0], float(g["valid0"][0]), rel_tol=RTOL)
+        assert np.allclose(v0[1:], g["valid0"][1:], rtol=0.1, atol=2e-3)      # ranking metrics: ties aside
+    total = tr.train(tb, keeps=keeps)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), g[f"c{ci}_losses"]) < RTOL
+    assert isclose(total, float(np.sum(g[f"c{ci}_losses"])), rel_tol=RTOL)
+    for k, v in tr.model.state_dict().items():
+        assert rel_err(v.cpu().numpy(), g[f"c{ci}_final_" + k]) < 2e-5, k
+    b = tr._bufs
+    assert all(int(torch.count_nonzero(t).item()) == 0 for t in b["grads"])            # grads re-zeroed
+    if ci == 0:
+        va = tr.validate(vb)
+        assert isclose(va[0], float(g["valid_after"][0]), rel_tol=2e-5)
+        te = tr.evaluate(eb)
+        # exact ranking check against the port's per-row top-10 (ties in the port follow NumPy)
+        port = tp.CDAEPort({k: v.detach().cpu() for k, v in tr.model.state_dict().items()})
+        (pm, ppred) = port._rank(eb, "test_mask")
+        same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ppred[r]) for r in range(nU))
+        assert same >= nU - max(2, nU // 20)
+        assert np.allclose(te, pm, rtol=0.08, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_default_dropout_draw_and_bad_ids():
+    g, nU, nI, B, tb, vb, eb, keeps, init = _fixture()
+    tr = _trainer(g, nU, nI, init, "adam", 1e-3)
+    loss = tr.train(tb)                                    # masks drawn on the device
+    assert np.isfinite(loss) and loss > 0
+    k = tr.model.draw_keep(torch.ones(64, nI, device="cuda"))
+    vals = torch.unique(k).cpu().numpy()
+    assert set(np.round(vals, 4)) <= {0.0, 2.5} and 0.3 < float((k > 0).float().mean()) < 0.5
+    bad = dict(tb[0])
+    bad["user_id"] = bad["user_id"].clone()
+    bad["user_id"][0] = nU
+    with pytest.raises(IndexError):
+        tr.train([bad])

@@ -25,6 +25,7 @@ SYMBOLS = (
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
+    "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_output", "yr_cdae_step", "yr_nsbce_loss",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -61,6 +62,10 @@ class YrCsr(C.Structure):
                 ("n_split_rows", C.c_int32),
                 ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p),
                 ("split_count", C.c_void_p)]
+
+
+class YrCdaeTensors(C.Structure):
+    _fields_ = [("Wh", C.c_void_p), ("bh", C.c_void_p), ("Vu", C.c_void_p), ("Wo", C.c_void_p), ("bo", C.c_void_p)]
 
 
 YR_NGCF_MAX_LAYERS = 7
@@ -128,6 +133,13 @@ def load() -> C.CDLL:
         "yr_eval_ws_bytes": (sz, [i64, i32, i32]),
         "yr_eval_topk_metrics": (C.c_int, [p, i64, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
                                            p, p, p, p, p, sz, p, p]),
+        "yr_cdae_ws_bytes": (sz, [i64, i64]),
+        "yr_cdae_hidden": (C.c_int, [C.POINTER(YrCdaeTensors), i64, i64, i32, p, p, p, i64, p, i64, p, sz, p, p]),
+        "yr_cdae_output": (C.c_int, [C.POINTER(YrCdaeTensors), i64, i32, p, i64, i64, p, p]),
+        "yr_cdae_step": (C.c_int, [C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors),
+                                   C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, p, p, p, p, p, i64, p, p,
+                                   p, sz, p, p]),
+        "yr_nsbce_loss": (C.c_int, [p, p, p, i64, p, p, sz, p]),
         "yr_ngcf_set_dense_mode": (C.c_int, [i32]),
         "yr_ngcf_get_dense_mode": (C.c_int, []),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),

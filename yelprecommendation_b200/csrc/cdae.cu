@@ -1,0 +1,330 @@
+// CDAE kernels (sm_100a) — BASELINE config 4: the reference's denoising auto-encoder
+//   models/cdae.py:46-52     out = sigmoid(Wo . sigmoid(Wh . dropout(x) + bh + Vu[u]) + bo)
+//   loss.py:7-16             NSBCELoss: BCE (mean) over the positions where target + negative_mask != 0
+//   trainers/cdae_trainer.py:36-54 (train step), :56-70 (validate loss)
+// The reference pushes dense [B x nI] tensors through two nn.Linear layers and materialises the dense output.
+// Here: the multi-hot input and the loss positions are compacted once per batch (ordered, deterministic), the first
+// layer is a gather-sum over the ~|x| active columns, logits are evaluated ONLY at the loss positions, and the
+// backward pass touches only those positions and the active columns — the dense [B x nI] output never exists during
+// training. The optimizer keeps torch's dense semantics (every element of every tensor is stepped).
+#include "common.cuh"
+
+namespace yr {
+
+constexpr int kCdaeThreads = 256;
+
+struct CdaeWs {
+  int32_t* xin_cnt;   // [B]
+  int32_t* tgt_cnt;   // [B]
+  int32_t* total;     // [1] number of loss positions in the batch
+  int32_t* xin_idx;   // [B x nI]
+  float* xin_val;     // [B x nI]
+  int32_t* tgt_idx;   // [B x nI]
+  float* tgt_val;     // [B x nI]
+  float* z;           // [B x h]
+};
+
+static size_t cdae_ws_layout(int64_t B, int64_t nI, void* base, CdaeWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_xc = take((size_t)B * 4), o_tc = take((size_t)B * 4), o_tot = take(16);
+  const size_t o_xi = take((size_t)B * nI * 4), o_xv = take((size_t)B * nI * 4);
+  const size_t o_ti = take((size_t)B * nI * 4), o_tv = take((size_t)B * nI * 4);
+  const size_t o_z = take((size_t)B * 256 * 4);
+  if (w && base) {
+    unsigned char* p = (unsigned char*)base;
+    w->xin_cnt = (int32_t*)(p + o_xc); w->tgt_cnt = (int32_t*)(p + o_tc); w->total = (int32_t*)(p + o_tot);
+    w->xin_idx = (int32_t*)(p + o_xi); w->xin_val = (float*)(p + o_xv);
+    w->tgt_idx = (int32_t*)(p + o_ti); w->tgt_val = (float*)(p + o_tv); w->z = (float*)(p + o_z);
+  }
+  return off;
+}
+
+// Block per batch row: ordered compaction of (a) the active inputs x*keep != 0 and (b) the loss positions
+// target + negative != 0 (value kept = target). Each warp owns a contiguous segment of the row; two passes.
+__global__ void __launch_bounds__(kCdaeThreads)
+cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep, const float* __restrict__ target,
+                    const float* __restrict__ neg, int64_t nI, CdaeWs w) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kCdaeThreads / 32;
+  const int64_t seg = ((nI + NW - 1) / NW + 31) / 32 * 32;
+  const int64_t s0 = warp * seg, s1 = min(nI, s0 + seg);
+  const float* xr = x + (int64_t)b * nI;
+  const float* kr = keep ? keep + (int64_t)b * nI : nullptr;
+  const float* tr = target ? target + (int64_t)b * nI : nullptr;
+  const float* nr = neg ? neg + (int64_t)b * nI : nullptr;
+  __shared__ int cx[NW], ct[NW];
+  int nx = 0, nt = 0;
+  for (int64_t i0 = s0; i0 < s1; i0 += 32) {
+    const int64_t i = i0 + lane;
+    bool px = false, pt = false;
+    if (i < s1) {
+      const float v = kr ? xr[i] * kr[i] : xr[i];
+      px = v != 0.f;
+      if (tr) pt = (tr[i] + (nr ? nr[i] : 0.f)) != 0.f;
+    }
+    nx += __popc(__ballot_sync(kFull, px));
+    nt += __popc(__ballot_sync(kFull, pt));
+  }
+  if (lane == 0) { cx[warp] = nx; ct[warp] = nt; }
+  __syncthreads();
+  int bx = 0, bt = 0, totx = 0, tott = 0;
+  for (int q = 0; q < NW; ++q) {
+    if (q < warp) { bx += cx[q]; bt += ct[q]; }
+    totx += cx[q]; tott += ct[q];
+  }
+  if (threadIdx.x == 0) {
+    w.xin_cnt[b] = totx;
+    w.tgt_cnt[b] = tott;
+    if (tott) atomicAdd(w.total, tott);
+  }
+  int32_t* xi = w.xin_idx + (int64_t)b * nI;
+  float* xv = w.xin_val + (int64_t)b * nI;
+  int32_t* ti = w.tgt_idx + (int64_t)b * nI;
+  float* tv = w.tgt_val + (int64_t)b * nI;
+  for (int64_t i0 = s0; i0 < s1; i0 += 32) {
+    const int64_t i = i0 + lane;
+    bool px = false, pt = false;
+    float v = 0.f, t = 0.f;
+    if (i < s1) {
+      v = kr ? xr[i] * kr[i] : xr[i];
+      px = v != 0.f;
+      if (tr) { t = tr[i]; pt = (t + (nr ? nr[i] : 0.f)) != 0.f; }
+    }
+    const unsigned mx = __ballot_sync(kFull, px), mt = __ballot_sync(kFull, pt);
+    const unsigned lower = (1u << lane) - 1u;
+    if (px) { const int p = bx + __popc(mx & lower); xi[p] = (int32_t)i; xv[p] = v; }
+    if (pt) { const int p = bt + __popc(mt & lower); ti[p] = (int32_t)i; tv[p] = t; }
+    bx += __popc(mx);
+    bt += __popc(mt);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Block per batch row. H = hidden size (64). Phase 1: hidden activation from the compacted inputs.
+// Phase 2 (targets given): logits at the loss positions, BCE terms, and — if GRAD — every gradient.
+template <int H, bool GRAD>
+__global__ void __launch_bounds__(kCdaeThreads)
+cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, const int64_t* __restrict__ uid,
+                CdaeWs w, bool with_loss, float* __restrict__ z_out, int64_t ldz, double* loss_acc, int32_t* err) {
+  static_assert(H == 64, "row kernel is laid out for hidden_size 64");
+  constexpr int NW = kCdaeThreads / 32;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float part[kCdaeThreads / H][H];   // 4 partial sums per hidden unit
+  __shared__ float z_s[H];
+  __shared__ float dz_s[NW][H];
+  __shared__ double loss_s[NW];
+  int64_t u = uid[b];
+  if (u < 0 || u >= nU) { if (tid == 0 && err) atomicExch(err, 1); u = 0; }
+  const int nx = w.xin_cnt[b];
+  const int32_t* xi = w.xin_idx + (int64_t)b * nI;
+  const float* xv = w.xin_val + (int64_t)b * nI;
+
+  // ---- hidden: z = sigmoid(bh + Vu[u] + sum_j xv_j * Wh[:, xi_j]) ; thread = (group g of 4, unit k of 64)
+  {
+    const int k = tid % H, g = tid / H;
+    float acc = 0.f;
+    for (int j = g; j < nx; j += kCdaeThreads / H) acc = fmaf(xv[j], __ldg(P.Wh + (int64_t)k * nI + xi[j]), acc);
+    part[g][k] = acc;
+  }
+  __syncthreads();
+  if (tid < H) {
+    float pre = P.bh[tid] + P.Vu[u * H + tid];
+    pre += (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    const float z = sigmoidf_(pre);
+    z_s[tid] = z;
+    w.z[(int64_t)b * H + tid] = z;
+    if (z_out) z_out[(int64_t)b * ldz + tid] = z;
+  }
+  if (z_out && tid >= H && tid < ldz) z_out[(int64_t)b * ldz + tid] = (tid == H) ? 1.f : 0.f;
+  __syncthreads();
+  if (!with_loss) return;
+
+  // ---- loss positions: warp per position, lanes hold 2 hidden units each ----
+  const int nt = w.tgt_cnt[b];
+  const int32_t* ti = w.tgt_idx + (int64_t)b * nI;
+  const float* tv = w.tgt_val + (int64_t)b * nI;
+  const float inv_m = 1.f / (float)(*w.total);
+  const float2 zz = make_float2(z_s[2 * lane], z_s[2 * lane + 1]);
+  float2 dz = make_float2(0.f, 0.f);
+  double lsum = 0.0;
+  for (int j = warp; j < nt; j += NW) {
+    const int item = ti[j];
+    const float t = tv[j];
+    const float2 wo = __ldg(reinterpret_cast<const float2*>(P.Wo + (int64_t)item * H) + lane);
+    float logit = warp_sum(fmaf(zz.x, wo.x, zz.y * wo.y)) + __ldg(P.bo + item);
+    const float p = sigmoidf_(logit);
+    // torch.nn.functional.binary_cross_entropy clamps both logs at -100
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
+    lsum += (double)(-(t * lp + (1.f - t) * lq));
+    if (GRAD) {
+      const float dl = (p - t) * inv_m;                        // d loss / d logit (mean over all loss positions)
+      dz.x = fmaf(dl, wo.x, dz.x); dz.y = fmaf(dl, wo.y, dz.y);
+      atomicAdd(reinterpret_cast<float2*>(Gr.Wo + (int64_t)item * H) + lane, make_float2(dl * zz.x, dl * zz.y));
+      if (lane == 0) atomicAdd(Gr.bo + item, dl);
+    }
+  }
+  if (lane == 0) loss_s[warp] = lsum;
+  if (GRAD) { dz_s[warp][2 * lane] = dz.x; dz_s[warp][2 * lane + 1] = dz.y; }
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int q = 0; q < NW; ++q) t += loss_s[q];
+    if (t != 0.0) atomicAdd(loss_acc, t);
+  }
+  if (!GRAD) return;
+  if (tid < H) {
+    float d = 0.f;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) d += dz_s[q][tid];
+    const float z = z_s[tid];
+    const float dpre = d * z * (1.f - z);
+    z_s[tid] = dpre;                                            // reuse: z_s now holds d loss / d pre-activation
+    atomicAdd(Gr.bh + tid, dpre);
+    atomicAdd(Gr.Vu + u * H + tid, dpre);
+  }
+  __syncthreads();
+  {
+    const int k = tid % H, g = tid / H;
+    const float dpre = z_s[k];
+    for (int j = g; j < nx; j += kCdaeThreads / H) atomicAdd(Gr.Wh + (int64_t)k * nI + xi[j], dpre * xv[j]);
+  }
+}
+
+__global__ void cdae_finish_kernel(double* loss, const int32_t* total, float* step_loss) {
+  const float mean = (*total > 0) ? (float)(loss[1] / (double)(*total)) : nanf("");
+  if (step_loss) *step_loss = mean;
+  loss[0] += (double)mean;
+  loss[1] = 0.0;
+}
+
+// pred[b, i] = sigmoid(z[b,:] . Wo[i,:] + bo[i])
+__global__ void __launch_bounds__(256)
+cdae_output_kernel(const float* __restrict__ Wo, const float* __restrict__ bo, int64_t nI, int h,
+                   const float* __restrict__ z, int64_t ldz, float* __restrict__ pred) {
+  extern __shared__ float zs[];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < h; k += blockDim.x) zs[k] = z[(int64_t)b * ldz + k];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nI) return;
+  const float* wr = Wo + i * h;
+  float acc = 0.f;
+  for (int k = 0; k < h; ++k) acc = fmaf(zs[k], __ldg(wr + k), acc);
+  pred[(int64_t)b * nI + i] = sigmoidf_(acc + bo[i]);
+}
+
+__global__ void __launch_bounds__(256)
+nsbce_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ neg,
+             int64_t n, double* acc /* [0] sum, [1] count */) {
+  double s = 0.0, c = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = target[i];
+    if (t + neg[i] != 0.f) {
+      const float p = pred[i];
+      s += (double)(-(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(log1pf(-p), -100.f)));
+      c += 1.0;
+    }
+  }
+  s = warp_sum_d(s); c = warp_sum_d(c);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(acc, s); atomicAdd(acc + 1, c); }
+}
+__global__ void nsbce_finish_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] / acc[1]); }
+
+}  // namespace yr
+
+using namespace yr;
+
+extern "C" size_t yr_cdae_ws_bytes(int64_t B, int64_t nI) { return cdae_ws_layout(B, nI, nullptr, nullptr) + 256; }
+
+static int cdae_tensors_ok(const yr_cdae_tensors* t) {
+  return (t && t->Wh && t->bh && t->Vu && t->Wo && t->bo) ? YR_OK : YR_ERR_BAD_ARG;
+}
+
+extern "C" int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, const int64_t* uid,
+                              const float* x, const float* keep, int64_t B, float* z_out, int64_t ldz, void* ws,
+                              size_t ws_bytes, int32_t* err, yr_stream stream) {
+  if (cdae_tensors_ok(P) || !uid || !x || !z_out || !ws || B <= 0 || nI <= 0 || ldz < h || ldz > 256) return YR_ERR_BAD_ARG;
+  if (h != 64) return YR_ERR_BAD_DIM;
+  if (ws_bytes < yr_cdae_ws_bytes(B, nI)) return YR_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  CdaeWs w;
+  cdae_ws_layout(B, nI, ws, &w);
+  YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
+  cdae_compact_kernel<<<(unsigned)B, kCdaeThreads, 0, s>>>(x, keep, nullptr, nullptr, nI, w);
+  YR_CHECK_LAUNCH();
+  yr_cdae_tensors none = {};
+  cdae_row_kernel<64, false><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, none, nU, nI, uid, w, false, z_out, ldz, nullptr, err);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" int yr_cdae_output(const yr_cdae_tensors* P, int64_t nI, int h, const float* z, int64_t ldz, int64_t B,
+                              float* pred, yr_stream stream) {
+  if (cdae_tensors_ok(P) || !z || !pred || B <= 0 || nI <= 0 || h <= 0 || ldz < h) return YR_ERR_BAD_ARG;
+  dim3 grid((unsigned)((nI + 255) / 256), (unsigned)B);
+  cdae_output_kernel<<<grid, 256, h * sizeof(float), (cudaStream_t)stream>>>(P->Wo, P->bo, nI, h, z, ldz, pred);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                            const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h,
+                            const int64_t* uid, const float* x, const float* keep, const float* target,
+                            const float* negative_mask, int64_t B, double* loss, float* step_loss, void* ws,
+                            size_t ws_bytes, int32_t* err, yr_stream stream) {
+  if (cdae_tensors_ok(P) || !uid || !x || !target || !loss || !ws || B <= 0 || nI <= 0) return YR_ERR_BAD_ARG;
+  if (h != 64) return YR_ERR_BAD_DIM;
+  if (ws_bytes < yr_cdae_ws_bytes(B, nI)) return YR_ERR_WORKSPACE;
+  const bool train = opt != nullptr;
+  if (train) {
+    if (cdae_tensors_ok(grads)) return YR_ERR_BAD_ARG;
+    if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
+    if (opt->kind != YR_OPT_SGD && (cdae_tensors_ok(m) || cdae_tensors_ok(v))) return YR_ERR_BAD_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CdaeWs w;
+  cdae_ws_layout(B, nI, ws, &w);
+  YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
+  cdae_compact_kernel<<<(unsigned)B, kCdaeThreads, 0, s>>>(x, keep, target, negative_mask, nI, w);
+  YR_CHECK_LAUNCH();
+  yr_cdae_tensors none = {};
+  if (train)
+    cdae_row_kernel<64, true><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, *grads, nU, nI, uid, w, true, nullptr, 0, loss + 1, err);
+  else
+    cdae_row_kernel<64, false><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, none, nU, nI, uid, w, true, nullptr, 0, loss + 1, err);
+  YR_CHECK_LAUNCH();
+  cdae_finish_kernel<<<1, 1, 0, s>>>(loss, w.total, step_loss);
+  YR_CHECK_LAUNCH();
+  if (!train) return YR_OK;
+  const bool adam = opt->kind != YR_OPT_SGD;
+  struct { float* p; float* g; float* m; float* v; int64_t n; } ts[5] = {
+      {P->Wh, grads->Wh, adam ? m->Wh : nullptr, adam ? v->Wh : nullptr, (int64_t)h * nI},
+      {P->bh, grads->bh, adam ? m->bh : nullptr, adam ? v->bh : nullptr, (int64_t)h},
+      {P->Vu, grads->Vu, adam ? m->Vu : nullptr, adam ? v->Vu : nullptr, nU * h},
+      {P->Wo, grads->Wo, adam ? m->Wo : nullptr, adam ? v->Wo : nullptr, nI * h},
+      {P->bo, grads->bo, adam ? m->bo : nullptr, adam ? v->bo : nullptr, nI}};
+  for (auto& t : ts) {
+    int rc = yr_dense_opt_step(t.p, t.g, t.m, t.v, t.n, opt, stream);
+    if (rc) return rc;
+    YR_CUDA(cudaMemsetAsync(t.g, 0, sizeof(float) * (size_t)t.n, s));
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_nsbce_loss(const float* pred, const float* target, const float* negative_mask, int64_t n,
+                             float* loss, void* ws, size_t ws_bytes, yr_stream stream) {
+  if (!pred || !target || !negative_mask || !loss || !ws || ws_bytes < 16 || n <= 0) return YR_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  YR_CUDA(cudaMemsetAsync(ws, 0, 16, s));
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > yr_sm_count() * 8) blocks = yr_sm_count() * 8;
+  nsbce_kernel<<<(unsigned)blocks, 256, 0, s>>>(pred, target, negative_mask, n, (double*)ws);
+  YR_CHECK_LAUNCH();
+  nsbce_finish_kernel<<<1, 1, 0, s>>>((const double*)ws, loss);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
