@@ -393,6 +393,81 @@ def main():
         mtr.evaluate(w.ecsr)
         extra["eval_mf"]["e2e_users_per_s"] = w.ecsr.n_eval / (time.perf_counter() - t0)
 
+        # -------------------------------------------------------------- CDAE training (configs[3]), B = 32
+        try:
+            from yelprecommendation_b200.trainers import CDAETrainer
+            nI, Bc, n_b = w.inter.num_items, 32, 48
+            rng = np.random.default_rng(4 + rank)
+            users = rng.choice(w.inter.num_users, Bc * n_b, replace=False)
+            xin = np.zeros((Bc * n_b, nI), np.float32)
+            neg = np.zeros_like(xin)
+            for r, u in enumerate(users):
+                items = w.split.train_items[w.split.train_ptr[u]:w.split.train_ptr[u + 1]]
+                xin[r, items] = 1.0
+                cand = rng.integers(0, nI, size=5 * len(items) + 8)
+                cand = cand[xin[r, cand] == 0][: 5 * len(items)]
+                neg[r, cand] = 1.0
+            ccfg = cfg(hidden_size=64, corruption_level=0.6, hidden_activation="sigmoid", output_activation="sigmoid",
+                       negative_sampling=True, loss_name="bce", lr=1e-4, optimizer="adam")
+            torch.manual_seed(42)
+            ctr = CDAETrainer(ccfg, nI, w.inter.num_users)
+            hb = [{"user_id": torch.from_numpy(users[s:s + Bc].copy()), "input_mask": torch.from_numpy(xin[s:s + Bc]),
+                   "negative_mask": torch.from_numpy(neg[s:s + Bc])} for s in range(0, Bc * n_b, Bc)]
+            db = [{k: v.to(dev) for k, v in b.items()} for b in hb]
+            ctr.train(db[:4])
+            barrier()
+            ms_c = max_over_ranks(timed(lambda i: ctr.train(db), 1))
+            t0 = time.perf_counter()
+            ctr.train(hb)                                   # host tensors: H2D of the dense masks every step
+            torch.cuda.synchronize()
+            e2e_c = time.perf_counter() - t0
+            extra["cdae_train"] = {"value": world * Bc * n_b / (ms_c * 1e-3), "unit": "users/s", "ms_per_step": ms_c / n_b,
+                                   "batch": Bc, "e2e_value": world * Bc * n_b / e2e_c,
+                                   "h2d_bytes_per_step": 2 * Bc * nI * 4,
+                                   "note": "masks resident in HBM for `value`; e2e ships the dense [32 x 38,048] input/negative "
+                                           "masks the reference's CDAEDataset yields"}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                from oracle.torch_port import CDAEPort
+                port = CDAEPort({k: v.detach().cpu() for k, v in ctr.model.state_dict().items()}, "adam", 1e-4)
+                keeps = [(torch.rand(Bc, nI) >= 0.6).float() / 0.4 for _ in range(12)]
+                port.train(hb[:2], keeps[:2])
+                t0 = time.perf_counter()
+                port.train(hb[2:12], keeps[2:12])
+                extra["cdae_train"]["cpu_port_users_per_s"] = 10 * Bc / (time.perf_counter() - t0)
+            del xin, neg, hb, db
+        except Exception as ex:   # the CDAE row must not take the headline down
+            extra["cdae_train"] = {"error": repr(ex)}
+
+        # -------------------------------------------------------------- row-sharded BPR-MF (configs[4] shape), strong-scaled
+        try:
+            from yelprecommendation_b200.trainers.sharded_mf_trainer import ShardedMFTrainer
+            torch.cuda.empty_cache()
+            nU5, nI5, d5, n5 = 10_000_000, 2_000_000, 128, 24
+            g5 = torch.Generator(device=dev).manual_seed(5)          # same triples on every rank
+            su5 = torch.randint(0, nU5, (n5 + 4, B), device=dev, generator=g5)
+            sp5 = torch.randint(0, nI5, (n5 + 4, B), device=dev, generator=g5)
+            sn5 = torch.randint(0, nI5, (n5 + 4, B), device=dev, generator=g5)
+            for oname in ("sgd", "adam"):
+                str5 = ShardedMFTrainer(cfg(embed_size=d5, optimizer=oname), nI5, nU5)
+                acc5 = torch.zeros(1, device=dev, dtype=torch.float64)
+                for i in range(4):
+                    str5.train_step(su5[i], sp5[i], sn5[i], acc5)
+                barrier()
+                ms5 = max_over_ranks(timed(lambda i: str5.train_step(su5[4 + i], sp5[4 + i], sn5[4 + i], acc5), n5)) / n5
+                rows_local = (str5.u1 - str5.u0) + (str5.i1 - str5.i0)
+                # dense-semantics Adam streams p, g, m, v in and p, m, v (+ cleared g) out for every local row
+                alg5 = 3 * B * d5 * 4 * 4 + (rows_local * d5 * 4 * 8 if oname != "sgd" else 3 * B * d5 * 4 * 3)
+                extra[f"mf_sharded_{oname}"] = {
+                    "value": B / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "scaling": "strong",
+                    "tables": f"{nU5:,}u x {nI5:,}i x d{d5} row-sharded over {world} GPU(s)",
+                    "alg_bytes_per_step_per_gpu": alg5, "hbm_frac": alg5 / (ms5 * 1e-3) / 1e9 / pk["hbm"],
+                    "collectives": "none (1 GPU)" if world == 1 else "all_reduce(3B x d rows) + all_gather(3B x d grad rows) per step, NCCL",
+                    "loss_mean": float(acc5.item()) / ((n5 + 4) * B) * (world if world > 1 else 1)}
+                del str5
+                torch.cuda.empty_cache()
+        except Exception as ex:
+            extra["mf_sharded"] = {"error": repr(ex)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.torch_port import NGCFPort

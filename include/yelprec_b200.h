@@ -212,6 +212,45 @@ int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
 int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row-sharded BPR-MF (BASELINE config 5): each rank owns a contiguous block of user rows and of item rows
+ * (and their optimizer state). One step = gather owned rows -> all-reduce (NCCL, by the caller) -> per-rank slice
+ * of triples -> all-gather of the slice gradients (NCCL) -> owner-side update. The library provides the three
+ * device-side pieces; the collectives stay with the caller (torch.distributed / NCCL over NVLink).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out[j*out_ld .. +d) = T_local[ids[j] - row0, :] if row0 <= ids[j] < row1, else zeros.  Every id must fall in
+ * exactly one rank's [row0,row1), so the SUM all-reduce of `out` over ranks is the exact gather of all rows.
+ * ids outside [0, n_rows_global) set *err. */
+int yr_shard_gather_rows(const float* T_local, int64_t row0, int64_t row1, int64_t n_rows_global, int d,
+                         const int64_t* ids, int64_t n, float* out, int64_t out_ld, int32_t* err, yr_stream stream);
+
+/* R, G: [B x 3 x d] rows of (user, pos, neg) per triple. For triples b in [b0,b1): x = u.p - u.n, the BPR loss term
+ * is added to *loss_acc (sum, not mean) and G[b] = (g*(p-n), g*u, -g*u) with g = -sigmoid(-x)/B (mean over the GLOBAL
+ * batch B). Triples outside [b0,b1) are not touched. */
+int yr_bpr_rows_grad(const float* R, int d, int64_t B, int64_t b0, int64_t b1, float* G, double* loss_acc,
+                     yr_stream stream);
+
+/* Owner-side update of one table shard, in two calls so that several id lists (pos and neg items) feed ONE optimizer
+ * step: yr_shard_accumulate adds the gradient rows G[j*g_ld .. +d) of every j with row0 <= ids[j] < row1 into the shard's
+ * scratch (duplicates summed); yr_shard_step then performs one optimizer step per row with torch's dense semantics
+ * over the shard (SGD with wd = 0 touches only the accumulated rows; max_rows >= number of accumulated ids sizes its
+ * grid). gscratch [rows_local x d], flags [rows_local] and counters (>= 64 bytes) must be all-zero on first use and
+ * are all-zero again after yr_shard_step; rows_list needs one entry per accumulated id. */
+typedef struct yr_shard_state {
+  float* T;            /* [rows_local x d] parameters of this shard */
+  float *m, *v;        /* Adam moments (NULL for SGD) */
+  float* gscratch;
+  int32_t* flags;
+  int32_t* rows_list;
+  int32_t* counters;
+  int64_t row0, row1;
+  int32_t d;
+} yr_shard_state;
+int yr_shard_accumulate(const yr_shard_state* st, const yr_opt* opt, const int64_t* ids, int64_t n, const float* G,
+                        int64_t g_ld, yr_stream stream);
+int yr_shard_step(const yr_shard_state* st, const yr_opt* opt, int64_t max_rows, yr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CDAE  (models/cdae.py, loss.py:7-16 NSBCELoss, trainers/cdae_trainer.py) — BASELINE config 4
  * ---------------------------------------------------------------------------------------------- */
 

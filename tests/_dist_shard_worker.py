@@ -1,0 +1,107 @@
+"""world_size-2 gloo worker for test_host_logic: drives ShardedMFTrainer's collective choreography (owner gather ->
+all-reduce -> sliced gradient rows -> all-gather -> owner accumulate + step) with a CPU restatement of the four
+device-side pieces, and checks the gathered tables and the loss against the oracle's single-process MFPort.
+On GPUs the same class runs with CabiShardKernels (tests/test_gpu_shard.py)."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.torch_port import MFPort                                              # noqa: E402
+from yelprecommendation_b200 import _cabi                                          # noqa: E402
+from yelprecommendation_b200.data import synthetic as syn                          # noqa: E402
+from yelprecommendation_b200.trainers.sharded_mf_trainer import ShardedMFTrainer   # noqa: E402
+
+
+class CpuShardKernels:
+    """Semantics of yr_shard_gather_rows / yr_bpr_rows_grad / yr_shard_accumulate / yr_shard_step on CPU tensors
+    (include/yelprec_b200.h). Test infrastructure only."""
+
+    def gather_rows(self, s, total, ids, R, which, err):
+        if bool(((ids < 0) | (ids >= total)).any()):
+            err.fill_(1)
+        own = (ids >= s["lo"]) & (ids < s["hi"])
+        R[:, which, :] = 0
+        R[own, which, :] = s["T"][ids[own] - s["lo"]]
+
+    def rows_grad(self, R, B, b0, b1, Gs, loss_acc):
+        u, p, n = R[b0:b1, 0], R[b0:b1, 1], R[b0:b1, 2]
+        x = (u * p).sum(1) - (u * n).sum(1)
+        loss_acc += (-F.logsigmoid(x)).double().sum()
+        g = (-torch.sigmoid(-x) / B).unsqueeze(1)
+        Gs[: b1 - b0, 0] = g * p - g * n
+        Gs[: b1 - b0, 1] = g * u
+        Gs[: b1 - b0, 2] = -(g * u)
+
+    def accumulate(self, s, opt, ids, G, which):
+        own = (ids >= s["lo"]) & (ids < s["hi"])
+        j = torch.nonzero(own).flatten()
+        r = ids[j] - s["lo"]
+        s["g"].index_add_(0, r, G[j, which])
+        s["flags"][r] = 1
+
+    def step(self, s, opt, max_rows, d):
+        kind = {v: k for k, v in _cabi.OPT_KINDS.items()}[opt.kind]
+        n = s["hi"] - s["lo"]
+        T, g = s["T"], s["g"][:n]
+        if kind == "sgd":
+            T -= opt.lr * (g + opt.weight_decay * T)
+        else:
+            if kind == "adam":
+                g = g + opt.weight_decay * T
+            else:
+                T *= 1 - opt.lr * opt.weight_decay
+            m, v = s["m"][:n], s["v"][:n]
+            m.mul_(opt.beta1).add_(g, alpha=1 - opt.beta1)
+            v.mul_(opt.beta2).addcmul_(g, g, value=1 - opt.beta2)
+            bc1, bc2 = 1 - opt.beta1 ** opt.step, 1 - opt.beta2 ** opt.step
+            T.addcdiv_(m, (v.sqrt() / np.sqrt(bc2)).add_(opt.eps), value=-opt.lr / bc1)
+        s["g"].zero_()
+        s["flags"].zero_()
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    inter = syn.make_interactions(num_users=301, num_items=157, nnz=5000, seed=11, n_clusters=4)
+    split = syn.split_per_user(inter, seed=42)
+    U0, V0 = (torch.from_numpy(np.ascontiguousarray(a)) for a in syn.planted_embeddings(inter, d=32, seed=5))
+    u, p, n = syn.sample_triples(split, inter.num_items, seed=9)
+    batches = syn.to_batches(u, p, n, 509)[:4]          # 509: not a multiple of world -> ragged slices
+    for optname, lr, wd in (("sgd", 0.05, 0.0), ("adam", 1e-2, 1e-4), ("adamw", 1e-2, 1e-2)):
+        cfg = SimpleNamespace(embed_size=32, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+        tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0), device="cpu", kernels=CpuShardKernels())
+        assert (tr.u1 - tr.u0) in (150, 151) and (tr.i1 - tr.i0) in (78, 79)
+        loss = tr.train(batches)
+        U, V = tr.gather_tables()
+        port = MFPort(U0, V0, optimizer=optname, lr=lr, weight_decay=wd)
+        ref_loss, _ = port.train(batches)
+        for got, ref in ((U, port.user.weight.detach()), (V, port.item.weight.detach())):
+            assert got.shape == ref.shape
+            rel = float((got - ref).norm() / ref.norm())
+            assert rel < 2e-6, (optname, rel)
+        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+    # out-of-range id -> IndexError on every rank (nn.Embedding behaviour)
+    bad = dict(batches[0])
+    bad["pos_item"] = bad["pos_item"].clone()
+    bad["pos_item"][3] = inter.num_items
+    try:
+        tr.train([bad])
+        raise AssertionError("expected IndexError")
+    except IndexError:
+        pass
+    dist.barrier()
+    if rank == 0:
+        print("DIST_SHARD_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -88,3 +88,15 @@ def test_user_sharded_metric_reduction_gloo_world2():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_EVAL_OK" in r.stdout
+
+
+def test_row_sharded_mf_choreography_gloo_world2():
+    """BASELINE config 5 path: ShardedMFTrainer's gather / all-reduce / sliced grads / all-gather / owner update
+    over 2 ranks equals the oracle's single-process MFPort (SGD, Adam + L2, AdamW), ragged batch, OOB id -> IndexError."""
+    script = os.path.join(ROOT, "tests", "_dist_shard_worker.py")
+    port = 31500 + os.getpid() % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), script],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DIST_SHARD_OK" in r.stdout

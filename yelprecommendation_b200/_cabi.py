@@ -26,6 +26,7 @@ SYMBOLS = (
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_output", "yr_cdae_step", "yr_nsbce_loss",
+    "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -62,6 +63,12 @@ class YrCsr(C.Structure):
                 ("n_split_rows", C.c_int32),
                 ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p),
                 ("split_count", C.c_void_p)]
+
+
+class YrShardState(C.Structure):
+    _fields_ = [("T", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("gscratch", C.c_void_p),
+                ("flags", C.c_void_p), ("rows_list", C.c_void_p), ("counters", C.c_void_p),
+                ("row0", C.c_int64), ("row1", C.c_int64), ("d", C.c_int32)]
 
 
 class YrCdaeTensors(C.Structure):
@@ -140,6 +147,10 @@ def load() -> C.CDLL:
                                    C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, p, p, p, p, p, i64, p, p,
                                    p, sz, p, p]),
         "yr_nsbce_loss": (C.c_int, [p, p, p, i64, p, p, sz, p]),
+        "yr_shard_gather_rows": (C.c_int, [p, i64, i64, i64, i32, p, i64, p, i64, p, p]),
+        "yr_bpr_rows_grad": (C.c_int, [p, i32, i64, i64, i64, p, p, p]),
+        "yr_shard_accumulate": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, i64, p, i64, p]),
+        "yr_shard_step": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), i64, p]),
         "yr_ngcf_set_dense_mode": (C.c_int, [i32]),
         "yr_ngcf_get_dense_mode": (C.c_int, []),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),

@@ -21,7 +21,7 @@ constexpr int kFwdTM = 128;
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ W1,
-                         const float* __restrict__ W2, float slope, int64_t n, float* __restrict__ Eout, int n_pass) {
+                         const float* __restrict__ W2, float slope, int64_t n, float* __restrict__ Eout) {
   constexpr int D = 64;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
@@ -156,7 +156,7 @@ ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
       const uint32_t tacc = tmem_base + acc * D;
       uint32_t first = 1;
 #pragma unroll 1
-      for (int p = 0; p < n_pass; ++p) {
+      for (int p = 0; p < 6; ++p) {
         const uint32_t abase = s2u(A[pa[p]]), bbase = s2u(B[pb[p]]);
         for (int sl = 0; sl < 2; ++sl) {
           const uint64_t ad = sw128_desc(abase + sl * kFwdTM * 128);
@@ -195,7 +195,7 @@ int yr_ngcf_dense_fwd_tc_launch(const float* E, const float* LE, const float* W1
   const int64_t n_tiles = (n + kFwdTM - 1) / kFwdTM;
   int64_t grid = yr_sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  ngcf_dense_fwd_tc_kernel<<<(unsigned)grid, kFwdThreads, smem, s>>>(E, LE, W1, W2, slope, n, Eout, getenv("YR_DBG_PASSES") ? atoi(getenv("YR_DBG_PASSES")) : 6);
+  ngcf_dense_fwd_tc_kernel<<<(unsigned)grid, kFwdThreads, smem, s>>>(E, LE, W1, W2, slope, n, Eout);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }

@@ -5,7 +5,8 @@
 // LPR = d/4 lanes owns a chunk (d = 64: half a warp, two chunks per warp), every lane carries one float4 of the
 // row, so a neighbour row is ONE 256-byte request per group and 8 of them are kept in flight per group. Chunk
 // descriptors are one 16-byte load. fma chain in CSR order inside a chunk; chunks of split rows store a partial
-// that spmm_fixup_kernel adds left to right (the oracle restates exactly this order -> bit-exact).
+// and bump the row's split_count; the LAST chunk to arrive (atomic counter, threadfence) adds the row's partials left to
+// right in the same launch, so the sum order is fixed whatever the arrival order (the oracle restates it -> bit-exact).
 //
 // At Yelp shape X (17.85 MB) is L2-resident; the 3.12 M gathered rows are 800 MB of L2->SM traffic per SpMM
 // against 61 MB of algorithmic HBM traffic, so this kernel lives on L2 latency / bandwidth, not on HBM.
