@@ -164,6 +164,16 @@ int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, 
                       float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
                       yr_stream stream);
 
+/* The dense halves of the two calls above on n rows, WITHOUT the SpMM (models/ngcf.py:65-72 and its autograd):
+ * the row-sharded trainer (BASELINE config 5) runs the SpMM on its row block of L against the all-gathered operand
+ * and these on its local rows. yr_ngcf_dense_bwd: G += dS + dP*LE, T = dS + dP*E, dW1/dW2 overwritten. */
+int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
+                      float slope, float* E_next, yr_stream stream);
+int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
+                      const float* G_next, const float* W1, const float* W2, float slope,
+                      float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
+                      yr_stream stream);
+
 /* Tail of NGCF.bpr_forward + BPRLoss (models/ngcf.py:37-45, loss.py:25-27) and its backward:
  * rows u / nU+pos / nU+neg are gathered from every layer output E_l (l = 0..n_layers), the concatenated
  * dots give pos/neg scores, the batch-mean loss is added to

@@ -10,9 +10,11 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle.torch_port import MFPort                                              # noqa: E402
+from oracle.torch_port import MFPort, NGCFPort                                              # noqa: E402
 from yelprecommendation_b200.data import synthetic as syn                          # noqa: E402
+from yelprecommendation_b200.data.graph import build_laplacian                     # noqa: E402
 from yelprecommendation_b200.trainers.sharded_mf_trainer import ShardedMFTrainer   # noqa: E402
+from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer  # noqa: E402
 
 
 def main():
@@ -34,6 +36,33 @@ def main():
         for got, ref in ((U.cpu(), port.user.weight.detach()), (V.cpu(), port.item.weight.detach())):
             rel = float((got - ref).norm() / ref.norm())
             assert rel < 1e-5, (optname, rel)
+        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+    # ---- row-sharded NGCF (rectangular SpMM blocks, all-gather per layer, all-reduce of dW)
+    inter = syn.make_interactions(num_users=1203, num_items=958, nnz=30000, seed=21, n_clusters=4, star_ratings=True)
+    split = syn.split_per_user(inter, seed=42)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    u, p, n = syn.sample_triples(split, inter.num_items, seed=9)
+    batches = syn.to_batches(u, p, n, 1023)[:4]
+    N, d, layers = inter.num_users + inter.num_items, 64, 3
+    g = torch.Generator().manual_seed(3)
+    init = {"embedding.weight": torch.randn(N, d, generator=g) * 0.3}
+    for l in range(layers):
+        init[f"W1.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+        init[f"W2.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+    for optname, lr, wd in (("sgd", 0.05, 0.0), ("adam", 1e-2, 1e-4)):
+        cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+        tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init)
+        loss = tr.train(batches)
+        E0 = tr.gather_embedding().cpu()
+        port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
+                        [init[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, optname, lr, wd)
+        ref_loss, _ = port.train(batches)
+        rel = float((E0 - port.emb.detach()).norm() / port.emb.detach().norm())
+        assert rel < 1e-5, (optname, "E", rel)
+        for l in range(layers):
+            for got, ref in ((tr.W1[l].cpu(), port.W1[l].detach()), (tr.W2[l].cpu(), port.W2[l].detach())):
+                rel = float((got - ref).norm() / ref.norm())
+                assert rel < 1e-5, (optname, "W", l, rel)
         assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
     dist.barrier()
     if rank == 0:

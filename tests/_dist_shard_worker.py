@@ -14,10 +14,12 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle.torch_port import MFPort                                              # noqa: E402
+from oracle.torch_port import MFPort, NGCFPort                                    # noqa: E402
 from yelprecommendation_b200 import _cabi                                          # noqa: E402
 from yelprecommendation_b200.data import synthetic as syn                          # noqa: E402
+from yelprecommendation_b200.data.graph import build_laplacian                     # noqa: E402
 from yelprecommendation_b200.trainers.sharded_mf_trainer import ShardedMFTrainer   # noqa: E402
+from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer  # noqa: E402
 
 
 class CpuShardKernels:
@@ -67,6 +69,103 @@ class CpuShardKernels:
         s["flags"].zero_()
 
 
+def _opt_step_cpu(T, g, m, v, opt):
+    kind = {v_: k for k, v_ in _cabi.OPT_KINDS.items()}[opt.kind]
+    if kind == "sgd":
+        T -= opt.lr * (g + opt.weight_decay * T)
+        return
+    if kind == "adam":
+        g = g + opt.weight_decay * T
+    else:
+        T *= 1 - opt.lr * opt.weight_decay
+    m.mul_(opt.beta1).add_(g, alpha=1 - opt.beta1)
+    v.mul_(opt.beta2).addcmul_(g, g, value=1 - opt.beta2)
+    bc1, bc2 = 1 - opt.beta1 ** opt.step, 1 - opt.beta2 ** opt.step
+    T.addcdiv_(m, (v.sqrt() / np.sqrt(bc2)).add_(opt.eps), value=-opt.lr / bc1)
+
+
+class CpuNgcfShardKernels:
+    """Semantics of yr_spmm_csr / yr_ngcf_dense_fwd / yr_ngcf_dense_bwd / yr_shard_gather_rows / yr_bpr_rows_grad /
+    yr_shard_accumulate / yr_dense_opt_step on CPU tensors. Test infrastructure only."""
+
+    def make_csr(self, rowptr, col, val):
+        n = len(rowptr) - 1
+        rows = np.repeat(np.arange(n), np.diff(rowptr))
+        return (n, torch.from_numpy(rows.astype(np.int64)), torch.from_numpy(col.astype(np.int64)), torch.from_numpy(val))
+
+    def spmm(self, A, X, out, accumulate):
+        n, rows, cols, vals = A
+        y = torch.zeros(n, X.shape[1]).index_add_(0, rows, X[cols] * vals.unsqueeze(1))
+        if accumulate:
+            out += y
+        else:
+            out.copy_(y)
+
+    def dense_fwd(self, E, LE, W1, W2, out):
+        out.copy_(F.leaky_relu(F.linear(LE + E, W1) + F.linear(E * LE, W2), 0.01))
+
+    def dense_bwd(self, E, LE, En, Gn, W1, W2, G, T, dW1, dW2):
+        dZ = Gn * torch.where(En > 0, torch.ones_like(En), torch.full_like(En, 0.01))
+        dS, dP = dZ @ W1, dZ @ W2
+        G += dS + dP * LE
+        T.copy_(dS + dP * E)
+        dW1.copy_(dZ.t() @ (LE + E))
+        dW2.copy_(dZ.t() @ (E * LE))
+
+    def gather_rows(self, T, lo, hi, total, ids, R, col_off, err):
+        d = T.shape[1]
+        own = (ids >= lo) & (ids < hi)
+        R[:, col_off:col_off + d] = 0
+        R[own, col_off:col_off + d] = T[ids[own] - lo]
+
+    def rows_grad(self, R, B, width, Gr, loss_acc):
+        Rv, Gv = R.view(B, 3, width), Gr.view(B, 3, width)
+        u, p, n = Rv[:, 0], Rv[:, 1], Rv[:, 2]
+        x = (u * p).sum(1) - (u * n).sum(1)
+        loss_acc += (-F.logsigmoid(x)).double().sum()
+        g = (-torch.sigmoid(-x) / B).unsqueeze(1)
+        Gv[:, 0] = g * p - g * n
+        Gv[:, 1] = g * u
+        Gv[:, 2] = -(g * u)
+
+    def scatter_rows(self, G, lo, hi, ids, Gr, col_off, flags, scratch):
+        d = G.shape[1]
+        j = torch.nonzero((ids >= lo) & (ids < hi)).flatten()
+        G.index_add_(0, ids[j] - lo, Gr[j, col_off:col_off + d])
+
+    def opt_step(self, p, g, m, v, opt):
+        _opt_step_cpu(p, g, m, v, opt)
+
+
+def ngcf_case(rank):
+    inter = syn.make_interactions(num_users=203, num_items=158, nnz=4000, seed=21, n_clusters=4, star_ratings=True)
+    split = syn.split_per_user(inter, seed=42)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    u, p, n = syn.sample_triples(split, inter.num_items, seed=9)
+    batches = syn.to_batches(u, p, n, 257)[:3]
+    N, d, layers = inter.num_users + inter.num_items, 64, 3
+    g = torch.Generator().manual_seed(3)
+    init = {"embedding.weight": torch.randn(N, d, generator=g) * 0.3}
+    for l in range(layers):
+        init[f"W1.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+        init[f"W2.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+    for optname, lr, wd in (("sgd", 0.05, 0.0), ("adam", 1e-2, 1e-4)):
+        cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+        tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init, device="cpu", kernels=CpuNgcfShardKernels())
+        loss = tr.train(batches)
+        E0 = tr.gather_embedding()
+        port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
+                        [init[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, optname, lr, wd)
+        ref_loss, _ = port.train(batches)
+        rel = float((E0 - port.emb.detach()).norm() / port.emb.detach().norm())
+        assert rel < 2e-6, (optname, "E", rel)
+        for l in range(layers):
+            for got, ref in ((tr.W1[l], port.W1[l].detach()), (tr.W2[l], port.W2[l].detach())):
+                rel = float((got - ref).norm() / ref.norm())
+                assert rel < 5e-6, (optname, "W", l, rel)
+        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+
+
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -97,6 +196,7 @@ def main():
         raise AssertionError("expected IndexError")
     except IndexError:
         pass
+    ngcf_case(rank)
     dist.barrier()
     if rank == 0:
         print("DIST_SHARD_OK")

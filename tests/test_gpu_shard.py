@@ -47,6 +47,41 @@ def test_sharded_trainer_oob_id_raises():
         tr.train([b])
 
 
+def _ngcf_problem(seed=21, nu=1203, ni=958, nnz=30000, d=64, layers=3):
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian
+    inter = syn.make_interactions(num_users=nu, num_items=ni, nnz=nnz, seed=seed, n_clusters=4, star_ratings=True)
+    split = syn.split_per_user(inter, seed=42)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    u, p, n = syn.sample_triples(split, inter.num_items, seed=9)
+    batches = syn.to_batches(u, p, n, 1023)[:4]
+    g = torch.Generator().manual_seed(3)
+    init = {"embedding.weight": torch.randn(nu + ni, d, generator=g) * 0.3}
+    for l in range(layers):
+        init[f"W1.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+        init[f"W2.{l}.weight"] = (torch.rand(d, d, generator=g) * 2 - 1) / 8
+    return inter, L, batches, init
+
+
+@pytest.mark.parametrize("optname,lr,wd,layers", [("sgd", 0.05, 0.0, 3), ("adam", 1e-2, 1e-4, 3), ("adamw", 2e-3, 1e-2, 1)])
+def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers):
+    """Op-by-op sharded path (rectangular SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle."""
+    from oracle.torch_port import NGCFPort
+    from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
+    inter, L, batches, init = _ngcf_problem(layers=layers)
+    cfg = SimpleNamespace(embed_size=64, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+    tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init)
+    loss = tr.train(batches)
+    port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
+                    [init[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, optname, lr, wd)
+    ref_loss, _ = port.train(batches)
+    assert rel_fro(tr.gather_embedding().cpu(), port.emb.detach()) < 1e-5
+    for l in range(layers):
+        assert rel_fro(tr.W1[l].cpu(), port.W1[l].detach()) < 1e-5
+        assert rel_fro(tr.W2[l].cpu(), port.W2[l].detach()) < 1e-5
+    assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_sharded_trainer_nccl_world2():
     script = os.path.join(ROOT, "tests", "_dist_shard_gpu_worker.py")

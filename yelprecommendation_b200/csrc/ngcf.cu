@@ -373,15 +373,13 @@ extern "C" int yr_ngcf_set_dense_mode(int mode) {
 }
 extern "C" int yr_ngcf_get_dense_mode(void) { return g_dense_mode; }
 
-extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
-                                 float slope, float* E_next, float* LE_save, yr_stream stream) {
-  if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
+extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
+                                 float slope, float* E_next, yr_stream stream) {
+  if (!E || !LE || !W1 || !W2 || !E_next || n < 0) return YR_ERR_BAD_ARG;
   if (d != 64) return YR_ERR_BAD_DIM;
-  const int64_t n = L->n_rows;
-  int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
-  if (rc) return rc;
+  if (n == 0) return YR_OK;
   if (g_dense_mode == 1)      // tcgen05 3xTF32 (ngcf_tc.cu)
-    return yr_ngcf_dense_fwd_tc_launch(E, LE_save, W1, W2, slope, n, E_next, (cudaStream_t)stream);
+    return yr_ngcf_dense_fwd_tc_launch(E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -393,24 +391,31 @@ extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const f
   int64_t grid = (int64_t)yr_sm_count() * 3;
   if (grid > n_tiles) grid = n_tiles;
   ngcf_dense_fwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemFwd, (cudaStream_t)stream>>>(
-      E, LE_save, W1, W2, slope, n, E_next);
+      E, LE, W1, W2, slope, n, E_next);
   YR_CHECK_LAUNCH();
   return YR_OK;
+}
+
+extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
+                                 float slope, float* E_next, float* LE_save, yr_stream stream) {
+  if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
+  if (d != 64) return YR_ERR_BAD_DIM;
+  int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
+  if (rc) return rc;
+  return yr_ngcf_dense_fwd(d, L->n_rows, E, LE_save, W1, W2, slope, E_next, stream);
 }
 
 extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
   return (size_t)yr_sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
 }
 
-extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
+extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
                                  const float* G_next, const float* W1, const float* W2, float slope,
                                  float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
                                  yr_stream stream) {
-  if (!LT || !E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 || !dW2 || !ws || LT->n_rows <= 0)
-    return YR_ERR_BAD_ARG;
+  if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 || !dW2 || !ws || n <= 0) return YR_ERR_BAD_ARG;
   if (d != 64) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
-  const int64_t n = LT->n_rows;
   cudaStream_t s = (cudaStream_t)stream;
   using C = DenseCfg<64>;
   static bool attr_set = false;
@@ -428,6 +433,16 @@ extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const 
   const int len = 2 * d * d;
   reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
   YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
+                                 const float* G_next, const float* W1, const float* W2, float slope,
+                                 float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
+                                 yr_stream stream) {
+  if (!LT || LT->n_rows <= 0) return YR_ERR_BAD_ARG;
+  int rc = yr_ngcf_dense_bwd(d, LT->n_rows, E, LE, E_next, G_next, W1, W2, slope, G, T, dW1, dW2, ws, ws_bytes, stream);
+  if (rc) return rc;
   return yr_spmm_csr(LT, d, T, G, 1, stream);
 }
 
