@@ -110,9 +110,9 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
   static_assert(C::kColGroups * C::kColGroups == C::kThreads, "dW tiling assumes D == 64");
   extern __shared__ __align__(16) float smem[];
   float* dZs = smem;                    // [TM][D]
-  float* Es = dZs + TM * D;             // [TM][D]
-  float* LEs = Es + TM * D;             // [TM][D]
-  float* W1s = LEs + TM * D;            // [D][D]  (o, i) as stored
+  float* Ss = dZs + TM * D;             // [TM][D]  LE + E
+  float* Ps = Ss + TM * D;              // [TM][D]  E * LE
+  float* W1s = Ps + TM * D;             // [D][D]  (o, i) as stored
   float* W2s = W1s + D * D;
   const int tid = threadIdx.x;
   const int tx = tid % C::kColGroups, ty = tid / C::kColGroups;
@@ -133,42 +133,51 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
     __syncthreads();
     for (int idx = tid; idx < TM * (D / 4); idx += C::kThreads) {
       const int r = idx / (D / 4), c4 = idx % (D / 4);
-      float4 e = make_float4(0.f, 0.f, 0.f, 0.f), le = e, dz = e;
+      float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), pv = sv, dz = sv;
       if (r0 + r < n) {
         const int64_t off = (r0 + r) * D;
-        e = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
-        le = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
+        const float4 e = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
+        const float4 le = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
         const float4 en = __ldg(reinterpret_cast<const float4*>(Enext + off) + c4);
         const float4 g = __ldg(reinterpret_cast<const float4*>(Gnext + off) + c4);
         dz.x = en.x > 0.f ? g.x : g.x * slope; dz.y = en.y > 0.f ? g.y : g.y * slope;
         dz.z = en.z > 0.f ? g.z : g.z * slope; dz.w = en.w > 0.f ? g.w : g.w * slope;
+        sv = make_float4(le.x + e.x, le.y + e.y, le.z + e.z, le.w + e.w);
+        pv = make_float4(e.x * le.x, e.y * le.y, e.z * le.z, e.w * le.w);
       }
-      reinterpret_cast<float4*>(Es)[idx] = e;
-      reinterpret_cast<float4*>(LEs)[idx] = le;
+      reinterpret_cast<float4*>(Ss)[idx] = sv;
+      reinterpret_cast<float4*>(Ps)[idx] = pv;
       reinterpret_cast<float4*>(dZs)[idx] = dz;
     }
     __syncthreads();
 
-    // ---- dS, dP: rows ty*4.., cols tx*4.. ; k = o ----
+    // ---- dS, dP: rows ty*4.., cols tx*4.. ; k = o, four k per shared-memory round ----
     float ds[4][4], dp[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { ds[i][j] = 0.f; dp[i][j] = 0.f; }
-#pragma unroll 4
-    for (int o = 0; o < D; ++o) {
-      const float4 w1 = *reinterpret_cast<const float4*>(W1s + o * D + tx * 4);
-      const float4 w2 = *reinterpret_cast<const float4*>(W2s + o * D + tx * 4);
-      const float w1v[4] = {w1.x, w1.y, w1.z, w1.w};
-      const float w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll 2
+    for (int o = 0; o < D; o += 4) {
+      float av[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float a = dZs[(ty * 4 + i) * D + o];
+        const float4 a4 = *reinterpret_cast<const float4*>(dZs + (ty * 4 + i) * D + o);
+        av[i][0] = a4.x; av[i][1] = a4.y; av[i][2] = a4.z; av[i][3] = a4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ds[i][j] = fmaf(a, w1v[j], ds[i][j]);
-          dp[i][j] = fmaf(a, w2v[j], dp[i][j]);
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float4 w1 = *reinterpret_cast<const float4*>(W1s + (o + k) * D + tx * 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(W2s + (o + k) * D + tx * 4);
+        const float w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+        const float w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ds[i][j] = fmaf(av[i][k], w1v[j], ds[i][j]);
+            dp[i][j] = fmaf(av[i][k], w2v[j], dp[i][j]);
+          }
       }
     }
 #pragma unroll
@@ -176,8 +185,9 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       const int rl = ty * 4 + i;
       const int64_t r = r0 + rl;
       if (r < n) {
-        const float4 e = *reinterpret_cast<const float4*>(Es + rl * D + tx * 4);
-        const float4 le = *reinterpret_cast<const float4*>(LEs + rl * D + tx * 4);
+        // E / LE again (L1/L2 hits: this CTA has just read the tile) — shared memory holds S and P instead
+        const float4 e = __ldg(reinterpret_cast<const float4*>(E + r * D) + tx);
+        const float4 le = __ldg(reinterpret_cast<const float4*>(LE + r * D) + tx);
         float4 t, dd;
         t.x = fmaf(dp[i][0], e.x, ds[i][0]); t.y = fmaf(dp[i][1], e.y, ds[i][1]);
         t.z = fmaf(dp[i][2], e.z, ds[i][2]); t.w = fmaf(dp[i][3], e.w, ds[i][3]);
@@ -195,11 +205,11 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
 #pragma unroll 4
     for (int r = 0; r < TM; ++r) {
       const float4 dz = *reinterpret_cast<const float4*>(dZs + r * D + ty * 4);
-      const float4 e = *reinterpret_cast<const float4*>(Es + r * D + tx * 4);
-      const float4 le = *reinterpret_cast<const float4*>(LEs + r * D + tx * 4);
+      const float4 s4 = *reinterpret_cast<const float4*>(Ss + r * D + tx * 4);
+      const float4 p4 = *reinterpret_cast<const float4*>(Ps + r * D + tx * 4);
       const float dzv[4] = {dz.x, dz.y, dz.z, dz.w};
-      const float sv[4] = {le.x + e.x, le.y + e.y, le.z + e.z, le.w + e.w};
-      const float pv[4] = {e.x * le.x, e.y * le.y, e.z * le.z, e.w * le.w};
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
