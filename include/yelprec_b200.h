@@ -221,6 +221,17 @@ int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
 /* out[r, l*d + k] = E_l[r, k]: the concatenation torch.concat(..., dim=1) of models/ngcf.py:41-43. */
 int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
 
+/* ---- Negative sampler -----------------------------------------------------------------
+ * MFDataset._negative_sampling (data/datasets/mf_dataset.py:18-22): for every training interaction t one item
+ * drawn uniformly from the items NOT in the user's positive list. pos_ptr/pos_idx: CSR of the users' `pos_items`
+ * (mf_data_pipeline.py:41-47), item ids sorted ascending inside a user. Stream: Philox4x32-10, key = seed,
+ * counter = (offset + t, block, 0) — a function of (seed, global triple index) only, hence identical under any
+ * sharding. A triple that finds no negative within max_blocks*4 draws (user has ~every item) gets -1 and sets
+ * *err = 2 (the reference would not terminate); an out-of-range uid sets *err = 1. */
+int yr_sample_negatives(const int64_t* uid, int64_t n, const int32_t* pos_ptr, const int32_t* pos_idx,
+                        int64_t num_users, int64_t num_items, uint64_t seed, uint64_t offset, int max_blocks,
+                        int64_t* neg_out, int32_t* err, yr_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-sharded BPR-MF (BASELINE config 5): each rank owns a contiguous block of user rows and of item rows
  * (and their optimizer state). One step = gather owned rows -> all-reduce (NCCL, by the caller) -> per-rank slice

@@ -180,3 +180,20 @@ def metrics_from_sums(sums, n_eval):
     m = sums[2] / sums[5] if sums[5] else float("nan")
     n = sums[3] / sums[4] if sums[4] else float("nan")
     return p, r, m, n
+
+
+def philox4x32_10(ctr, key) -> np.ndarray:
+    out = np.zeros(4, np.uint32)
+    lib().orc_philox4x32_10(_p(np.ascontiguousarray(ctr, dtype=np.uint32)), _p(np.ascontiguousarray(key, dtype=np.uint32)), _p(out))
+    return out
+
+
+def sample_negatives(uid, pos_ptr, pos_idx, num_items, seed, offset=0, max_blocks=64):
+    """(neg int64[n], n_failed) — Philox4x32-10 rejection sampler, see oracle/yr_oracle.c."""
+    uid = _i64(uid)
+    neg = np.empty(uid.shape[0], np.int64)
+    f = lib().orc_sample_negatives
+    f.restype = C.c_int64
+    failed = f(_p(uid), C.c_int64(uid.shape[0]), _p(_i32(pos_ptr)), _p(_i32(pos_idx)), C.c_int64(num_items),
+               C.c_uint64(seed), C.c_uint64(offset), C.c_int(max_blocks), _p(neg))
+    return neg, int(failed)

@@ -305,3 +305,55 @@ void orc_eval_topk_metrics(const float* Uemb, const float* Vemb, int64_t nI, int
   }
   free(sc); free(bs); free(bi);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Negative sampler (reference data/datasets/mf_dataset.py:18-22: draw uniformly over the items until the
+ * draw is not one of the user's positives). The reference draws from NumPy's global Mersenne Twister, one
+ * sample at a time inside DataLoader workers — a sequential stream a data-parallel sampler cannot reproduce,
+ * so the stream is REDEFINED as counter-based Philox4x32-10 (Salmon et al., SC'11; Random123 known-answer
+ * vectors pinned in tests/test_oracle_golden.py): triple t uses key = seed, counter = (t_lo, t_hi, block, 0),
+ * words consumed in order; a word w maps to an item with Lemire's unbiased multiply-shift (reject w when
+ * lo32(w * nI) < (2^32 - nI) mod nI), and the item is rejected when it is in the user's positive list.
+ * Same distribution as the reference (uniform over the user's non-positives), different stream. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* returns the number of triples that exhausted max_blocks Philox blocks (neg = -1 for those) */
+int64_t orc_sample_negatives(const int64_t* uid, int64_t n, const int32_t* pos_ptr, const int32_t* pos_idx,
+                             int64_t num_items, uint64_t seed, uint64_t offset, int max_blocks, int64_t* neg_out) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  const uint32_t nI = (uint32_t)num_items;
+  const uint32_t thresh = (uint32_t)(0u - nI) % nI;
+  int64_t failed = 0;
+  for (int64_t t = 0; t < n; ++t) {
+    const uint64_t idx = offset + (uint64_t)t;
+    const int32_t lo = pos_ptr[uid[t]], hi = pos_ptr[uid[t] + 1];
+    int64_t found = -1;
+    for (int blk = 0; blk < max_blocks && found < 0; ++blk) {
+      const uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)blk, 0u};
+      uint32_t w[4];
+      orc_philox4x32_10(ctr, key, w);
+      for (int q = 0; q < 4 && found < 0; ++q) {
+        const uint64_t m = (uint64_t)w[q] * nI;
+        if ((uint32_t)m < thresh) continue;
+        const int32_t cand = (int32_t)(m >> 32);
+        int32_t a = lo, b = hi;                       /* binary search in the sorted positives */
+        while (a < b) { const int32_t mid = (a + b) >> 1; if (pos_idx[mid] < cand) a = mid + 1; else b = mid; }
+        if (a < hi && pos_idx[a] == cand) continue;
+        found = cand;
+      }
+    }
+    if (found < 0) ++failed;
+    neg_out[t] = found;
+  }
+  return failed;
+}

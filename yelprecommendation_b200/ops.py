@@ -166,6 +166,30 @@ def dense_opt_step(p, g, m, v, opt: _cabi.YrOpt):
                                 stream_ptr(p.device)), "yr_dense_opt_step")
 
 
+def sample_negatives(uid: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, num_users: int, num_items: int,
+                     seed: int, offset: int = 0, max_blocks: int = 64, err: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One negative per entry of `uid` (int64, device), uniform over the items outside the user's sorted positive list
+    (CSR int32 pos_ptr / pos_idx) — MFDataset._negative_sampling (data/datasets/mf_dataset.py:18-22) on the device."""
+    lib = _cabi.load()
+    uid = uid.contiguous()
+    neg = torch.empty_like(uid)
+    if uid.numel() == 0:
+        return neg
+    own_err = err is None
+    if own_err:
+        err = torch.zeros(1, dtype=I32, device=uid.device)
+    check(lib.yr_sample_negatives(dptr(uid, I64), uid.numel(), dptr(pos_ptr, I32), dptr(pos_idx, I32), int(num_users),
+                                  int(num_items), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(max_blocks),
+                                  dptr(neg, I64), dptr(err, I32), stream_ptr(uid.device)), "yr_sample_negatives")
+    if own_err:
+        code = int(err.item())
+        if code == 1:
+            raise IndexError("sample_negatives: index out of range in self")
+        if code == 2:
+            raise RuntimeError("sample_negatives: no item outside a user's positives")
+    return neg
+
+
 def device_ptr_array(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """int64 device tensor holding the data pointers of `tensors` (a `float* const*` for the kernels)."""
     dev = tensors[0].device

@@ -103,6 +103,16 @@ class MFTrainer(BaseTrainer):
 
     def train(self, train_dataloader) -> float:
         self.model.train()
+        if hasattr(train_dataloader, "epoch_triples"):        # data.sampler.DeviceTripleLoader: epoch resident in HBM
+            uid, pos, neg = train_dataloader.epoch_triples()
+            B = int(train_dataloader.batch_size)
+            self._state(B)[1]["loss_sum"].zero_()
+            if uid.numel() == 0:
+                return 0
+            sl = torch.empty((uid.numel() + B - 1) // B, device=self.device, dtype=F32)
+            self.train_on_device(uid, pos, neg, B, sl)
+            self.last_step_losses = sl
+            return self.loss_sum()
         stager = self._get_stager(train_dataloader)
         self._state(stager.cap)[1]["loss_sum"].zero_()
         step_losses = []

@@ -128,6 +128,16 @@ class NGCFTrainer(BaseTrainer):
         self.model.train()
         st, b = self._state()
         b["loss"].zero_()
+        if hasattr(train_dataloader, "epoch_triples"):        # data.sampler.DeviceTripleLoader: epoch resident in HBM
+            uid, pos, neg = train_dataloader.epoch_triples()
+            B, n = int(train_dataloader.batch_size), int(uid.numel())
+            if n == 0:
+                return 0
+            sl = torch.empty((n + B - 1) // B, device=self.device, dtype=F32)
+            for k, s in enumerate(range(0, n, B)):
+                self.train_step_on_device(uid[s:s + B], pos[s:s + B], neg[s:s + B], sl[k:k + 1], st)
+            self.last_step_losses = sl
+            return self.loss_sum()
         stager = self._get_stager(train_dataloader)
         losses = []
         for uid, pos, neg, n, B in stager.chunks(train_dataloader):
