@@ -221,6 +221,17 @@ int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
 /* out[r, l*d + k] = E_l[r, k]: the concatenation torch.concat(..., dim=1) of models/ngcf.py:41-43. */
 int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
 
+/* ---- Laplacian / CSR builder --------------------------------------------------------------
+ * NGCFDataPipeline._set_laplacian_matrix (data/datasets/ngcf_data_pipeline.py:19-44) without the two dense
+ * (U+I)^2 arrays: interactions (user, item, rating), any order, duplicates averaged (pivot_table mean), zero means
+ * dropped -> CSR of L = (D^-1/2 A) D^-1/2 over N = U+I nodes, columns sorted inside a row, fp32 with the reference's
+ * association and its row-by-row degree accumulation. rowptr [N+1], col / val [2*nnz] (rowptr[N] entries are used).
+ * ws: yr_laplacian_ws_bytes. *err = 1 if an id is out of range (the interaction is skipped). */
+size_t yr_laplacian_ws_bytes(int64_t nnz, int64_t num_users, int64_t num_items);
+int yr_laplacian_build(const int64_t* user, const int64_t* item, const float* rating, int64_t nnz,
+                       int64_t num_users, int64_t num_items, int32_t* rowptr, int32_t* col, float* val,
+                       void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+
 /* ---- Negative sampler -----------------------------------------------------------------
  * MFDataset._negative_sampling (data/datasets/mf_dataset.py:18-22): for every training interaction t one item
  * drawn uniformly from the items NOT in the user's positive list. pos_ptr/pos_idx: CSR of the users' `pos_items`

@@ -28,7 +28,7 @@ SYMBOLS = (
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_output", "yr_cdae_step", "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
-    "yr_sample_negatives",
+    "yr_sample_negatives", "yr_laplacian_ws_bytes", "yr_laplacian_build",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -151,6 +151,8 @@ def load() -> C.CDLL:
                                    C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, p, p, p, p, p, i64, p, p,
                                    p, sz, p, p]),
         "yr_nsbce_loss": (C.c_int, [p, p, p, i64, p, p, sz, p]),
+        "yr_laplacian_ws_bytes": (sz, [i64, i64, i64]),
+        "yr_laplacian_build": (C.c_int, [p, p, p, i64, i64, i64, p, p, p, p, sz, p, p]),
         "yr_sample_negatives": (C.c_int, [p, i64, p, p, i64, i64, C.c_uint64, C.c_uint64, i32, p, p, p]),
         "yr_shard_gather_rows": (C.c_int, [p, i64, i64, i64, i32, p, i64, p, i64, p, p]),
         "yr_bpr_rows_grad": (C.c_int, [p, i32, i64, i64, i64, p, p, p]),

@@ -60,10 +60,14 @@ class CSRMatrix:
     """Device CSR (int32 / fp32) + the SpMM load-balancing plan of include/yelprec_b200.h (yr_csr).
     On CPU (tests of the host logic) the plan is still built, only the struct() call needs CUDA."""
 
-    def __init__(self, rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, device):
+    def __init__(self, rowptr, col, val, device):
+        """rowptr/col/val: numpy arrays, or torch tensors (col/val may already live on `device`: only rowptr is
+        read on the host, for the plan)."""
         import ctypes as C
         from .. import _cabi
         lib = _cabi.load()
+        if isinstance(rowptr, torch.Tensor):
+            rowptr = rowptr.detach().cpu().numpy()
         self.n_rows = int(rowptr.shape[0] - 1)
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
         nc, ns, npart = C.c_int32(0), C.c_int32(0), C.c_int32(0)
@@ -76,7 +80,9 @@ class CSRMatrix:
                                             sptr.ctypes.data), "yr_spmm_plan_fill_h")
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.device = torch.device(device)
-        self.rowptr, self.col, self.val = t(rowptr), t(col.astype(np.int32)), t(val.astype(np.float32))
+        tt = lambda a, dt_np, dt_t: (a.to(device=device, dtype=dt_t).contiguous() if isinstance(a, torch.Tensor)
+                                     else t(a.astype(dt_np)))
+        self.rowptr, self.col, self.val = t(rowptr), tt(col, np.int32, torch.int32), tt(val, np.float32, torch.float32)
         self.chunk_desc = t(cdesc)
         self.split_row, self.split_ptr = t(srow), t(sptr)
         self.split_count = torch.zeros(max(ns.value, 1), dtype=torch.int32, device=device)
@@ -123,6 +129,34 @@ def laplacian_to_csr(L: torch.Tensor, device) -> LaplacianCSR:
     fwd = CSRMatrix(rp, ci, va, device)
     bwd = fwd if sym else CSRMatrix(rpt, cit, vat, device)
     return LaplacianCSR(n, fwd, bwd, sym)
+
+
+def build_laplacian_csr_device(user: torch.Tensor, item: torch.Tensor, rating: torch.Tensor, num_users: int,
+                               num_items: int) -> LaplacianCSR:
+    """ngcf_data_pipeline.py:19-44 on the device (yr_laplacian_build): interactions (int64 ids, fp32 ratings, any
+    order, duplicates averaged) -> LaplacianCSR ready for the SpMM kernels. Bit-identical to
+    laplacian_to_csr(build_laplacian(...)). L is symmetric by construction, so L^T shares the arrays."""
+    from .. import _cabi
+    lib = _cabi.load()
+    dev = user.device
+    user, item = user.to(torch.int64).contiguous(), item.to(torch.int64).contiguous()
+    rating = rating.to(torch.float32).contiguous()
+    nnz, n = int(user.numel()), int(num_users + num_items)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(2 * nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(2 * nnz, dtype=torch.float32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = lib.yr_laplacian_ws_bytes(nnz, int(num_users), int(num_items))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    p = _cabi.dptr
+    _cabi.check(lib.yr_laplacian_build(p(user), p(item), p(rating), nnz, int(num_users), int(num_items), p(rowptr), p(col),
+                                       p(val), p(ws), nbytes, p(err), _cabi.stream_ptr(dev)), "yr_laplacian_build")
+    rp = rowptr.cpu()
+    if int(err.item()):
+        raise IndexError("build_laplacian_csr_device: index out of range in self")
+    total = int(rp[-1])
+    m = CSRMatrix(rp, col[:total].clone(), val[:total].clone(), dev)
+    return LaplacianCSR(n, m, m, True)
 
 
 @dataclass
