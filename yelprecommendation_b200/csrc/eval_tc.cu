@@ -195,14 +195,15 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         for (int k = 0; k < d; ++k) nn = fmaf(urow[k], urow[k], nn);
         eps2 = 2.f * kTcErrCoef * sqrtf(nn) * (*P.vmax) * 1.0001f + FLT_MIN;
       }
-      float* my_tk = tk + (size_t)half * K * kTcTM + r;
       int* my_cid = cid + (size_t)half * CAP * kTcTM + r;
       float* my_csc = csc + (size_t)half * CAP * kTcTM + r;
-      int* my_pid = pid + (size_t)half * kTcPend * kTcTM + r;
-      float* my_psc = psc + (size_t)half * kTcPend * kTcTM + r;
-      for (int j = 0; j < K; ++j) my_tk[j * kTcTM] = -INFINITY;
+      // the K best s~ values of this half-stream live in REGISTERS, ascending: tkr[0] is the K-th best (tau). Slots
+      // K..15 hold +inf so that one static 15-step bubble pass serves every K <= 16 without dynamic indexing.
+      float tkr[kTcMaxK];
+#pragma unroll
+      for (int j = 0; j < kTcMaxK; ++j) tkr[j] = (j < K) ? -INFINITY : INFINITY;
       float tau = -INFINITY, theta = -INFINITY;
-      int cnt = 0, npend = 0;
+      int cnt = 0;
       bool overflow = false;
       int mcur = live ? P.mask_ptr[e] : 0;
       const int mend = live ? P.mask_ptr[e + 1] : 0;
@@ -222,20 +223,16 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
           if (cnt == CAP) { overflow = true; return; }
         }
         my_cid[cnt * kTcTM] = item; my_csc[cnt * kTcTM] = s; ++cnt;
-        if (s > tau) {                                              // insert into the sorted K best s~ values
-          int j = K - 1;
-          while (j > 0 && my_tk[(j - 1) * kTcTM] < s) { my_tk[j * kTcTM] = my_tk[(j - 1) * kTcTM]; --j; }
-          my_tk[j * kTcTM] = s;
-          tau = my_tk[(K - 1) * kTcTM];
+        if (s > tau) {                                              // replace the K-th best, one bubble pass re-sorts
+          tkr[0] = s;
+#pragma unroll
+          for (int j = 0; j + 1 < kTcMaxK; ++j) {
+            const float lo = fminf(tkr[j], tkr[j + 1]), hi = fmaxf(tkr[j], tkr[j + 1]);
+            tkr[j] = lo; tkr[j + 1] = hi;
+          }
+          tau = tkr[0];
           theta = tau - eps2;
         }
-      };
-      auto drain = [&]() {                            // warp-uniform loop: lanes pop their pending FIFO in lock step
-        int head = 0;
-        while (__any_sync(kFull, head < npend)) {
-          if (head < npend) { handle(my_pid[head * kTcTM], my_psc[head * kTcTM]); ++head; }
-        }
-        npend = 0;
       };
 
       for (int it = 0; it < n_itiles; ++it) {
@@ -261,22 +258,18 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
             const int item0 = it * TN + half * (TN / 2) + c0;
             // columns past the catalog are zero-filled TMA rows (score 0): never candidates
             if ((int64_t)item0 + 32 > P.nI) mask = (item0 < P.nI) ? (mask & ((1u << (int)(P.nI - item0)) - 1u)) : 0u;
-            while (__any_sync(kFull, mask != 0)) {
+            while (__any_sync(kFull, mask != 0)) {                    // few lanes, few bits: handled in place
               if (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                my_pid[npend * kTcTM] = item0 + j;
-                my_psc[npend * kTcTM] = select32(v, j);
-                ++npend;
+                handle(item0 + j, select32(v, j));
               }
-              if (__any_sync(kFull, npend == kTcPend)) drain();
             }
           }
         }
         tc_fence_before();
         mbar_arrive(tempty + acc_e);
         if (++acc_e == kTcAcc) { acc_e = 0; aph_e ^= 1; }
-        if (__any_sync(kFull, npend > 0)) drain();
       }
 
       // ---- hand the second half-stream's state to the first; first half finishes the row ----
