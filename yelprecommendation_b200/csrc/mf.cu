@@ -139,6 +139,70 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
   int32_t* rowsV = st.rows + B;
   __shared__ double s_part[kTrainWarps];
 
+  // ---- plain SGD with at most one triple per warp: the three gradient rows stay in REGISTERS across the barrier and
+  // are applied as vector REDs of -lr * g straight into the tables — no gradient scratch, no touched-row list, no
+  // second pass over the rows. Two grid barriers per step remain (every read of step s precedes every update of
+  // step s, every update precedes the reads of step s + 1): the reference's sequential step semantics.
+  if (!dense && B <= nwarps) {
+    const float neg_lr = -(float)opt.lr;
+    int64_t u = 0, p = 0, n = 0;
+    if (gwarp < ((n_triples < B) ? (int)n_triples : B)) { u = uid[gwarp]; p = pos[gwarp]; n = neg[gwarp]; }
+    for (int64_t s = 0; s < n_steps; ++s) {
+      const int par = (parity0 + (int)(s & 1)) & 1;
+      const int64_t base = s * (int64_t)B;
+      const int nb = (int)((n_triples - base < B) ? (n_triples - base) : B);
+      const float inv_nb = 1.f / (float)nb;
+      bool act = gwarp < nb;
+      if (act && (u < 0 || u >= st.nU || p < 0 || p >= st.nI || n < 0 || n >= st.nI)) {
+        if (lane == 0) atomicExch(st.err, 1);
+        act = false;
+      }
+      Row<VPL> gu, gp, gn;
+      double wl = 0.0;
+      if (act) {
+        const Row<VPL> ur = ld_row<VPL>(st.U + u * D, lane);
+        const Row<VPL> pr = ld_row<VPL>(st.V + p * D, lane);
+        const Row<VPL> nr = ld_row<VPL>(st.V + n * D, lane);
+        const float x = warp_sum(dot_partial<VPL>(ur, pr)) - warp_sum(dot_partial<VPL>(ur, nr));
+        const float g = neg_logsigmoid_grad(x) * inv_nb;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const float a = __fsub_rn(__fmul_rn(g, pr.x[j]), __fmul_rn(g, nr.x[j]));   // Q2: two rounded products
+          const float c = g * ur.x[j];
+          gu.x[j] = neg_lr * a; gp.x[j] = neg_lr * c; gn.x[j] = -gp.x[j];
+        }
+        wl = (double)neg_logsigmoid(x);
+      }
+      const int64_t uu = u, pp = p, nn = n;
+      // ids of the next step (read-only input): requested before the barrier, consumed after the second one
+      const int64_t nbase = base + B;
+      if (nbase + gwarp < n_triples && gwarp < B) { u = uid[nbase + gwarp]; p = pos[nbase + gwarp]; n = neg[nbase + gwarp]; }
+      if (lane == 0) s_part[wib] = wl;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < kTrainWarps; ++i) t += s_part[i];
+        if (t != 0.0) atomicAdd(loss_acc + par, t);
+      }
+      grid.sync();
+      if (act) {
+        red_row<VPL>(st.U + uu * D, lane, gu);
+        red_row<VPL>(st.V + pp * D, lane, gp);
+        red_row<VPL>(st.V + nn * D, lane, gn);
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float mean = (float)(__ldcg(loss_acc + par) / (double)nb);
+        if (step_loss) step_loss[s] = mean;
+        if (loss_sum) *loss_sum += (double)mean;
+        loss_acc[par ^ 1] = 0.0;
+        if (s + 1 == n_steps) counters[4] = par ^ 1;
+      }
+      if (s + 1 < n_steps) grid.sync();
+    }
+    return;
+  }
+
   for (int64_t s = 0; s < n_steps; ++s) {
     const int par = (parity0 + (int)(s & 1)) & 1;
     int32_t* cnt = counters + 2 * par;
