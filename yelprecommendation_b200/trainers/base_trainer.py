@@ -139,31 +139,43 @@ class BatchStager:
         self.which = 0
 
     def chunks(self, dataloader):
-        """Yields (uid, pos, neg, n_triples, B) device views; every batch in a chunk has size B except the last."""
-        host = self._acquire()
+        """Yields (uid, pos, neg, n_triples, B) device views; every batch in a chunk has size B except the last.
+        Batches are collected by reference and collated with three torch.cat(out=pinned) calls per chunk, so the
+        per-batch host cost is a few attribute lookups, not three small copies."""
+        us, ps, ns = [], [], []
         fill, B = 0, None
+        cap_n = self.cap * self.chunk
+
+        def flush():
+            nonlocal us, ps, ns, fill, B
+            host = self._acquire()
+            torch.cat(us, out=host[0, :fill])
+            torch.cat(ps, out=host[1, :fill])
+            torch.cat(ns, out=host[2, :fill])
+            out = self._ship(host, fill, B)
+            us, ps, ns, fill, B = [], [], [], 0, None
+            return out
+
         for data in dataloader:
             u, p, n = data["user_id"], data["pos_item"], data["neg_item"]
             nb = int(u.numel())
             if nb == 0:
                 continue
             short_pending = B is not None and fill % B != 0      # a short batch must end its chunk
-            if B is not None and (nb > B or short_pending or fill + nb > host.shape[1] or nb > self.cap):
-                yield self._ship(host, fill, B)
-                host, fill, B = self._acquire(), 0, None
-            if nb > host.shape[1]:
-                raise _cabi.YelprecError(f"batch of {nb} triples exceeds the staging capacity {host.shape[1]}")
+            if B is not None and (nb > B or short_pending or fill + nb > cap_n or nb > self.cap):
+                yield flush()
+            if nb > cap_n:
+                raise _cabi.YelprecError(f"batch of {nb} triples exceeds the staging capacity {cap_n}")
             if B is None:
                 B = nb
-            host[0, fill:fill + nb].copy_(u.reshape(-1))
-            host[1, fill:fill + nb].copy_(p.reshape(-1))
-            host[2, fill:fill + nb].copy_(n.reshape(-1))
+            if u.device.type != "cpu" or u.dtype != torch.int64 or p.dtype != torch.int64 or n.dtype != torch.int64:
+                u, p, n = (t.to("cpu", torch.int64) for t in (u, p, n))
+            us.append(u.reshape(-1)); ps.append(p.reshape(-1)); ns.append(n.reshape(-1))
             fill += nb
-            if fill + B > host.shape[1] or nb < B:
-                yield self._ship(host, fill, B)
-                host, fill, B = self._acquire(), 0, None
+            if fill + B > cap_n or nb < B:
+                yield flush()
         if fill:
-            yield self._ship(host, fill, B)
+            yield flush()
 
     def _acquire(self):
         self.which ^= 1
