@@ -329,13 +329,59 @@ def golden_cdae():
     print("cdae_small: losses", out["c0_losses"], "valid", out["valid_after"])
 
 
+# ------------------------------------------------------------------------------------------------
+def golden_run_loop():
+    """BaseTrainer.run (trainers/mf_trainer.py:34-97): epoch loop, best-metric selection, best_model.pt, early stop.
+    Adam at lr 0.05 over-fits the 160-user problem within a few epochs, so the validation loss turns and patience = 1
+    stops the loop before cfg.epochs — the recorded per-epoch history and the saved best model pin that behaviour."""
+    inter = syn.make_interactions(num_users=160, num_items=240, nnz=3200, seed=5, n_clusters=4)
+    pipe = MFDataPipeline(cfg())
+    pipe.num_users, pipe.num_items = inter.num_users, inter.num_items
+    _, _, valid_eval, _ = pipe.split(frame(inter))
+    split = syn.split_per_user(inter, seed=42)
+    tu, tp, tn = syn.sample_triples(split, inter.num_items, seed=42)
+    vu, vp, vn = syn.sample_triples(split, inter.num_items, seed=43, which="valid", reject="train+valid")
+    batches, vbatches = syn.to_batches(tu, tp, tn, 256), syn.to_batches(vu, vp, vn, 256)
+    out = {}
+    for tag, kw in (("loss", dict(best_metric="loss", patience=1)), ("recall", dict(best_metric="recall", patience=2))):
+        mdir = tempfile.mkdtemp()
+        torch.manual_seed(42)
+        tr = RefMFTrainer(cfg(optimizer="adam", lr=0.05, epochs=12, model_dir=mdir, **kw), inter.num_items, inter.num_users)
+        out[f"{tag}_U0"] = tr.model.user_embedding.weight.detach().numpy().copy()
+        out[f"{tag}_V0"] = tr.model.item_embedding.weight.detach().numpy().copy()
+        hist = {"train": [], "valid": [], "metrics": []}
+        for name in ("train", "validate", "evaluate"):
+            orig = getattr(tr, name)
+
+            def wrapped(*a, _orig=orig, _name=name, **k):
+                r = _orig(*a, **k)
+                hist[{"train": "train", "validate": "valid", "evaluate": "metrics"}[_name]].append(r)
+                return r
+            setattr(tr, name, wrapped)
+        tr.run(batches, vbatches, valid_eval)
+        best = torch.load(os.path.join(mdir, "best_model.pt"))
+        out[f"{tag}_train"] = np.array(hist["train"])
+        out[f"{tag}_valid"] = np.array(hist["valid"])
+        out[f"{tag}_metrics"] = np.array(hist["metrics"])
+        out[f"{tag}_best_U"] = best["user_embedding.weight"].numpy()
+        out[f"{tag}_best_V"] = best["item_embedding.weight"].numpy()
+        out[f"{tag}_keys"] = np.array(sorted(best.keys()))
+        print(f"run_loop[{tag}]: epochs run {len(hist['train'])} of 12; valid", np.round(hist["valid"], 4),
+              "recall", np.round([m[1] for m in hist["metrics"]], 4))
+    np.savez_compressed(os.path.join(HERE, "run_loop.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cdae":
         golden_cdae()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "run_loop":
+        golden_run_loop()
         sys.exit(0)
     golden_metrics()
     golden_split_and_mf()
     golden_ngcf()
     golden_cdae()
+    golden_run_loop()
     print("fixtures written to", HERE)
     os.system(f"ls -la {HERE}")
