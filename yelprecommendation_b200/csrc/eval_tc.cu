@@ -73,6 +73,17 @@ __device__ __forceinline__ float select32(const float (&v)[32], int j) {
   return (j & 16) ? e[1] : e[0];
 }
 
+__device__ __forceinline__ float select16(const float (&v)[16], int j) {
+  float a[8], b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+  return (j & 8) ? c[1] : c[0];
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -203,6 +214,17 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
 #pragma unroll
       for (int j = 0; j < kTcMaxK; ++j) tkr[j] = (j < K) ? -INFINITY : INFINITY;
       float tau = -INFINITY, theta = -INFINITY;
+      // Threshold exchange between the two half-streams of a row (shared memory, monotone floats, stale reads are
+      // still valid bounds): besides its tau each stream publishes `mid`, its ceil(K/2)-th best value. At least
+      // 2*ceil(K/2) >= K items of the row score >= min(mid_a, mid_b), so that minimum is a lower bound of the K-th
+      // best of the UNION — about the threshold a single stream over all columns would have, which halves the
+      // number of candidates either stream lets through.
+      const int midx = K - (K + 1) / 2;                   // ascending list: index of the ceil(K/2)-th best
+      float mid = -INFINITY;
+      float* xch_own = tk + (size_t)half * 2 * kTcTM + r;          // [half][tau, mid][128]
+      float* xch_oth = tk + (size_t)(half ^ 1) * 2 * kTcTM + r;
+      xch_own[0] = -INFINITY; xch_own[kTcTM] = -INFINITY;
+      asm volatile("bar.sync 1, 256;" ::: "memory");               // both halves initialised before anyone reads
       int cnt = 0;
       bool overflow = false;
       int mcur = live ? P.mask_ptr[e] : 0;
@@ -231,13 +253,19 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
             tkr[j] = lo; tkr[j + 1] = hi;
           }
           tau = tkr[0];
-          theta = tau - eps2;
+          mid = select16(tkr, midx);
+          xch_own[0] = tau; xch_own[kTcTM] = mid;
+          theta = fmaxf(theta, tau - eps2);
         }
       };
 
       for (int it = 0; it < n_itiles; ++it) {
         mbar_wait(tfull + acc_e, aph_e);
         tc_fence_after();
+        {
+          const float tau_o = xch_oth[0], mid_o = xch_oth[kTcTM];
+          theta = fmaxf(theta, fmaxf(tau_o, fminf(mid, mid_o)) - eps2);
+        }
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_e * TN + half * (TN / 2);
 #pragma unroll 1
         for (int c0 = 0; c0 < TN / 2; c0 += 32) {
@@ -274,11 +302,13 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
 
       // ---- hand the second half-stream's state to the first; first half finishes the row ----
       if (half == 1) { tauB[r] = tau; cntB[r] = overflow ? -1 : cnt; }
+      xch_own[0] = tau; xch_own[kTcTM] = mid;
       asm volatile("bar.sync 1, 256;" ::: "memory");            // epilogue warps only
       if (half == 0 && live) {
         const float tau_b = tauB[r];
         const int cnt_b = cntB[r];
-        const float tau_f = fmaxf(tau, tau_b);                      // both are lower bounds of the K-th best s~
+        // all three are lower bounds of the K-th best s~ of the row
+        const float tau_f = fmaxf(fmaxf(tau, tau_b), fminf(mid, xch_oth[kTcTM]));
         const float theta_f = tau_f - eps2;
         bool fallback = overflow || cnt_b < 0 || tau_f == -INFINITY;
         int topi[kTcMaxK];
