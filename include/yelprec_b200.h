@@ -190,6 +190,13 @@ int yr_ngcf_tail(const float* const* E_layers, float* const* G_layers, int n_lay
 int yr_dense_opt_step(float* p, const float* g, float* m, float* v, int64_t n, const yr_opt* opt,
                       yr_stream stream);
 
+/* The same step over up to YR_OPT_MAX_TENSORS parameter tensors in ONE launch (host arrays of device pointers and
+ * element counts; every count a multiple of 4, every pointer 16-byte aligned). zero_grad != 0 clears each gradient
+ * after it has been consumed (optimizer.zero_grad() of the next step, trainers/cdae_trainer.py:42). */
+#define YR_OPT_MAX_TENSORS 8
+int yr_dense_opt_step_multi(int count, float* const* p, float* const* g, float* const* m, float* const* v,
+                            const int64_t* n, const yr_opt* opt, int zero_grad, yr_stream stream);
+
 /* Whole NGCFTrainer.train step (trainers/ngcf_trainer.py:106-115) as one host call: n_layers x layer_fwd,
  * tail (+loss), n_layers x layer_bwd, dense optimizer step over embedding.weight and every W1/W2.
  * All buffers are caller-owned; E[0] is the embedding parameter, E[1..n_layers] the layer outputs. */

@@ -22,7 +22,7 @@ SYMBOLS = (
     "yr_bpr_mf_train", "yr_bpr_mf_validate",
     "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
-    "yr_ngcf_tail", "yr_dense_opt_step", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
+    "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
@@ -135,6 +135,7 @@ def load() -> C.CDLL:
         "yr_ngcf_dense_bwd": (C.c_int, [i32, i64, p, p, p, p, p, p, f32, p, p, p, p, p, sz, p]),
         "yr_ngcf_tail": (C.c_int, [p, p, i32, i64, i64, i32, p, p, p, i64, p, p, p, p, p, p]),
         "yr_dense_opt_step": (C.c_int, [p, p, p, p, i64, C.POINTER(YrOpt), p]),
+        "yr_dense_opt_step_multi": (C.c_int, [i32, p, p, p, p, p, C.POINTER(YrOpt), i32, p]),
         "yr_ngcf_propagate": (C.c_int, [C.POINTER(YrNgcfState), f32, p]),
         "yr_ngcf_train_step": (C.c_int, [C.POINTER(YrNgcfState), C.POINTER(YrOpt), f32, p, p, p, i64, p, p]),
         "yr_ngcf_concat": (C.c_int, [p, i32, i64, i32, p, p]),

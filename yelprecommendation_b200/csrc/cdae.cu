@@ -56,16 +56,27 @@ cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep,
   const float* nr = neg ? neg + (int64_t)b * nI : nullptr;
   __shared__ int cx[NW], ct[NW];
   int nx = 0, nt = 0;
-  for (int64_t i0 = s0; i0 < s1; i0 += 32) {
-    const int64_t i = i0 + lane;
-    bool px = false, pt = false;
-    if (i < s1) {
-      const float v = kr ? xr[i] * kr[i] : xr[i];
-      px = v != 0.f;
-      if (tr) pt = (tr[i] + (nr ? nr[i] : 0.f)) != 0.f;
+  constexpr int UN = 8;                                   // 8 x 32 columns per round: all loads of a round are in flight
+  // pass 1: counts
+  for (int64_t i0 = s0; i0 < s1; i0 += 32 * UN) {
+    float xv_[UN], kv_[UN], tv_[UN], nv_[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t i = i0 + q * 32 + lane;
+      const bool in = i < s1;
+      xv_[q] = in ? xr[i] : 0.f;
+      kv_[q] = (in && kr) ? kr[i] : 1.f;
+      tv_[q] = (in && tr) ? tr[i] : 0.f;
+      nv_[q] = (in && nr) ? nr[i] : 0.f;
     }
-    nx += __popc(__ballot_sync(kFull, px));
-    nt += __popc(__ballot_sync(kFull, pt));
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const float v = kr ? xv_[q] * kv_[q] : xv_[q];
+      const bool px = v != 0.f;
+      const bool pt = tr ? ((tv_[q] + nv_[q]) != 0.f) : false;
+      nx += __popc(__ballot_sync(kFull, px));
+      nt += __popc(__ballot_sync(kFull, pt));
+    }
   }
   if (lane == 0) { cx[warp] = nx; ct[warp] = nt; }
   __syncthreads();
@@ -83,21 +94,31 @@ cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep,
   float* xv = w.xin_val + (int64_t)b * nI;
   int32_t* ti = w.tgt_idx + (int64_t)b * nI;
   float* tv = w.tgt_val + (int64_t)b * nI;
-  for (int64_t i0 = s0; i0 < s1; i0 += 32) {
-    const int64_t i = i0 + lane;
-    bool px = false, pt = false;
-    float v = 0.f, t = 0.f;
-    if (i < s1) {
-      v = kr ? xr[i] * kr[i] : xr[i];
-      px = v != 0.f;
-      if (tr) { t = tr[i]; pt = (t + (nr ? nr[i] : 0.f)) != 0.f; }
+  // pass 2: ordered writes (the second read of the row comes from L2)
+  for (int64_t i0 = s0; i0 < s1; i0 += 32 * UN) {
+    float xv_[UN], kv_[UN], tv_[UN], nv_[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t i = i0 + q * 32 + lane;
+      const bool in = i < s1;
+      xv_[q] = in ? xr[i] : 0.f;
+      kv_[q] = (in && kr) ? kr[i] : 1.f;
+      tv_[q] = (in && tr) ? tr[i] : 0.f;
+      nv_[q] = (in && nr) ? nr[i] : 0.f;
     }
-    const unsigned mx = __ballot_sync(kFull, px), mt = __ballot_sync(kFull, pt);
-    const unsigned lower = (1u << lane) - 1u;
-    if (px) { const int p = bx + __popc(mx & lower); xi[p] = (int32_t)i; xv[p] = v; }
-    if (pt) { const int p = bt + __popc(mt & lower); ti[p] = (int32_t)i; tv[p] = t; }
-    bx += __popc(mx);
-    bt += __popc(mt);
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t i = i0 + q * 32 + lane;
+      const float v = kr ? xv_[q] * kv_[q] : xv_[q];
+      const bool px = v != 0.f;
+      const bool pt = tr ? ((tv_[q] + nv_[q]) != 0.f) : false;
+      const unsigned mx = __ballot_sync(kFull, px), mt = __ballot_sync(kFull, pt);
+      const unsigned lower = (1u << lane) - 1u;
+      if (px) { const int p = bx + __popc(mx & lower); xi[p] = (int32_t)i; xv[p] = v; }
+      if (pt) { const int p = bt + __popc(mt & lower); ti[p] = (int32_t)i; tv[p] = tv_[q]; }
+      bx += __popc(mx);
+      bt += __popc(mt);
+    }
   }
 }
 
@@ -151,20 +172,37 @@ cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, c
   const float2 zz = make_float2(z_s[2 * lane], z_s[2 * lane + 1]);
   float2 dz = make_float2(0.f, 0.f);
   double lsum = 0.0;
-  for (int j = warp; j < nt; j += NW) {
-    const int item = ti[j];
-    const float t = tv[j];
-    const float2 wo = __ldg(reinterpret_cast<const float2*>(P.Wo + (int64_t)item * H) + lane);
-    float logit = warp_sum(fmaf(zz.x, wo.x, zz.y * wo.y)) + __ldg(P.bo + item);
-    const float p = sigmoidf_(logit);
-    // torch.nn.functional.binary_cross_entropy clamps both logs at -100
-    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
-    lsum += (double)(-(t * lp + (1.f - t) * lq));
-    if (GRAD) {
-      const float dl = (p - t) * inv_m;                        // d loss / d logit (mean over all loss positions)
-      dz.x = fmaf(dl, wo.x, dz.x); dz.y = fmaf(dl, wo.y, dz.y);
-      atomicAdd(reinterpret_cast<float2*>(Gr.Wo + (int64_t)item * H) + lane, make_float2(dl * zz.x, dl * zz.y));
-      if (lane == 0) atomicAdd(Gr.bo + item, dl);
+  constexpr int UN = 4;                        // 4 positions per warp round: ids, then the 4 Wo rows, are in flight together
+  for (int j0 = warp * UN; j0 < nt; j0 += NW * UN) {
+    int item[UN];
+    float t[UN], bo[UN];
+    float2 wo[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const bool in = j0 + q < nt;
+      item[q] = in ? ti[j0 + q] : -1;
+      t[q] = in ? tv[j0 + q] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int it = item[q] < 0 ? 0 : item[q];
+      wo[q] = __ldg(reinterpret_cast<const float2*>(P.Wo + (int64_t)it * H) + lane);
+      bo[q] = __ldg(P.bo + it);
+    }
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      if (item[q] < 0) continue;                                 // warp-uniform
+      const float logit = warp_sum(fmaf(zz.x, wo[q].x, zz.y * wo[q].y)) + bo[q];
+      const float p = sigmoidf_(logit);
+      // torch.nn.functional.binary_cross_entropy clamps both logs at -100
+      const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
+      lsum += (double)(-(t[q] * lp + (1.f - t[q]) * lq));
+      if (GRAD) {
+        const float dl = (p - t[q]) * inv_m;                     // d loss / d logit (mean over all loss positions)
+        dz.x = fmaf(dl, wo[q].x, dz.x); dz.y = fmaf(dl, wo[q].y, dz.y);
+        atomicAdd(reinterpret_cast<float2*>(Gr.Wo + (int64_t)item[q] * H) + lane, make_float2(dl * zz.x, dl * zz.y));
+        if (lane == 0) atomicAdd(Gr.bo + item[q], dl);
+      }
     }
   }
   if (lane == 0) loss_s[warp] = lsum;
@@ -307,10 +345,25 @@ extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* gra
       {P->Vu, grads->Vu, adam ? m->Vu : nullptr, adam ? v->Vu : nullptr, nU * h},
       {P->Wo, grads->Wo, adam ? m->Wo : nullptr, adam ? v->Wo : nullptr, nI * h},
       {P->bo, grads->bo, adam ? m->bo : nullptr, adam ? v->bo : nullptr, nI}};
+  // one launch for the tensors whose size is a multiple of 4 (all of them at h = 64 and a catalog size % 4 == 0),
+  // gradients cleared in the same pass; anything else takes the single-tensor path
+  float *pp[5], *gg[5], *mm[5], *vv[5];
+  int64_t nn[5];
+  int cnt = 0;
   for (auto& t : ts) {
-    int rc = yr_dense_opt_step(t.p, t.g, t.m, t.v, t.n, opt, stream);
+    const bool aligned = ((t.n & 3) == 0) &&
+        ((((uintptr_t)t.p | (uintptr_t)t.g | (adam ? ((uintptr_t)t.m | (uintptr_t)t.v) : 0)) & 15) == 0);
+    if (aligned) {
+      pp[cnt] = t.p; gg[cnt] = t.g; mm[cnt] = t.m; vv[cnt] = t.v; nn[cnt++] = t.n;
+    } else {
+      int rc = yr_dense_opt_step(t.p, t.g, t.m, t.v, t.n, opt, stream);
+      if (rc) return rc;
+      YR_CUDA(cudaMemsetAsync(t.g, 0, sizeof(float) * (size_t)t.n, s));
+    }
+  }
+  if (cnt) {
+    int rc = yr_dense_opt_step_multi(cnt, pp, gg, mm, vv, nn, opt, 1, stream);
     if (rc) return rc;
-    YR_CUDA(cudaMemsetAsync(t.g, 0, sizeof(float) * (size_t)t.n, s));
   }
   return YR_OK;
 }

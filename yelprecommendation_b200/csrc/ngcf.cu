@@ -228,6 +228,42 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
   }
 }
 
+// Several parameter tensors in ONE launch (a step of a model with many small tensors is launch-bound otherwise).
+// Tensor t covers float4 units [start4[t], start4[t+1]) of a virtual concatenation; sizes must be multiples of 4.
+struct MultiOptArgs {
+  float* p[YR_OPT_MAX_TENSORS]; float* g[YR_OPT_MAX_TENSORS]; float* m[YR_OPT_MAX_TENSORS]; float* v[YR_OPT_MAX_TENSORS];
+  int64_t start4[YR_OPT_MAX_TENSORS + 1];
+  int count, zero_grad;
+};
+
+__global__ void __launch_bounds__(256)
+dense_opt_multi_kernel(MultiOptArgs a, yr_opt opt) {
+  OptScalars os;
+  opt_scalars_for_step(os, opt, opt.step);
+  const bool adam = opt.kind != YR_OPT_SGD;
+  const int64_t total4 = a.start4[a.count];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    int t = 0;
+#pragma unroll
+    for (int q = 1; q < YR_OPT_MAX_TENSORS; ++q) t += (q < a.count && i >= a.start4[q]) ? 1 : 0;
+    const int64_t k = i - a.start4[t];
+    float4* pp = reinterpret_cast<float4*>(a.p[t]) + k;
+    float4* gp = reinterpret_cast<float4*>(a.g[t]) + k;
+    float4 pv = *pp;
+    const float4 gv = *gp;
+    float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
+    if (adam) { mv = reinterpret_cast<float4*>(a.m[t])[k]; vv = reinterpret_cast<float4*>(a.v[t])[k]; }
+    opt_update(os, pv.x, gv.x, mv.x, vv.x);
+    opt_update(os, pv.y, gv.y, mv.y, vv.y);
+    opt_update(os, pv.z, gv.z, mv.z, vv.z);
+    opt_update(os, pv.w, gv.w, mv.w, vv.w);
+    *pp = pv;
+    if (adam) { reinterpret_cast<float4*>(a.m[t])[k] = mv; reinterpret_cast<float4*>(a.v[t])[k] = vv; }
+    if (a.zero_grad) *gp = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // dW[idx] = sum over CTA partials in CTA order (deterministic).
 // Block = 32 outputs x 8 partial-groups: group g sums partials g, g+8, ... (8 loads in flight), then the 8 group
 // sums are added in group order.
@@ -500,6 +536,32 @@ extern "C" int yr_dense_opt_step(float* p, const float* g, float* m, float* v, i
   return YR_OK;
 }
 
+extern "C" int yr_dense_opt_step_multi(int count, float* const* p, float* const* g, float* const* m, float* const* v,
+                                       const int64_t* n, const yr_opt* opt, int zero_grad, yr_stream stream) {
+  if (count < 0 || count > YR_OPT_MAX_TENSORS || !p || !g || !n || !opt) return YR_ERR_BAD_ARG;
+  if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
+  const bool adam = opt->kind != YR_OPT_SGD;
+  if (adam && (!m || !v)) return YR_ERR_BAD_ARG;
+  MultiOptArgs a;
+  a.count = 0; a.zero_grad = zero_grad ? 1 : 0; a.start4[0] = 0;
+  for (int t = 0; t < count; ++t) {
+    if (n[t] < 0 || (n[t] & 3) || !p[t] || !g[t] || (adam && (!m[t] || !v[t]))) return YR_ERR_BAD_ARG;
+    if (((uintptr_t)p[t] | (uintptr_t)g[t] | (adam ? ((uintptr_t)m[t] | (uintptr_t)v[t]) : 0)) & 15) return YR_ERR_BAD_ARG;
+    if (n[t] == 0) continue;
+    const int c = a.count++;
+    a.p[c] = p[t]; a.g[c] = g[t]; a.m[c] = adam ? m[t] : nullptr; a.v[c] = adam ? v[t] : nullptr;
+    a.start4[c + 1] = a.start4[c] + (n[t] >> 2);
+  }
+  if (a.count == 0) return YR_OK;
+  const int threads = 256;
+  int64_t blocks = (a.start4[a.count] + threads - 1) / threads;
+  const int64_t cap = (int64_t)yr_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  dense_opt_multi_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(a, *opt);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Composite entry points: a whole propagate / train step per host call.
 // ---------------------------------------------------------------------------------------------
@@ -566,12 +628,20 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
                            st->ws, st->ws_bytes, stream);
     if (rc) return rc;
   }
-  rc = yr_dense_opt_step(st->E[0], st->G[0], st->mE, st->vE, n * d, opt, stream);
-  if (rc) return rc;
+  // embedding.weight and the 2L weights: parameter order of nn.Module.parameters() does not matter for a per-tensor
+  // optimizer; two launches (1 + 2L <= 15 tensors, 8 per launch)
+  float *pp[2 * YR_NGCF_MAX_LAYERS + 1], *gg[2 * YR_NGCF_MAX_LAYERS + 1], *mm[2 * YR_NGCF_MAX_LAYERS + 1],
+      *vv[2 * YR_NGCF_MAX_LAYERS + 1];
+  int64_t nn[2 * YR_NGCF_MAX_LAYERS + 1];
+  int cnt = 0;
+  pp[cnt] = st->E[0]; gg[cnt] = st->G[0]; mm[cnt] = st->mE; vv[cnt] = st->vE; nn[cnt++] = n * d;
   for (int l = 0; l < L; ++l) {
-    rc = yr_dense_opt_step(st->W1[l], st->dW1[l], st->mW1[l], st->vW1[l], (int64_t)d * d, opt, stream);
-    if (rc) return rc;
-    rc = yr_dense_opt_step(st->W2[l], st->dW2[l], st->mW2[l], st->vW2[l], (int64_t)d * d, opt, stream);
+    pp[cnt] = st->W1[l]; gg[cnt] = st->dW1[l]; mm[cnt] = st->mW1[l]; vv[cnt] = st->vW1[l]; nn[cnt++] = (int64_t)d * d;
+    pp[cnt] = st->W2[l]; gg[cnt] = st->dW2[l]; mm[cnt] = st->mW2[l]; vv[cnt] = st->vW2[l]; nn[cnt++] = (int64_t)d * d;
+  }
+  for (int c0 = 0; c0 < cnt; c0 += YR_OPT_MAX_TENSORS) {
+    const int c = (cnt - c0 < YR_OPT_MAX_TENSORS) ? cnt - c0 : YR_OPT_MAX_TENSORS;
+    rc = yr_dense_opt_step_multi(c, pp + c0, gg + c0, mm + c0, vv + c0, nn + c0, opt, 0, stream);
     if (rc) return rc;
   }
   return YR_OK;
