@@ -146,6 +146,9 @@ int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate
  * Applies to the forward transform; process-wide. */
 int yr_ngcf_set_dense_mode(int mode);
 int yr_ngcf_get_dense_mode(void);
+/* yr_ngcf_train_step, top layer: 1 (default) = backward on the batch rows only (dLoss/dE_L is zero elsewhere) with
+ * G += L^T T as a scatter from those rows; 0 = the dense layer backward. Same sums, different fp32 order. */
+int yr_ngcf_set_top_rows_mode(int mode);
 
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
  *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
@@ -218,6 +221,9 @@ typedef struct yr_ngcf_state {
   void* ws; size_t ws_bytes;          /* >= yr_ngcf_layer_bwd_ws_bytes(d) */
   double* loss;                       /* device double[2]: [0] running sum of batch means, [1] scratch (zero) */
   int32_t* err;
+  /* optional scratch for the row-sparse top-layer backward of yr_ngcf_train_step (all NULL/0 = dense everywhere):
+   * row_flag [n] and row_count [1] zero between steps, row_list [row_list_cap], row_list_cap >= 3 * B */
+  int32_t* row_flag; int32_t* row_list; int32_t* row_count; int64_t row_list_cap;
 } yr_ngcf_state;
 
 /* forward only: fills E[1..n_layers] (and LE[]) — used by validate / evaluate (propagate ONCE, not per user) */

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import cport, torch_port as tp
-from util import RTOL, batches_from, cfg, load_npz, rel_err
+from util import rel_fro, RTOL, batches_from, cfg, load_npz, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -149,6 +149,31 @@ def test_train_steps_vs_reference_golden(ci):
     for l in range(3):
         assert rel_err(sd[f"W1.{l}.weight"].cpu().numpy(), g[f"ngcf_{ci}_final_W1.{l}.weight"]) < 5e-5
         assert rel_err(sd[f"W2.{l}.weight"].cpu().numpy(), g[f"ngcf_{ci}_final_W2.{l}.weight"]) < 5e-5
+
+
+@pytest.mark.parametrize("name,lr", [("sgd", 0.05), ("adam", 1e-3)])
+def test_row_sparse_top_layer_equals_dense_step(name, lr):
+    """yr_ngcf_train_step: last-layer forward/backward on the <= 3B batch rows + scatter form of L^T T (default) vs the
+    dense layer everywhere (yr_ngcf_set_top_rows_mode(0)) — same sums in a different fp32 order: 1e-6 norm-wise here.
+    validate()/evaluate() after a row-sparse step must see a fully recomputed propagation (no stale rows)."""
+    from yelprecommendation_b200 import _cabi
+    lib = _cabi.load()
+    g, nU, nI, L, *_ = _golden()
+    batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 128, limit=4)
+    out = {}
+    for mode in (1, 0):
+        lib.yr_ngcf_set_top_rows_mode(mode)
+        try:
+            tr = _trainer(g, nU, nI, L, name, lr, 0.0)
+            total = tr.train(batches)
+            sd = {k: v.detach().cpu().numpy().copy() for k, v in tr.model.state_dict().items()}
+            out[mode] = (total, tr.last_step_losses.cpu().numpy().copy(), sd, tr.validate(batches))
+        finally:
+            lib.yr_ngcf_set_top_rows_mode(1)
+    (ta, la, sa, va), (tb, lb, sb, vb) = out[1], out[0]
+    assert isclose(ta, tb, rel_tol=1e-6) and rel_err(la, lb) < 1e-6 and isclose(va, vb, rel_tol=1e-6)
+    for k in sb:
+        assert rel_fro(sa[k], sb[k]) < 1e-6, k
 
 
 def test_dropin_model_signatures_and_autograd():

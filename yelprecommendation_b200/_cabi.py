@@ -25,7 +25,7 @@ SYMBOLS = (
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
-    "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode",
+    "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode", "yr_ngcf_set_top_rows_mode",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_output", "yr_cdae_step", "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
     "yr_sample_negatives", "yr_laplacian_ws_bytes", "yr_laplacian_build",
@@ -91,7 +91,8 @@ class YrNgcfState(C.Structure):
                 ("mW1", _PL), ("vW1", _PL), ("mW2", _PL), ("vW2", _PL),
                 ("E_dev", C.c_void_p), ("G_dev", C.c_void_p),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
-                ("loss", C.c_void_p), ("err", C.c_void_p)]
+                ("loss", C.c_void_p), ("err", C.c_void_p),
+                ("row_flag", C.c_void_p), ("row_list", C.c_void_p), ("row_count", C.c_void_p), ("row_list_cap", C.c_int64)]
 
 
 class YelprecError(RuntimeError):
@@ -161,6 +162,7 @@ def load() -> C.CDLL:
         "yr_shard_step": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), i64, p]),
         "yr_ngcf_set_dense_mode": (C.c_int, [i32]),
         "yr_ngcf_get_dense_mode": (C.c_int, []),
+        "yr_ngcf_set_top_rows_mode": (C.c_int, [i32]),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),
         "yr_eval_tc_ws_bytes": (sz, [i64]),
         "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,

@@ -104,10 +104,14 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
                       const float* __restrict__ Enext, const float* __restrict__ Gnext,
                       const float* __restrict__ W1, const float* __restrict__ W2, float slope,
                       int64_t n, float* __restrict__ G, float* __restrict__ T,
-                      float* __restrict__ ws) {
+                      float* __restrict__ ws, const int32_t* __restrict__ row_list,
+                      const int32_t* __restrict__ row_count) {
+  // row_list != NULL: only the listed rows carry a gradient (top layer of a BPR step: the 3B batch rows); tile row q
+  // is graph row row_list[q], everything else is unchanged.
   using C = DenseCfg<D>;
   constexpr int TM = C::TM;
   static_assert(C::kColGroups * C::kColGroups == C::kThreads, "dW tiling assumes D == 64");
+  if (row_list) n = *row_count;
   extern __shared__ __align__(16) float smem[];
   float* dZs = smem;                    // [TM][D]
   float* Ss = dZs + TM * D;             // [TM][D]  LE + E
@@ -135,7 +139,7 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       const int r = idx / (D / 4), c4 = idx % (D / 4);
       float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), pv = sv, dz = sv;
       if (r0 + r < n) {
-        const int64_t off = (r0 + r) * D;
+        const int64_t off = (row_list ? (int64_t)row_list[r0 + r] : (r0 + r)) * D;
         const float4 e = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
         const float4 le = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
         const float4 en = __ldg(reinterpret_cast<const float4*>(Enext + off) + c4);
@@ -183,8 +187,9 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int rl = ty * 4 + i;
-      const int64_t r = r0 + rl;
+      int64_t r = r0 + rl;
       if (r < n) {
+        if (row_list) r = row_list[r];
         // E / LE again (L1/L2 hits: this CTA has just read the tile) — shared memory holds S and P instead
         const float4 e = __ldg(reinterpret_cast<const float4*>(E + r * D) + tx);
         const float4 le = __ldg(reinterpret_cast<const float4*>(LE + r * D) + tx);
@@ -418,6 +423,13 @@ extern "C" int yr_ngcf_set_dense_mode(int mode) {
   return YR_OK;
 }
 extern "C" int yr_ngcf_get_dense_mode(void) { return g_dense_mode; }
+// 1 (default) = the top layer's backward of yr_ngcf_train_step runs on the batch rows only; 0 = dense (debug / A-B)
+static int g_top_rows_mode = 1;
+extern "C" int yr_ngcf_set_top_rows_mode(int mode) {
+  if (mode != 0 && mode != 1) return YR_ERR_BAD_ARG;
+  g_top_rows_mode = mode;
+  return YR_OK;
+}
 
 extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
                                  float slope, float* E_next, yr_stream stream) {
@@ -474,10 +486,106 @@ extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* 
   int64_t grid = (int64_t)yr_sm_count() * kBwdCtasPerSm;
   if (grid > n_tiles) grid = n_tiles;
   ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
-      E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws);
+      E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, nullptr, nullptr);
   YR_CHECK_LAUNCH();
   const int len = 2 * d * d;
   reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+// ---- top layer of a BPR step: only the <= 3B batch rows carry a gradient -------------------------------------
+namespace yr {
+__global__ void __launch_bounds__(256)
+touched_rows_kernel(const int64_t* __restrict__ uid, const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                    int64_t B, int64_t nU, int64_t nI, int32_t* flag, int32_t* list, int32_t* count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B; i += (int64_t)gridDim.x * blockDim.x) {
+    const int which = (int)(i / B);
+    const int64_t b = i - which * B;
+    const int64_t id = which == 0 ? uid[b] : (which == 1 ? pos[b] : neg[b]);
+    if (id < 0 || id >= (which == 0 ? nU : nI)) continue;          // the tail kernel has flagged the error
+    const int64_t row = which == 0 ? id : nU + id;
+    if (atomicExch(flag + row, 1) == 0) list[atomicAdd(count, 1)] = (int32_t)row;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+untouch_rows_kernel(int32_t* flag, const int32_t* __restrict__ list, int32_t* count) {
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flag[list[i]] = 0;
+  __syncthreads();
+  // single block launch: the counter is re-armed once every listed flag has been cleared
+  if (threadIdx.x == 0) *count = 0;
+}
+
+// G += A^T T restricted to the flagged rows j of T: every stored A[j, i] scatters a(j,i) * T[j] into G[i] with one
+// vector RED per lane. Walks the SpMM plan of A (chunks of <= 128 non-zeros), so hub rows are spread over many groups.
+template <int D>
+__global__ void __launch_bounds__(256)
+spmm_scatter_rows_kernel(yr_csr A, const int32_t* __restrict__ flag, const float* __restrict__ T, float* __restrict__ G) {
+  constexpr int kVec = D / 4, LPR = kVec >= 32 ? 32 : kVec, VPT = kVec / LPR, CPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int4* __restrict__ desc = reinterpret_cast<const int4*>(A.chunk_desc);
+  for (int cb = gwarp * CPW; cb < A.n_chunks; cb += nwarps * CPW) {
+    const int c = cb + sub;
+    int4 dsc = make_int4(0, 0, 0, -1);
+    if (c < A.n_chunks) dsc = __ldg(desc + c);
+    const int row = dsc.x, s0 = dsc.y;
+    int len = dsc.z & 0xff;
+    if (c >= A.n_chunks || !__ldg(flag + row)) len = 0;
+    int maxlen = len;
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, o));
+    if (maxlen == 0) continue;
+    float4 t[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+      t[v] = len ? reinterpret_cast<const float4*>(T + (int64_t)row * D)[sl * VPT + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < maxlen; j0 += LPR) {
+      const int j = j0 + sl;
+      const int cc = (j < len) ? __ldg(A.col + s0 + j) : -1;
+      const float aa = (j < len) ? __ldg(A.val + s0 + j) : 0.f;
+      for (int q = 0; q < LPR && j0 + q < maxlen; ++q) {
+        const int cq = __shfl_sync(kFull, cc, q, LPR);
+        const float a = __shfl_sync(kFull, aa, q, LPR);
+        if (cq >= 0) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+            atomicAdd(reinterpret_cast<float4*>(G + (int64_t)cq * D) + sl * VPT + v,
+                      make_float4(a * t[v].x, a * t[v].y, a * t[v].z, a * t[v].w));
+        }
+      }
+    }
+  }
+}
+}  // namespace yr
+
+// dense backward of one layer on the listed rows + scatter form of G += L^T T (ngcf_train_step, top layer)
+static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cudaStream_t s) {
+  const int d = st->d;
+  using C = DenseCfg<64>;
+  if (d != 64) return YR_ERR_BAD_DIM;
+  int64_t grid = (st->row_list_cap + C::TM - 1) / C::TM;
+  const int64_t cap = (int64_t)yr_sm_count() * kBwdCtasPerSm;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBwd));
+    attr_set = true;
+  }
+  ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
+      st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope, st->nU + st->nI, st->G[l], st->T,
+      (float*)st->ws, st->row_list, st->row_count);
+  YR_CHECK_LAUNCH();
+  const int len = 2 * d * d;
+  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)st->ws, (int)grid, len, st->dW1[l], st->dW2[l], d * d);
+  YR_CHECK_LAUNCH();
+  const int wpb = 8, cpw = 2;
+  int64_t blocks = ((int64_t)st->L.n_chunks + wpb * cpw - 1) / (wpb * cpw);
+  spmm_scatter_rows_kernel<64><<<(unsigned)blocks, 256, 0, s>>>(st->L, st->row_flag, st->T, st->G[l]);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }
@@ -616,13 +724,43 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
     if (!st->G[l]) return YR_ERR_BAD_ARG;
     YR_CUDA(cudaMemsetAsync(st->G[l], 0, sizeof(float) * (size_t)n * d, s));
   }
-  rc = yr_ngcf_propagate(st, slope, stream);
-  if (rc) return rc;
+  // Top layer: E_L is READ only at the <= 3B rows the batch touches (the tail) and dLoss/dE_L is non-zero only there.
+  // So the last layer's forward (SpMM + transform) and backward run on those rows, and G_{L-1} += L^T T becomes a
+  // scatter from them (same sums, different fp32 order). Needs the row scratch; E_L / LE_{L-1} keep stale values in
+  // the other rows (yr_ngcf_propagate recomputes everything for validate / evaluate).
+  const bool rows_path = st->row_flag && st->row_list && st->row_count && st->row_list_cap >= 3 * B && d == 64 &&
+                         g_top_rows_mode;
+  if (rows_path) {
+    touched_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, s>>>(uid, pos, neg, B, st->nU, st->nI, st->row_flag,
+                                                                       st->row_list, st->row_count);
+    YR_CHECK_LAUNCH();
+  }
+  if (rows_path && g_dense_mode == 1) {
+    for (int l = 0; l + 1 < L; ++l) {
+      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+      if (rc) return rc;
+    }
+    rc = yr_spmm_csr_rows(&st->L, d, st->E[L - 1], st->LE[L - 1], st->row_flag, s);
+    if (rc) return rc;
+    rc = yr_ngcf_dense_fwd_tc_launch(st->E[L - 1], st->LE[L - 1], st->W1[L - 1], st->W2[L - 1], slope, n, st->E[L], s,
+                                     st->row_list, st->row_count, 3 * B);
+    if (rc) return rc;
+  } else {
+    rc = yr_ngcf_propagate(st, slope, stream);
+    if (rc) return rc;
+  }
   rc = yr_ngcf_tail(st->E_dev, st->G_dev, L, st->nU, st->nI, d, uid, pos, neg, B, nullptr, nullptr, st->loss,
                     step_loss, st->err, stream);
   if (rc) return rc;
   for (int l = L - 1; l >= 0; --l) {
     if (!st->dW1[l] || !st->dW2[l]) return YR_ERR_BAD_ARG;
+    if (rows_path && l == L - 1) {
+      rc = ngcf_layer_bwd_rows(st, l, slope, s);
+      if (rc) return rc;
+      untouch_rows_kernel<<<1, 256, 0, s>>>(st->row_flag, st->row_list, st->row_count);
+      YR_CHECK_LAUNCH();
+      continue;
+    }
     rc = yr_ngcf_layer_bwd(&st->LT, d, st->E[l], st->LE[l], st->E[l + 1],
                            st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l], st->T, st->dW1[l], st->dW2[l],
                            st->ws, st->ws_bytes, stream);

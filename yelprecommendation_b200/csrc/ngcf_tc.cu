@@ -21,8 +21,12 @@ constexpr int kFwdTM = 128;
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ W1,
-                         const float* __restrict__ W2, float slope, int64_t n, float* __restrict__ Eout) {
+                         const float* __restrict__ W2, float slope, int64_t n, float* __restrict__ Eout,
+                         const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+  // row_list != NULL: tile row q is graph row row_list[q] (only those rows are transformed: the batch rows of the
+  // last layer in a BPR step)
   constexpr int D = 64;
+  if (row_list) n = *row_count;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
   // A operands: S_hi, S_lo, P_hi, P_lo  [128 x 64] each = 32 KB;  B operands: W1_hi, W1_lo, W2_hi, W2_lo [64 x 64] = 16 KB
@@ -74,9 +78,10 @@ ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
       const int64_t lim4 = n * (D / 4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int64_t g = base4 + tid + 256 * i;
+        int64_t g = base4 + tid + 256 * i;
         e[i] = make_float4(0.f, 0.f, 0.f, 0.f); le[i] = e[i];
         if (g < lim4) {
+          if (row_list) g = (int64_t)row_list[g >> 4] * (D / 4) + (g & 15);
           e[i] = __ldg(reinterpret_cast<const float4*>(E) + g);
           le[i] = __ldg(reinterpret_cast<const float4*>(LE) + g);
         }
@@ -121,7 +126,7 @@ ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
       tc_fence_before();
       mbar_arrive(d_empty + acc);                        // accumulator stage free again
       if (row < n) {
-        float4* o4 = reinterpret_cast<float4*>(Eout + row * D);
+        float4* o4 = reinterpret_cast<float4*>(Eout + (row_list ? (int64_t)row_list[row] : row) * D);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 o;
@@ -185,17 +190,19 @@ using namespace yr;
 
 // internal launcher used by yr_ngcf_layer_fwd (ngcf.cu)
 int yr_ngcf_dense_fwd_tc_launch(const float* E, const float* LE, const float* W1, const float* W2, float slope,
-                                int64_t n, float* Eout, cudaStream_t s) {
+                                int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list,
+                                const int32_t* row_count, int64_t row_cap) {
   const size_t smem = 4 * 32768 + 4 * 16384 + 64 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int64_t n_tiles = (n + kFwdTM - 1) / kFwdTM;
+  const int64_t n_tiles = ((row_list ? row_cap : n) + kFwdTM - 1) / kFwdTM;
   int64_t grid = yr_sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  ngcf_dense_fwd_tc_kernel<<<(unsigned)grid, kFwdThreads, smem, s>>>(E, LE, W1, W2, slope, n, Eout);
+  if (grid < 1) grid = 1;
+  ngcf_dense_fwd_tc_kernel<<<(unsigned)grid, kFwdThreads, smem, s>>>(E, LE, W1, W2, slope, n, Eout, row_list, row_count);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }

@@ -28,7 +28,7 @@ __device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
 
 template <int D, bool ACC>
 __global__ void __launch_bounds__(256, D <= 64 ? 3 : 2)
-spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) {
+spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, const int32_t* __restrict__ row_flag) {
   using C = SpmmCfg<D>;
   constexpr int LPR = C::LPR, VPT = C::VPT, CPW = C::CPW;
   const int lane = threadIdx.x & 31;
@@ -40,14 +40,18 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
 
   for (int cb = gwarp * CPW; cb < A.n_chunks; cb += nwarps * CPW) {
     const int c = cb + sub;
+    bool c_valid = c < A.n_chunks;
     int4 dsc = make_int4(0, 0, 0, -1);
     if (c < A.n_chunks) dsc = __ldg(desc + c);
+    // row subset (last layer of a BPR step): chunks of unflagged rows behave like padding; all chunks of a row share
+    // the flag, so the split-row arrival count stays consistent
+    if (row_flag && c < A.n_chunks && !__ldg(row_flag + dsc.x)) { dsc = make_int4(0, 0, 0, -1); c_valid = false; }
     const int row = dsc.x, s = dsc.y, len = dsc.z & 0xff, slot = dsc.w;
     const int split_idx = dsc.z >> 8;            // index into split_row / split_ptr / split_count (split chunks only)
     float4 acc[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ACC && slot < 0 && len >= 0 && c < A.n_chunks) {
+    if (ACC && slot < 0 && len >= 0 && c_valid) {
 #pragma unroll
       for (int v = 0; v < VPT; ++v) acc[v] = reinterpret_cast<const float4*>(Y + (int64_t)row * D)[sl * VPT + v];
     }
@@ -85,7 +89,7 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
         }
       }
     }
-    if (c < A.n_chunks) {
+    if (c_valid) {
       float4* dst = (slot < 0) ? reinterpret_cast<float4*>(Y + (int64_t)row * D)
                                : reinterpret_cast<float4*>(A.partials + (int64_t)slot * D);
 #pragma unroll
@@ -93,7 +97,7 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
     }
     // ---- split rows: the chunk that arrives LAST sums the row's partials left to right (deterministic order).
     // Long rows' chunks are scheduled first (plan order), so this tail work overlaps the bulk of the kernel.
-    const bool is_split = (c < A.n_chunks) && slot >= 0;
+    const bool is_split = (c_valid) && slot >= 0;
     if (__any_sync(kFull, is_split)) {
       if (is_split) __threadfence();                       // my part of the partial is visible device-wide
       __syncwarp();
@@ -147,14 +151,15 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y) 
 }
 
 template <int D>
-static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s) {
+static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s,
+                       const int32_t* row_flag = nullptr) {
   using C = SpmmCfg<D>;
   const int threads = 256, wpb = threads / 32;
   int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
   const int64_t cap = (int64_t)yr_sm_count() * 8 * 16;
   if (blocks > cap) blocks = cap;
-  if (accumulate) spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
-  else spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y);
+  if (accumulate) spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y, row_flag);
+  else spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y, row_flag);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }
@@ -205,6 +210,20 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     ++c;
   }
   return YR_OK;
+}
+
+int yr_spmm_csr_rows(const yr_csr* A, int d, const float* X, float* Y, const int32_t* row_flag, cudaStream_t s) {
+  int rc = yr_csr_ok(A);
+  if (rc) return rc;
+  if (!X || !Y) return YR_ERR_BAD_ARG;
+  if (A->n_rows == 0 || A->n_chunks == 0) return YR_OK;
+  switch (d) {
+    case 32: return launch_spmm<32>(A, X, Y, 0, s, row_flag);
+    case 64: return launch_spmm<64>(A, X, Y, 0, s, row_flag);
+    case 128: return launch_spmm<128>(A, X, Y, 0, s, row_flag);
+    case 256: return launch_spmm<256>(A, X, Y, 0, s, row_flag);
+    default: return YR_ERR_BAD_DIM;
+  }
 }
 
 extern "C" int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream) {

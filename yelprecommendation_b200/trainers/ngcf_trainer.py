@@ -37,6 +37,8 @@ class NGCFTrainer(BaseTrainer):
         self.loss = self._loss()
         self.laplacian_matrix = laplacian_matrix
         self._bufs = None
+        # batches up to this many triples use the row-sparse top-layer backward (larger ones run it densely)
+        self._row_cap = max(int(getattr(cfg, "batch_size", 0) or 0), 4096)
         self._stager = None
         self._eval_cache = {}
         self.last_step_losses = None
@@ -63,7 +65,9 @@ class NGCFTrainer(BaseTrainer):
                  "E": [z(n, d) for _ in range(L)], "LE": [z(n, d) for _ in range(L)],
                  "G": [z(n, d) for _ in range(L + 1)], "T": z(n, d),
                  "dW1": [z(d, d) for _ in range(L)], "dW2": [z(d, d) for _ in range(L)],
-                 "loss": z(2, dt=F64), "err": z(1, dt=I32)}
+                 "loss": z(2, dt=F64), "err": z(1, dt=I32),
+                 # row scratch of the row-sparse top-layer backward (flags / count stay zero between steps)
+                 "row_flag": z(n, dt=I32), "row_list": z(3 * self._row_cap, dt=I32), "row_count": z(1, dt=I32)}
             nbytes = lib.yr_ngcf_layer_bwd_ws_bytes(d)
             b["ws"] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             b["E_dev"] = ops.device_ptr_array([E0] + b["E"])
@@ -92,6 +96,8 @@ class NGCFTrainer(BaseTrainer):
         st.E_dev, st.G_dev = p(b["E_dev"]), p(b["G_dev"])
         st.ws, st.ws_bytes = p(b["ws"]), b["ws"].numel()
         st.loss, st.err = p(b["loss"]), p(b["err"])
+        st.row_flag, st.row_list, st.row_count = p(b["row_flag"]), p(b["row_list"]), p(b["row_count"])
+        st.row_list_cap = b["row_list"].numel()
         return st, b
 
     def _get_stager(self, dataloader) -> BatchStager:
