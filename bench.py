@@ -318,14 +318,17 @@ def main():
     # profiles/ launch list). Its algorithmic HBM bytes are CSR + read X + write Y; what it actually lives on is the
     # L2->SM gather traffic nnz * d * 4 (X is L2-resident), reported next to it.
     dom = "spmm_csr"
-    spmm_share = 2 * LAYERS * pieces[dom]["ms"] / (ms / K)
+    # per step: 2 (LAYERS - 1) full SpMMs (forward + backward of every layer but the last) + the last layer's forward
+    # on the batch rows and its backward as a scatter from them (both ~half the non-zeros: popular positives)
+    n_full_spmm = 2 * (LAYERS - 1)
+    spmm_share = n_full_spmm * pieces[dom]["ms"] / (ms / K)
     gather_bytes = nnzL * D * 4
     roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<64> (yr_spmm_csr)", "achieved": pieces[dom]["gbs"],
                 "peak": pk["hbm"], "unit": "GB/s", "frac": pieces[dom]["gbs"] / pk["hbm"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/): see DESIGN.md
                 "traffic": NCU_SPMM_DRAM_BYTES, "peak_source": pk["src"],
                 "launch_ms": pieces[dom]["ms"], "alg_bytes_per_launch": pieces[dom]["alg_bytes"],
-                "launches_per_step": 2 * LAYERS, "share_of_step": spmm_share,
+                "launches_per_step": n_full_spmm, "share_of_step": spmm_share,
                 "l2_gather": {"bytes_per_launch": gather_bytes, "achieved_GBps": gather_bytes / (pieces[dom]["ms"] * 1e-3) / 1e9,
                               "note": "every non-zero gathers one 256 B row of the L2-resident operand; this, not HBM, bounds the kernel"},
                 "step": {"alg_bytes": step_alg_bytes, "achieved": step_alg_bytes / (ms / K * 1e-3) / 1e9,
@@ -558,7 +561,9 @@ def main():
                         "ms_per_step": 1e3 * dt / n_cpu}
 
     if rank == 0:
-        launches_per_step = LAYERS * 2 + 2 + LAYERS * 3 + 1 + 2 * LAYERS
+        # kernels of one yr_ngcf_train_step (profiles/ launch list): touched rows 1, forward 2 per layer, tail 2,
+        # backward: last layer 4 (dense-on-rows, reduce, scatter, clear) + 3 per other layer, optimizer 1
+        launches_per_step = 1 + 2 * LAYERS + 2 + 4 + 3 * (LAYERS - 1) + 1
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -510,12 +510,9 @@ touched_rows_kernel(const int64_t* __restrict__ uid, const int64_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-untouch_rows_kernel(int32_t* flag, const int32_t* __restrict__ list, int32_t* count) {
-  const int n = *count;
+untouch_rows_kernel(int32_t* flag, const int32_t* __restrict__ list, const int32_t* __restrict__ count) {
+  const int n = *count;                 // the counter itself is cleared by a memset node after this kernel
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flag[list[i]] = 0;
-  __syncthreads();
-  // single block launch: the counter is re-armed once every listed flag has been cleared
-  if (threadIdx.x == 0) *count = 0;
 }
 
 // G += A^T T restricted to the flagged rows j of T: every stored A[j, i] scatters a(j,i) * T[j] into G[i] with one
@@ -757,8 +754,9 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
     if (rows_path && l == L - 1) {
       rc = ngcf_layer_bwd_rows(st, l, slope, s);
       if (rc) return rc;
-      untouch_rows_kernel<<<1, 256, 0, s>>>(st->row_flag, st->row_list, st->row_count);
+      untouch_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, s>>>(st->row_flag, st->row_list, st->row_count);
       YR_CHECK_LAUNCH();
+      YR_CUDA(cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), s));
       continue;
     }
     rc = yr_ngcf_layer_bwd(&st->LT, d, st->E[l], st->LE[l], st->E[l + 1],
