@@ -91,7 +91,8 @@ def _random_problem(rng, nU, nI, d, n_eval, heavy=False, ties=False):
 
 @pytest.mark.parametrize("nU,nI,d,n_eval,K", [(64, 100, 64, 1, 10), (300, 1000, 64, 129, 10), (500, 3001, 64, 400, 20),
                                                (200, 777, 256, 130, 10), (128, 640, 32, 128, 1), (90, 512, 128, 77, 32),
-                                               (50, 33, 20, 40, 10), (400, 5000, 64, 300, 16)])
+                                               (50, 33, 20, 40, 10), (400, 5000, 64, 300, 16),
+                                               (300, 2000, 64, 200, 5), (300, 2000, 96, 150, 13), (150, 900, 64, 100, 2)])
 @pytest.mark.parametrize("mode", MODES)
 def test_eval_random_vs_oracle(nU, nI, d, n_eval, K, mode):
     rng = np.random.default_rng(nI + d)

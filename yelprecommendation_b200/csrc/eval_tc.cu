@@ -11,11 +11,13 @@
 // (score desc, item id asc), and fed to the same metric code. Rows the filter cannot decide (candidate overflow, or
 // fewer than K unmasked items) are appended to a fallback list that the exact kernel of eval.cu evaluates.
 //
-// Pipeline per CTA (one per SM, persistent over 128-user tiles):
-//   warp 0  : TMA producer  — item tiles [TN x 32 floats] boxes, 128B swizzle, mbarrier expect_tx
-//   warp 1  : MMA issuer    — tcgen05.mma.kind::tf32, M=128, N=TN, K=8 per instruction, A/B from shared memory
-//   warp 2  : TMEM allocator (2 accumulator stages of TN columns)
-//   warps 4-7: epilogue     — tcgen05.ld 32x32b.x32, filter, candidate buffers, final exact re-score + metrics
+// Pipeline per CTA (one per SM, persistent over 128-user tiles), 384 threads:
+//   warp 0   : TMA producer  — item tiles [128 x 32 floats] boxes, 128B swizzle, mbarrier expect_tx
+//   warp 1   : MMA issuer    — tcgen05.mma.kind::tf32, M=128, N=128, K=8 per instruction, A/B from shared memory
+//   warp 2   : TMEM allocator (4 accumulator stages of 128 columns = all 512 columns)
+//   warps 4-11: epilogue     — two threads per user row (column halves), tcgen05.ld 32x32b.x32, filter, candidate
+//                              buffers in global scratch, the K best s~ in registers; the two half-streams exchange
+//                              their thresholds through shared memory; final exact re-score + metrics
 // The user tile (gathered rows of eval_uid) is written to shared memory by all threads in the 128B-swizzled K-major
 // layout the UMMA descriptor expects.
 #include <float.h>
@@ -27,7 +29,6 @@ constexpr int kTcTM = 128;
 constexpr int kTcTN = 128;         // items per MMA tile (N)
 constexpr int kTcAcc = 4;          // TMEM accumulator stages (4 x 128 columns)
 constexpr int kTcThreads = 384;    // 4 control warps + 8 epilogue warps
-constexpr int kTcPend = 4;         // per-thread pending FIFO (deferred candidate handling)
 constexpr int kTcMaxK = 16;
 constexpr int kTcCap = 128;        // candidate buffer entries per half-stream (global scratch): compaction is rare
 constexpr float kTcErrCoef = 0.0025f;   // > 2*2^-10 (TF32 operands) + accumulation + fp32-chain rounding
@@ -96,14 +97,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   const uint32_t stage_bytes = (uint32_t)SPS * TN * 128;
   unsigned char* Us = smem;                             // [n_slabs][128 rows][128 B] swizzled
   unsigned char* Vs = Us + (size_t)n_slabs * 16384;     // [NST][SPS][TN rows][128 B] swizzled (TMA)
-  float* tk = reinterpret_cast<float*>(Vs + (size_t)NST * stage_bytes);   // [2][K][128] approx top-K values
+  float* xch = reinterpret_cast<float*>(Vs + (size_t)NST * stage_bytes);  // [2 halves][tau, mid][128] threshold exchange
   // candidate buffers live in global scratch (L2): touched ~100 times per user, and 64 KB of shared memory is
   // worth more as pipeline stages
   int* cid = P.cand + (size_t)blockIdx.x * 4 * CAP * kTcTM;               // [2][CAP][128] candidate item ids
   float* csc = reinterpret_cast<float*>(cid + 2 * CAP * kTcTM);           // [2][CAP][128] candidate s~
-  int* pid = reinterpret_cast<int*>(tk + 2 * K * kTcTM);                  // [2][kTcPend][128] pending ids
-  float* psc = reinterpret_cast<float*>(pid + 2 * kTcPend * kTcTM);       // [2][kTcPend][128] pending s~
-  float* tauB = psc + 2 * kTcPend * kTcTM;                                // [128] tau of the second half-stream
+  float* tauB = xch + 4 * kTcTM;                                          // [128] tau of the second half-stream
   int* cntB = reinterpret_cast<int*>(tauB + kTcTM);                       // [128] its candidate count (-1 = overflow)
   uint64_t* bars = reinterpret_cast<uint64_t*>(cntB + kTcTM);             // full[4] empty[4] tfull[4] tempty[4]
   uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 12;
@@ -221,8 +220,8 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
       // number of candidates either stream lets through.
       const int midx = K - (K + 1) / 2;                   // ascending list: index of the ceil(K/2)-th best
       float mid = -INFINITY;
-      float* xch_own = tk + (size_t)half * 2 * kTcTM + r;          // [half][tau, mid][128]
-      float* xch_oth = tk + (size_t)(half ^ 1) * 2 * kTcTM + r;
+      float* xch_own = xch + (size_t)half * 2 * kTcTM + r;         // [half][tau, mid][128]
+      float* xch_oth = xch + (size_t)(half ^ 1) * 2 * kTcTM + r;
       xch_own[0] = -INFINITY; xch_own[kTcTM] = -INFINITY;
       asm volatile("bar.sync 1, 256;" ::: "memory");               // both halves initialised before anyone reads
       int cnt = 0;
@@ -414,8 +413,7 @@ static bool tc_config(int d, int K, TcConfig* c) {
   if (d < 32 || d > 256 || (d % 32) != 0 || K < 1 || K > kTcMaxK) return false;
   c->SPS = (d % 64 == 0 && d <= 128) ? 2 : 1;
   c->CAP = kTcCap;
-  const size_t fixed = (size_t)(d / 32) * 16384 + 2 * (size_t)K * kTcTM * 4 +
-                       4 * (size_t)kTcPend * kTcTM * 4 + 2 * kTcTM * 4 + 16 * 8 + 16;
+  const size_t fixed = (size_t)(d / 32) * 16384 + 4 * kTcTM * 4 + 2 * kTcTM * 4 + 16 * 8 + 16;   // Us, xch, tauB/cntB, barriers
   const size_t stage = (size_t)c->SPS * kTcTN * 128;
   int nst = (int)((224 * 1024 - fixed) / stage);
   if (nst > 4) nst = 4;
