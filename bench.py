@@ -40,7 +40,7 @@ B = 2048
 D = 64
 LAYERS = 3
 M_BYTES = (31_668 + 38_048) * D * 4            # one N x d fp32 row matrix = 17.85 MB
-NCU_SPMM_DRAM_BYTES = 46_115_584               # ncu --set full, spmm_chunk_kernel<64,0>: dram read 44.04 MB + write 2.07 MB
+NCU_SPMM_DRAM_BYTES = 45_472_000               # ncu --set full, spmm_chunk_kernel<64,0> (full graph): dram read 44.07 MB + write 1.40 MB (profiles/r01_ncu_full_summary_final.txt)
 
 
 def peaks():

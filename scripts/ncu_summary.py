@@ -29,9 +29,10 @@ for rep in sys.argv[1:]:
     for r in rows[2:]:
         name = r[hdr.index('Kernel Name')][:48]
         seen.setdefault(name, []).append(r)
+    ti = hdr.index('gpu__time_duration.sum')
     for name, rs in seen.items():
-        r = rs[-1]
-        print(f"## {name}   (launches captured: {len(rs)})")
+        r = max(rs, key=lambda x: float(x[ti].replace(',', '')))      # the longest launch represents the kernel
+        print(f"## {name}   (launches captured: {len(rs)}; durations {[x[ti] for x in rs]} {units[ti]}; counters of the longest)")
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
