@@ -40,6 +40,8 @@ B = 2048
 D = 64
 LAYERS = 3
 M_BYTES = (31_668 + 38_048) * D * 4            # one N x d fp32 row matrix = 17.85 MB
+WORKLOAD = ("NGCF 3-layer d=64 BPR train step, Yelp2018-shape graph (31,668u x 38,048i, 1,561,406 interactions), "
+            "batch 2048, Adam lr 1e-4 (BASELINE.json configs[1])")
 NCU_SPMM_DRAM_BYTES = 45_472_000               # ncu --set full, spmm_chunk_kernel<64,0> (full graph): dram read 44.07 MB + write 1.40 MB (profiles/r01_ncu_full_summary_final.txt)
 
 
@@ -167,7 +169,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "steps_requested": args.steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "NGCF 3-layer d=64 BPR train step, Yelp2018-shape graph, batch 2048, Adam lr 1e-4"},
+            "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} full train steps of oracle/torch_port.NGCFPort (torch CPU ops of the "
                                        "reference, N x N identity hoisted: (L+I)E = LE + E)"},
@@ -567,8 +569,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "NGCF 3-layer d=64 BPR train step, Yelp2018-shape graph (31,668u x 38,048i, "
-                                       "1,561,406 interactions), batch 2048, Adam lr 1e-4 (BASELINE.json configs[1])",
+                "config": {"workload": WORKLOAD,
                            "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (replicas only)",
                            "l2": "per-step working set (~0.4 GB of E/LE/G/T/CSR/Adam state) exceeds the 126 MB L2; no flush"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline,
