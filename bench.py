@@ -486,6 +486,19 @@ def main():
             ms_s = timed(lambda i: ld.epoch_triples(), 5) / 5
             extra["negative_sampling"] = {"value": ld.user.numel() / (ms_s * 1e-3), "unit": "triples/s", "ms_per_epoch": ms_s,
                                           "note": "one epoch of (user, pos, fresh negative) triples sampled + shuffled in HBM"}
+            # one whole epoch the way train.py drives it: fresh negatives + shuffle + every batch, nothing leaves HBM
+            for oname in ("sgd", "adam"):
+                torch.manual_seed(42)
+                etr = MFTrainer(cfg(optimizer=oname), w.inter.num_items, w.inter.num_users)
+                etr.train(ld)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                etr.train(ld)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                extra[f"mf_epoch_device_loader_{oname}"] = {
+                    "value": ld.user.numel() / dt, "unit": UNIT, "ms_per_epoch": 1e3 * dt, "steps": len(ld),
+                    "note": "MFTrainer.train(DeviceTripleLoader): sampling + shuffle + all steps of an epoch (wall clock)"}
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 t0 = time.perf_counter()
                 syn.sample_triples(w.split, w.inter.num_items, seed=1)
