@@ -93,7 +93,8 @@ class CDAETrainer(BaseTrainer):
     def train(self, train_dataloader, keeps=None) -> float:
         """`keeps`: optional iterable of dropout multipliers (one [B x num_items] tensor per batch) to replay a run with
         the masks another implementation drew; by default they are drawn on the device like nn.Dropout does."""
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         self._state()[0]["loss"].zero_()
         keeps = iter(keeps) if keeps is not None else None
         losses = []

@@ -102,7 +102,8 @@ class MFTrainer(BaseTrainer):
         return v
 
     def train(self, train_dataloader) -> float:
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         if hasattr(train_dataloader, "epoch_triples"):        # data.sampler.DeviceTripleLoader: epoch resident in HBM
             uid, pos, neg = train_dataloader.epoch_triples()
             B = int(train_dataloader.batch_size)

@@ -51,6 +51,20 @@ class NGCFTrainer(BaseTrainer):
     def _state(self):
         m = self.model
         dev = self.device
+        # the ctypes struct only holds pointers: rebuild it when one of them changed (load_state_dict, new optimizer state)
+        key = (m.embedding.weight.data_ptr(), tuple(w.weight.data_ptr() for w in m.W1), tuple(w.weight.data_ptr() for w in m.W2),
+               id(self.laplacian_matrix), self._bufs is not None and self._bufs["E0_ptr"])
+        hit = getattr(self, "_st_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], self._bufs
+        st, b = self._build_state()
+        key = key[:4] + (b["E0_ptr"],)
+        self._st_cache = (key, st)
+        return st, b
+
+    def _build_state(self):
+        m = self.model
+        dev = self.device
         csr = m.csr(self.laplacian_matrix)
         E0 = m.embedding.weight.data
         n, d = E0.shape
@@ -123,15 +137,24 @@ class NGCFTrainer(BaseTrainer):
         self.optimizer.step_count += 1
 
     def loss_sum(self, reset=True) -> float:
+        """Running sum of batch-mean losses; one stream synchronisation brings the loss and the bad-id flag back."""
         b = self._bufs
-        v = float(b["loss"][0].item())
-        ops._raise_if_err(b["err"], "NGCFTrainer")
+        h = b.get("host_out")
+        if h is None:
+            h = b["host_out"] = (torch.empty(2, dtype=F64).pin_memory(), torch.empty(1, dtype=I32).pin_memory())
+        h[0].copy_(b["loss"], non_blocking=True)
+        h[1].copy_(b["err"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        v = float(h[0][0])
+        if int(h[1][0]) != 0:
+            ops._raise_if_err(b["err"], "NGCFTrainer")
         if reset:
             b["loss"].zero_()
         return v
 
     def train(self, train_dataloader) -> float:
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         st, b = self._state()
         b["loss"].zero_()
         if hasattr(train_dataloader, "epoch_triples"):        # data.sampler.DeviceTripleLoader: epoch resident in HBM
