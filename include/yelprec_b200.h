@@ -141,9 +141,10 @@ int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */
 int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream);
 
-/* Where the per-layer d x d transforms run: 1 (default) = tensor cores, tcgen05.mma.kind::tf32 with the 3xTF32 split
- * (within the 1e-5 parity bar); 0 = FP32 pipe, one fma chain per output (bit-comparable with the oracle).
- * Applies to the forward transform; process-wide. */
+/* Where the per-layer d x d transforms run: 1 (default) = forward on tensor cores, tcgen05.mma.kind::tf32 with the
+ * 3xTF32 split (within the 1e-5 parity bar), backward on the FP32 pipe; 0 = FP32 pipe for both, one fma chain per
+ * output (forward bit-comparable with the oracle); 2 = tensor cores for the backward too (correct, currently slower
+ * than the FP32-pipe kernel: see csrc/ngcf_tc_bwd.cu). Process-wide. */
 int yr_ngcf_set_dense_mode(int mode);
 int yr_ngcf_get_dense_mode(void);
 /* yr_ngcf_train_step, top layer: 1 (default) = backward on the batch rows only (dLoss/dE_L is zero elsewhere) with

@@ -109,9 +109,32 @@ def test_layer_forward_tensor_core_3xtf32():
     assert rel_err(En.cpu().numpy(), Eo) < 2e-6
 
 
-def test_layer_backward_vs_oracle_and_autograd_golden():
-    from yelprecommendation_b200 import ops
+@pytest.mark.parametrize("dense_mode", [1, 2])
+def test_layer_backward_vs_oracle_and_autograd_golden(dense_mode):
+    """dense_mode 1: FP32-pipe backward kernel (default); 2: tcgen05 backward (3xTF32, MN-major operands for dW)."""
+    from yelprecommendation_b200 import _cabi, ops
     from yelprecommendation_b200.data.graph import laplacian_to_csr
+    lib = _cabi.load()
+    lib.yr_ngcf_set_dense_mode(dense_mode)
+    try:
+        _layer_backward_case(ops, laplacian_to_csr)
+    finally:
+        lib.yr_ngcf_set_dense_mode(1)
+
+
+def test_train_steps_with_tensor_core_backward():
+    """Whole train steps (row-sparse last layer included) with the tcgen05 backward vs the reference golden."""
+    from yelprecommendation_b200 import _cabi
+    lib = _cabi.load()
+    lib.yr_ngcf_set_dense_mode(2)
+    try:
+        assert lib.yr_ngcf_get_dense_mode() == 2
+        test_train_steps_vs_reference_golden(1)
+    finally:
+        lib.yr_ngcf_set_dense_mode(1)
+
+
+def _layer_backward_case(ops, laplacian_to_csr):
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
     dcsr = laplacian_to_csr(L, "cuda")
     layers, LEs = [E0], []

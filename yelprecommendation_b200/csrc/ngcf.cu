@@ -417,12 +417,15 @@ using namespace yr;
 
 // 0 = FP32 pipe (one fma chain per output, bit-comparable with the oracle), 1 = tensor cores (3xTF32 split)
 static int g_dense_mode = 1;
+static int g_bwd_tc = 0;       // mode 2: tensor cores for the backward transforms too (ngcf_tc_bwd.cu; slower, see there)
 extern "C" int yr_ngcf_set_dense_mode(int mode) {
+  if (mode == 2) { g_dense_mode = 1; g_bwd_tc = 1; return YR_OK; }
   if (mode != 0 && mode != 1) return YR_ERR_BAD_ARG;
+  g_bwd_tc = 0;
   g_dense_mode = mode;
   return YR_OK;
 }
-extern "C" int yr_ngcf_get_dense_mode(void) { return g_dense_mode; }
+extern "C" int yr_ngcf_get_dense_mode(void) { return g_bwd_tc ? 2 : g_dense_mode; }
 // 1 (default) = the top layer's backward of yr_ngcf_train_step runs on the batch rows only; 0 = dense (debug / A-B)
 static int g_top_rows_mode = 1;
 extern "C" int yr_ngcf_set_top_rows_mode(int mode) {
@@ -475,6 +478,15 @@ extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* 
   if (d != 64) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_dense_mode == 1 && g_bwd_tc) {          // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
+    int parts = 0;
+    int rc = yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, &parts, s);
+    if (rc) return rc;
+    const int len_tc = 2 * d * d;
+    reduce_partials_kernel<<<(len_tc + 31) / 32, 256, 0, s>>>((const float*)ws, parts, len_tc, dW1, dW2, d * d);
+    YR_CHECK_LAUNCH();
+    return YR_OK;
+  }
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -564,6 +576,20 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
   const int d = st->d;
   using C = DenseCfg<64>;
   if (d != 64) return YR_ERR_BAD_DIM;
+  if (g_dense_mode == 1 && g_bwd_tc) {
+    int parts = 0;
+    int rc = yr_ngcf_dense_bwd_tc_launch(st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope,
+                                         st->nU + st->nI, st->G[l], st->T, (float*)st->ws, &parts, s, st->row_list,
+                                         st->row_count, st->row_list_cap);
+    if (rc) return rc;
+    const int len_tc = 2 * d * d;
+    reduce_partials_kernel<<<(len_tc + 31) / 32, 256, 0, s>>>((const float*)st->ws, parts, len_tc, st->dW1[l], st->dW2[l], d * d);
+    YR_CHECK_LAUNCH();
+    const int64_t blocks_tc = ((int64_t)st->L.n_chunks + 15) / 16;
+    spmm_scatter_rows_kernel<64><<<(unsigned)blocks_tc, 256, 0, s>>>(st->L, st->row_flag, st->T, st->G[l]);
+    YR_CHECK_LAUNCH();
+    return YR_OK;
+  }
   int64_t grid = (st->row_list_cap + C::TM - 1) / C::TM;
   const int64_t cap = (int64_t)yr_sm_count() * kBwdCtasPerSm;
   if (grid > cap) grid = cap;
