@@ -285,11 +285,14 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
             const int item0 = it * TN + half * (TN / 2) + c0;
             // columns past the catalog are zero-filled TMA rows (score 0): never candidates
             if ((int64_t)item0 + 32 > P.nI) mask = (item0 < P.nI) ? (mask & ((1u << (int)(P.nI - item0)) - 1u)) : 0u;
+            const bool single = __popc(mask) == 1;                  // the usual case: the only candidate is the max
             while (__any_sync(kFull, mask != 0)) {                    // few lanes, few bits: handled in place
               if (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                handle(item0 + j, select32(v, j));
+                float sj;
+                if (single) sj = m; else sj = select32(v, j);
+                handle(item0 + j, sj);
               }
             }
           }
