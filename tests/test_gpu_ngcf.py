@@ -314,3 +314,48 @@ def test_full_size_yelp_shape_train_steps_vs_port():
     for l in range(3):
         assert rel_fro(tr.model.W1[l].weight.detach().cpu().numpy(), port.W1[l].detach().numpy()) < RTOL
         assert rel_fro(tr.model.W2[l].weight.detach().cpu().numpy(), port.W2[l].detach().numpy()) < RTOL
+
+
+def test_batch_larger_than_row_scratch_falls_back_to_dense_last_layer():
+    """A batch beyond the trainer's row-scratch capacity (3 * 4096 rows) runs the last layer densely — same result."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    inter = syn.make_interactions(num_users=2500, num_items=3500, nnz=90_000, seed=8, n_clusters=8)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tpos, tneg = syn.sample_triples(split, inter.num_items, seed=42)
+    batches = syn.to_batches(tu, tpos, tneg, 5000)[:2]
+    torch.manual_seed(5)
+    tr = NGCFTrainer(cfg(optimizer="sgd", lr=0.05, num_orders=3, batch_size=2048), inter.num_items, inter.num_users, L)
+    assert tr._row_cap < 5000
+    sd = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    port = tp.NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(3)],
+                       [sd[f"W2.{l}.weight"] for l in range(3)], inter.num_users, L, "sgd", 0.05, 0.0)
+    total = tr.train(batches)
+    ptotal, psteps = port.train(batches)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), psteps) < RTOL
+    assert rel_fro(tr.model.embedding.weight.detach().cpu().numpy(), port.emb.detach().numpy()) < RTOL
+
+
+def test_ngcf_trainer_consumes_device_loader():
+    """NGCFTrainer.train(DeviceTripleLoader) == the same triples fed as host batches (1e-6: atomics order only)."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian
+    from yelprecommendation_b200.data.sampler import DeviceTripleLoader
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    inter = syn.make_interactions(num_users=900, num_items=700, nnz=20_000, seed=6, n_clusters=4)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    split = syn.split_per_user(inter, seed=42)
+    ld = DeviceTripleLoader.from_split(split, inter.num_items, batch_size=1024, seed=3)
+    mk = lambda: NGCFTrainer(cfg(optimizer="sgd", lr=0.05, num_orders=3, batch_size=1024), inter.num_items, inter.num_users, L)
+    torch.manual_seed(1)
+    a = mk()
+    torch.manual_seed(1)
+    b = mk()
+    la = a.train(ld)
+    ld.set_epoch(0)
+    u, p, n = (x.cpu().numpy() for x in ld.epoch_triples())
+    lb = b.train(syn.to_batches(u, p, n, 1024))
+    assert isclose(la, lb, rel_tol=1e-6)
+    assert rel_fro(a.model.embedding.weight.detach().cpu().numpy(), b.model.embedding.weight.detach().cpu().numpy()) < 1e-6
