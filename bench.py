@@ -383,6 +383,23 @@ def main():
                     best = dt if best is None else min(best, dt)
                 extra["mf_train_sgd"]["e2e_value"] = world * nt / best
                 extra["mf_train_sgd"]["e2e_note"] = "MFTrainer.train(host batches): best of 3 passes over 200 batches, wall clock"
+        # -------------------------------------------------------------- TF32 tensor peak of this GPU, measured here
+        # (MEASURED_PEAKS.json has no TF32 figure). Library GEMM used as a yardstick only.
+        tf32_peak = None
+        try:
+            old_tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            ma = torch.randn(8192, 8192, device=dev)
+            mb = torch.randn(8192, 8192, device=dev)
+            for _ in range(2):
+                torch.matmul(ma, mb)
+            ms_mm = min(timed(lambda i: torch.matmul(ma, mb), 3) / 3 for _ in range(3))
+            tf32_peak = 2.0 * 8192 ** 3 / (ms_mm * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
+            del ma, mb
+            extra["tf32_matmul_peak"] = {"value": tf32_peak, "unit": "TFLOP/s", "how": "torch.matmul fp32 with TF32 on, 8192^3, best of 3 x 3"}
+        except Exception as ex:
+            extra["tf32_matmul_peak"] = {"error": repr(ex)}
         # -------------------------------------------------------------- full-catalog evaluation (configs[2])
         lo, hi = parallel.shard_range(w.ecsr.n_eval, rank, world)
         decsr_full = ops.DeviceEvalCSR(w.ecsr, dev, 10)
@@ -410,6 +427,7 @@ def main():
                                      "ms_calls": [round(x, 3) for x in calls],
                                      "tflops": flops / (ms_ev * 1e-3) / 1e12,
                                      "tensor_frac_vs_bf16_peak": flops / (ms_ev * 1e-3) / 1e12 / pk["bf16"],
+                                     "tensor_frac_vs_tf32_measured": (flops / (ms_ev * 1e-3) / 1e12 / tf32_peak) if tf32_peak else None,
                                      "metrics": [round(x, 6) for x in ops.metrics_from_sums(sums.cpu(), w.ecsr.n_eval)],
                                      "fallback_rows": int(ops.eval_topk_metrics.last_fallback_rows.item())
                                      if hasattr(ops.eval_topk_metrics, "last_fallback_rows") else None,
