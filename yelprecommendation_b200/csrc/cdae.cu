@@ -12,6 +12,7 @@
 namespace yr {
 
 constexpr int kCdaeThreads = 256;
+constexpr int kCompactThreads = 1024;   // 32 warps per row: the compaction is a latency chain, parallelism is what it needs
 
 struct CdaeWs {
   int32_t* xin_cnt;   // [B]
@@ -42,12 +43,12 @@ static size_t cdae_ws_layout(int64_t B, int64_t nI, void* base, CdaeWs* w) {
 
 // Block per batch row: ordered compaction of (a) the active inputs x*keep != 0 and (b) the loss positions
 // target + negative != 0 (value kept = target). Each warp owns a contiguous segment of the row; two passes.
-__global__ void __launch_bounds__(kCdaeThreads)
+__global__ void __launch_bounds__(kCompactThreads)
 cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep, const float* __restrict__ target,
                     const float* __restrict__ neg, int64_t nI, CdaeWs w) {
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kCdaeThreads / 32;
+  constexpr int NW = kCompactThreads / 32;
   const int64_t seg = ((nI + NW - 1) / NW + 31) / 32 * 32;
   const int64_t s0 = warp * seg, s1 = min(nI, s0 + seg);
   const float* xr = x + (int64_t)b * nI;
@@ -292,7 +293,7 @@ extern "C" int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, 
   CdaeWs w;
   cdae_ws_layout(B, nI, ws, &w);
   YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
-  cdae_compact_kernel<<<(unsigned)B, kCdaeThreads, 0, s>>>(x, keep, nullptr, nullptr, nI, w);
+  cdae_compact_kernel<<<(unsigned)B, kCompactThreads, 0, s>>>(x, keep, nullptr, nullptr, nI, w);
   YR_CHECK_LAUNCH();
   yr_cdae_tensors none = {};
   cdae_row_kernel<64, false><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, none, nU, nI, uid, w, false, z_out, ldz, nullptr, err);
@@ -327,7 +328,7 @@ extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* gra
   CdaeWs w;
   cdae_ws_layout(B, nI, ws, &w);
   YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
-  cdae_compact_kernel<<<(unsigned)B, kCdaeThreads, 0, s>>>(x, keep, target, negative_mask, nI, w);
+  cdae_compact_kernel<<<(unsigned)B, kCompactThreads, 0, s>>>(x, keep, target, negative_mask, nI, w);
   YR_CHECK_LAUNCH();
   yr_cdae_tensors none = {};
   if (train)
