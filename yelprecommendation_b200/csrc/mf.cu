@@ -116,7 +116,7 @@ __global__ void bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* 
 // loss_acc (double[2]) sits right behind the counters (counters is 8 x int32 = 32 bytes; loss_acc at
 // byte offset 32) — the state struct hands us one 64-byte block for both.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrainThreads = 256;
+constexpr int kTrainThreads = 512;
 constexpr int kTrainWarps = kTrainThreads / 32;
 
 template <int VPL>
