@@ -232,6 +232,16 @@ int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream stream);
 int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
                        const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
                        float* step_loss, yr_stream stream);
+/* The first n_prefix layers of the propagation do not depend on the batch, only on the parameters: a caller that has
+ * to read the loss back after every step (train.py does) can enqueue them for the NEXT step with
+ * yr_ngcf_propagate_prefix right after the loss copy, so the GPU works through them while the host handles the
+ * read-back and stages the next batch, and then passes prefix_done = n_prefix to yr_ngcf_train_step_ex, which starts
+ * the forward at that layer. The caller guarantees that no parameter changed in between. prefix_done = 0 is
+ * yr_ngcf_train_step. */
+int yr_ngcf_propagate_prefix(const yr_ngcf_state* st, float slope, int n_prefix, yr_stream stream);
+int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                          const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                          float* step_loss, int prefix_done, yr_stream stream);
 /* out[r, l*d + k] = E_l[r, k]: the concatenation torch.concat(..., dim=1) of models/ngcf.py:41-43. */
 int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out, yr_stream stream);
 

@@ -359,3 +359,27 @@ def test_ngcf_trainer_consumes_device_loader():
     lb = b.train(syn.to_batches(u, p, n, 1024))
     assert isclose(la, lb, rel_tol=1e-6)
     assert rel_fro(a.model.embedding.weight.detach().cpu().numpy(), b.model.embedding.weight.detach().cpu().numpy()) < 1e-6
+
+
+def test_per_batch_train_calls_with_prefetched_prefix_equal_one_call():
+    """train([b]) per batch (what train.py's epoch loop amounts to with a 1-batch loader) pre-propagates the
+    batch-independent layers of the next step behind the loss read-back; the result must equal one train(batches) call,
+    also when validate() / load_state_dict() happen in between (the latter must invalidate the prefetched layers)."""
+    g, nU, nI, L, *_ = _golden()
+    batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 128, limit=5)
+    a = _trainer(g, nU, nI, L, "adam", 1e-3, 0.0)
+    b = _trainer(g, nU, nI, L, "adam", 1e-3, 0.0)
+    total_a = a.train(batches)
+    total_b = 0.0
+    for i, bt in enumerate(batches):
+        total_b += b.train([bt])
+        assert b._prefix_tag is not None                       # the next step's first layers are in flight / done
+        if i == 1:
+            b.validate(batches[:1])                            # recomputes every layer; prefix stays valid
+        if i == 2:                                             # a Python-side parameter write must invalidate it
+            sd = {k: v.clone() for k, v in b.model.state_dict().items()}
+            b.model.load_state_dict(sd)
+            assert b._take_prefix() == 0
+    assert isclose(total_a, total_b, rel_tol=1e-6)
+    for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+        assert rel_fro(vb.cpu().numpy(), va.cpu().numpy()) < 1e-6, ka

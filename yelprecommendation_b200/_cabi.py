@@ -23,6 +23,7 @@ SYMBOLS = (
     "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
+    "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode", "yr_ngcf_set_top_rows_mode",
@@ -139,6 +140,8 @@ def load() -> C.CDLL:
         "yr_dense_opt_step_multi": (C.c_int, [i32, p, p, p, p, p, C.POINTER(YrOpt), i32, p]),
         "yr_ngcf_propagate": (C.c_int, [C.POINTER(YrNgcfState), f32, p]),
         "yr_ngcf_train_step": (C.c_int, [C.POINTER(YrNgcfState), C.POINTER(YrOpt), f32, p, p, p, i64, p, p]),
+        "yr_ngcf_propagate_prefix": (C.c_int, [C.POINTER(YrNgcfState), f32, i32, p]),
+        "yr_ngcf_train_step_ex": (C.c_int, [C.POINTER(YrNgcfState), C.POINTER(YrOpt), f32, p, p, p, i64, p, i32, p]),
         "yr_ngcf_concat": (C.c_int, [p, i32, i64, i32, p, p]),
         "yr_topk_masked_row": (C.c_int, [p, i64, p, i64, i32, p, p]),
         "yr_topk_metrics": (C.c_int, [p, i64, i64, p, p, p, p, i32, p, p, p]),

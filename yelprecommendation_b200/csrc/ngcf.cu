@@ -720,6 +720,17 @@ static int ngcf_state_ok(const yr_ngcf_state* st) {
   return YR_OK;
 }
 
+extern "C" int yr_ngcf_propagate_prefix(const yr_ngcf_state* st, float slope, int n_prefix, yr_stream stream) {
+  int rc = ngcf_state_ok(st);
+  if (rc) return rc;
+  if (n_prefix < 0 || n_prefix > st->n_layers) return YR_ERR_BAD_ARG;
+  for (int l = 0; l < n_prefix; ++l) {
+    rc = yr_ngcf_layer_fwd(&st->L, st->d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+    if (rc) return rc;
+  }
+  return YR_OK;
+}
+
 extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream stream) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
@@ -731,11 +742,22 @@ extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream
   return YR_OK;
 }
 
+extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                                     const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                                     float* step_loss, int prefix_done, yr_stream stream);
+
 extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, float slope,
                                   const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
                                   float* step_loss, yr_stream stream) {
+  return yr_ngcf_train_step_ex(st, opt, slope, uid, pos, neg, B, step_loss, 0, stream);
+}
+
+extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                                     const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                                     float* step_loss, int prefix_done, yr_stream stream) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
+  if (prefix_done < 0 || prefix_done > st->n_layers) return YR_ERR_BAD_ARG;
   if (!opt || !uid || !pos || !neg || B <= 0 || yr_csr_ok(&st->LT) || !st->T ||
       !st->E_dev || !st->G_dev || !st->ws || !st->loss)
     return YR_ERR_BAD_ARG;
@@ -759,7 +781,7 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
     YR_CHECK_LAUNCH();
   }
   if (rows_path && g_dense_mode == 1) {
-    for (int l = 0; l + 1 < L; ++l) {
+    for (int l = (prefix_done < L - 1 ? prefix_done : L - 1); l + 1 < L; ++l) {
       rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
       if (rc) return rc;
     }
@@ -769,8 +791,10 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
                                      st->row_list, st->row_count, 3 * B);
     if (rc) return rc;
   } else {
-    rc = yr_ngcf_propagate(st, slope, stream);
-    if (rc) return rc;
+    for (int l = prefix_done; l < L; ++l) {
+      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+      if (rc) return rc;
+    }
   }
   rc = yr_ngcf_tail(st->E_dev, st->G_dev, L, st->nU, st->nI, d, uid, pos, neg, B, nullptr, nullptr, st->loss,
                     step_loss, st->err, stream);

@@ -130,21 +130,55 @@ class NGCFTrainer(BaseTrainer):
         lib = _cabi.load()
         st = _st if _st is not None else self._state()[0]
         opt = self.optimizer.opt_struct(self.optimizer.step_count + 1)
-        _cabi.check(lib.yr_ngcf_train_step(C.byref(st), C.byref(opt), _LEAKY_SLOPE, _cabi.dptr(uid, I64),
-                                           _cabi.dptr(pos, I64), _cabi.dptr(neg, I64), int(uid.numel()),
-                                           _cabi.dptr(step_loss) if step_loss is not None else None,
-                                           _cabi.stream_ptr(self.device)), "yr_ngcf_train_step")
+        prefix = self._take_prefix()
+        _cabi.check(lib.yr_ngcf_train_step_ex(C.byref(st), C.byref(opt), _LEAKY_SLOPE, _cabi.dptr(uid, I64),
+                                              _cabi.dptr(pos, I64), _cabi.dptr(neg, I64), int(uid.numel()),
+                                              _cabi.dptr(step_loss) if step_loss is not None else None, prefix,
+                                              _cabi.stream_ptr(self.device)), "yr_ngcf_train_step_ex")
         self.optimizer.step_count += 1
 
-    def loss_sum(self, reset=True) -> float:
-        """Running sum of batch-mean losses; one stream synchronisation brings the loss and the bad-id flag back."""
+    # ---- batch-independent part of the next step, enqueued while the host reads the loss back -----------------
+    def _param_versions(self):
+        m = self.model
+        return (m.embedding.weight._version, m.embedding.weight.data_ptr(), tuple(w.weight._version for w in m.W1),
+                tuple(w.weight._version for w in m.W2), self.optimizer.step_count, id(self.laplacian_matrix))
+
+    def _take_prefix(self) -> int:
+        """Number of leading layers already propagated for the CURRENT parameters (0 unless _prepropagate ran and nothing
+        touched the parameters since — Python-side writes bump the tensors' versions, our steps bump step_count)."""
+        tag = getattr(self, "_prefix_tag", None)
+        self._prefix_tag = None
+        if tag is not None and tag[0] == self._param_versions():
+            return tag[1]
+        return 0
+
+    def _prepropagate(self, st) -> None:
+        n_prefix = int(st.n_layers) - 1            # the last layer depends on the batch rows (row-sparse), the others do not
+        if n_prefix <= 0:
+            return
+        lib = _cabi.load()
+        _cabi.check(lib.yr_ngcf_propagate_prefix(C.byref(st), _LEAKY_SLOPE, n_prefix, _cabi.stream_ptr(self.device)),
+                    "yr_ngcf_propagate_prefix")
+        self._prefix_tag = (self._param_versions(), n_prefix)
+
+    def loss_sum(self, reset=True, prepropagate_state=None) -> float:
+        """Running sum of batch-mean losses; one event synchronisation brings the loss and the bad-id flag back. With
+        `prepropagate_state` the batch-independent layers of the NEXT step are enqueued behind the copies, so the GPU
+        is busy while the host returns the loss and stages the next batch (include/yelprec_b200.h)."""
         b = self._bufs
         h = b.get("host_out")
         if h is None:
-            h = b["host_out"] = (torch.empty(2, dtype=F64).pin_memory(), torch.empty(1, dtype=I32).pin_memory())
+            h = b["host_out"] = (torch.empty(2, dtype=F64).pin_memory(), torch.empty(1, dtype=I32).pin_memory(),
+                                 torch.cuda.Event())
         h[0].copy_(b["loss"], non_blocking=True)
         h[1].copy_(b["err"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        h[2].record(torch.cuda.current_stream(self.device))
+        if reset:
+            b["loss"].zero_()                      # stream-ordered after the copy
+        if prepropagate_state is not None and self.model.training:
+            self._prepropagate(prepropagate_state)
+        h[2].synchronize()
+        reset = False
         v = float(h[0][0])
         if int(h[1][0]) != 0:
             ops._raise_if_err(b["err"], "NGCFTrainer")
@@ -166,7 +200,7 @@ class NGCFTrainer(BaseTrainer):
             for k, s in enumerate(range(0, n, B)):
                 self.train_step_on_device(uid[s:s + B], pos[s:s + B], neg[s:s + B], sl[k:k + 1], st)
             self.last_step_losses = sl
-            return self.loss_sum()
+            return self.loss_sum(prepropagate_state=st)
         stager = self._get_stager(train_dataloader)
         losses = []
         for uid, pos, neg, n, B in stager.chunks(train_dataloader):
@@ -176,8 +210,8 @@ class NGCFTrainer(BaseTrainer):
             losses.append(sl)
         if not losses:
             return 0
-        self.last_step_losses = torch.cat(losses)
-        return self.loss_sum()
+        self.last_step_losses = torch.cat(losses) if len(losses) > 1 else losses[0]
+        return self.loss_sum(prepropagate_state=st)
 
     def propagate(self):
         """E_0..E_L after one propagation of the current parameters (device tensors, not copies)."""
