@@ -5,6 +5,7 @@
 //   yr_ngcf_tail         — gather/concat/dot tail of bpr_forward + BPRLoss and its scatter backward
 //                          (reference models/ngcf.py:37-45, loss.py:25-27)
 //   yr_dense_opt_step    — torch.optim Adam/AdamW/SGD single-tensor step (trainers/base_trainer.py:34-40)
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace yr {
@@ -742,6 +743,27 @@ extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream
   return YR_OK;
 }
 
+// One helper stream + two events per device, created on first use (the only resources the library ever creates):
+// independent memsets of a step run on it, ordered against the caller's stream with events. YR_NGCF_SIDE_STREAM=0
+// keeps everything on the caller's stream.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+  static SideStream pool[64];
+  static int state[64];                 // 0 = not tried, 1 = ready, -1 = unavailable
+  const char* e = getenv("YR_NGCF_SIDE_STREAM");
+  if (e && e[0] == '0') return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (state[dev] == 0) {
+    SideStream& x = pool[dev];
+    const bool ok = cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &pool[dev] : nullptr;
+}
+
 extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
                                      const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
                                      float* step_loss, int prefix_done, yr_stream stream);
@@ -765,10 +787,18 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
   const int L = st->n_layers, d = st->d;
   const int64_t n = st->nU + st->nI;
   cudaStream_t s = (cudaStream_t)stream;
-  for (int l = 0; l <= L; ++l) {
+  // The gradient buffers are first written by the tail, after the whole forward: clear them on a side stream
+  // underneath the forward SpMMs (HBM writes next to an L2-bound kernel) and join before the tail.
+  SideStream* side = side_stream();
+  for (int l = 0; l <= L; ++l)
     if (!st->G[l]) return YR_ERR_BAD_ARG;
-    YR_CUDA(cudaMemsetAsync(st->G[l], 0, sizeof(float) * (size_t)n * d, s));
+  cudaStream_t ms = side ? side->stream : s;
+  if (side) {
+    YR_CUDA(cudaEventRecord(side->fork, s));                 // everything enqueued so far (the previous optimizer step reads G[0])
+    YR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }
+  for (int l = 0; l <= L; ++l) YR_CUDA(cudaMemsetAsync(st->G[l], 0, sizeof(float) * (size_t)n * d, ms));
+  if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
   // Top layer: E_L is READ only at the <= 3B rows the batch touches (the tail) and dLoss/dE_L is non-zero only there.
   // So the last layer's forward (SpMM + transform) and backward run on those rows, and G_{L-1} += L^T T becomes a
   // scatter from them (same sums, different fp32 order). Needs the row scratch; E_L / LE_{L-1} keep stale values in
@@ -796,6 +826,7 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
       if (rc) return rc;
     }
   }
+  if (side) YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   rc = yr_ngcf_tail(st->E_dev, st->G_dev, L, st->nU, st->nI, d, uid, pos, neg, B, nullptr, nullptr, st->loss,
                     step_loss, st->err, stream);
   if (rc) return rc;
