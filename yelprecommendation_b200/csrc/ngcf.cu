@@ -471,23 +471,15 @@ extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
   return (size_t)yr_sm_count() * kBwdCtasPerSm * 2 * (size_t)d * d * sizeof(float);
 }
 
-extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
-                                 const float* G_next, const float* W1, const float* W2, float slope,
-                                 float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
-                                 yr_stream stream) {
-  if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !dW1 || !dW2 || !ws || n <= 0) return YR_ERR_BAD_ARG;
+// the dense backward kernel WITHOUT the reduction of its per-CTA dW partials (n_parts of them are left in ws)
+static int dense_bwd_launch(int d, int64_t n, const float* E, const float* LE, const float* E_next, const float* G_next,
+                            const float* W1, const float* W2, float slope, float* G, float* T, void* ws, size_t ws_bytes,
+                            cudaStream_t s, int* n_parts) {
+  if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !ws || n <= 0) return YR_ERR_BAD_ARG;
   if (d != 64) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (g_dense_mode == 1 && g_bwd_tc) {          // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
-    int parts = 0;
-    int rc = yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, &parts, s);
-    if (rc) return rc;
-    const int len_tc = 2 * d * d;
-    reduce_partials_kernel<<<(len_tc + 31) / 32, 256, 0, s>>>((const float*)ws, parts, len_tc, dW1, dW2, d * d);
-    YR_CHECK_LAUNCH();
-    return YR_OK;
-  }
+  if (g_dense_mode == 1 && g_bwd_tc)            // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
+    return yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
   using C = DenseCfg<64>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -501,10 +493,26 @@ extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* 
   ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
       E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, nullptr, nullptr);
   YR_CHECK_LAUNCH();
+  *n_parts = (int)grid;
+  return YR_OK;
+}
+
+static int dense_bwd_reduce(int d, const void* ws, int n_parts, float* dW1, float* dW2, cudaStream_t s) {
   const int len = 2 * d * d;
-  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)ws, (int)grid, len, dW1, dW2, d * d);
+  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)ws, n_parts, len, dW1, dW2, d * d);
   YR_CHECK_LAUNCH();
   return YR_OK;
+}
+
+extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
+                                 const float* G_next, const float* W1, const float* W2, float slope,
+                                 float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
+                                 yr_stream stream) {
+  if (!dW1 || !dW2) return YR_ERR_BAD_ARG;
+  int parts = 0;
+  int rc = dense_bwd_launch(d, n, E, LE, E_next, G_next, W1, W2, slope, G, T, ws, ws_bytes, (cudaStream_t)stream, &parts);
+  if (rc) return rc;
+  return dense_bwd_reduce(d, ws, parts, dW1, dW2, (cudaStream_t)stream);
 }
 
 // ---- top layer of a BPR step: only the <= 3B batch rows carry a gradient -------------------------------------
@@ -830,6 +838,7 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
   rc = yr_ngcf_tail(st->E_dev, st->G_dev, L, st->nU, st->nI, d, uid, pos, neg, B, nullptr, nullptr, st->loss,
                     step_loss, st->err, stream);
   if (rc) return rc;
+  bool reduce_pending = false;
   for (int l = L - 1; l >= 0; --l) {
     if (!st->dW1[l] || !st->dW2[l]) return YR_ERR_BAD_ARG;
     if (rows_path && l == L - 1) {
@@ -840,11 +849,27 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
       YR_CUDA(cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), s));
       continue;
     }
-    rc = yr_ngcf_layer_bwd(&st->LT, d, st->E[l], st->LE[l], st->E[l + 1],
-                           st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l], st->T, st->dW1[l], st->dW2[l],
-                           st->ws, st->ws_bytes, stream);
+    // dense backward, then the reduction of its dW partials on the side stream underneath the transposed SpMM
+    if (side && reduce_pending) { YR_CUDA(cudaStreamWaitEvent(s, side->join, 0)); reduce_pending = false; }   // ws is free again
+    int parts = 0;
+    rc = dense_bwd_launch(d, n, st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l],
+                          st->T, st->ws, st->ws_bytes, s, &parts);
+    if (rc) return rc;
+    if (side) {
+      YR_CUDA(cudaEventRecord(side->fork, s));
+      YR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      rc = dense_bwd_reduce(d, st->ws, parts, st->dW1[l], st->dW2[l], side->stream);
+      if (rc) return rc;
+      YR_CUDA(cudaEventRecord(side->join, side->stream));
+      reduce_pending = true;
+    } else {
+      rc = dense_bwd_reduce(d, st->ws, parts, st->dW1[l], st->dW2[l], s);
+      if (rc) return rc;
+    }
+    rc = yr_spmm_csr(&st->LT, d, st->T, st->G[l], 1, stream);
     if (rc) return rc;
   }
+  if (side && reduce_pending) YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   // embedding.weight and the 2L weights: parameter order of nn.Module.parameters() does not matter for a per-tensor
   // optimizer; two launches (1 + 2L <= 15 tensors, 8 per launch)
   float *pp[2 * YR_NGCF_MAX_LAYERS + 1], *gg[2 * YR_NGCF_MAX_LAYERS + 1], *mm[2 * YR_NGCF_MAX_LAYERS + 1],
