@@ -581,7 +581,30 @@ spmm_scatter_rows_kernel(yr_csr A, const int32_t* __restrict__ flag, const float
 }  // namespace yr
 
 // dense backward of one layer on the listed rows + scatter form of G += L^T T (ngcf_train_step, top layer)
-static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cudaStream_t s) {
+// One helper stream + two events per device, created on first use (the only resources the library ever creates):
+// independent memsets of a step run on it, ordered against the caller's stream with events. YR_NGCF_SIDE_STREAM=0
+// keeps everything on the caller's stream.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+  static SideStream pool[64];
+  static int state[64];                 // 0 = not tried, 1 = ready, -1 = unavailable
+  const char* e = getenv("YR_NGCF_SIDE_STREAM");
+  if (e && e[0] == '0') return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (state[dev] == 0) {
+    SideStream& x = pool[dev];
+    const bool ok = cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &pool[dev] : nullptr;
+}
+
+static int rows_reduce(const yr_ngcf_state* st, int l, int parts, cudaStream_t s, SideStream* side);
+
+static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cudaStream_t s, SideStream* side) {
   const int d = st->d;
   using C = DenseCfg<64>;
   if (d != 64) return YR_ERR_BAD_DIM;
@@ -591,9 +614,8 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
                                          st->nU + st->nI, st->G[l], st->T, (float*)st->ws, &parts, s, st->row_list,
                                          st->row_count, st->row_list_cap);
     if (rc) return rc;
-    const int len_tc = 2 * d * d;
-    reduce_partials_kernel<<<(len_tc + 31) / 32, 256, 0, s>>>((const float*)st->ws, parts, len_tc, st->dW1[l], st->dW2[l], d * d);
-    YR_CHECK_LAUNCH();
+    rc = rows_reduce(st, l, parts, s, side);
+    if (rc) return rc;
     const int64_t blocks_tc = ((int64_t)st->L.n_chunks + 15) / 16;
     spmm_scatter_rows_kernel<64><<<(unsigned)blocks_tc, 256, 0, s>>>(st->L, st->row_flag, st->T, st->G[l]);
     YR_CHECK_LAUNCH();
@@ -612,13 +634,28 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
       st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope, st->nU + st->nI, st->G[l], st->T,
       (float*)st->ws, st->row_list, st->row_count);
   YR_CHECK_LAUNCH();
-  const int len = 2 * d * d;
-  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, s>>>((const float*)st->ws, (int)grid, len, st->dW1[l], st->dW2[l], d * d);
-  YR_CHECK_LAUNCH();
+  int rc = rows_reduce(st, l, (int)grid, s, side);
+  if (rc) return rc;
   const int wpb = 8, cpw = 2;
   int64_t blocks = ((int64_t)st->L.n_chunks + wpb * cpw - 1) / (wpb * cpw);
   spmm_scatter_rows_kernel<64><<<(unsigned)blocks, 256, 0, s>>>(st->L, st->row_flag, st->T, st->G[l]);
   YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+// reduction of the rows-layer dW partials: on the side stream (joined by the caller) when there is one
+static int rows_reduce(const yr_ngcf_state* st, int l, int parts, cudaStream_t s, SideStream* side) {
+  const int len = 2 * st->d * st->d;
+  cudaStream_t rs = s;
+  if (side) {
+    YR_CUDA(cudaEventRecord(side->fork, s));
+    YR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    rs = side->stream;
+  }
+  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, rs>>>((const float*)st->ws, parts, len, st->dW1[l], st->dW2[l],
+                                                         st->d * st->d);
+  YR_CHECK_LAUNCH();
+  if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
   return YR_OK;
 }
 
@@ -751,27 +788,6 @@ extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream
   return YR_OK;
 }
 
-// One helper stream + two events per device, created on first use (the only resources the library ever creates):
-// independent memsets of a step run on it, ordered against the caller's stream with events. YR_NGCF_SIDE_STREAM=0
-// keeps everything on the caller's stream.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
-static SideStream* side_stream() {
-  static SideStream pool[64];
-  static int state[64];                 // 0 = not tried, 1 = ready, -1 = unavailable
-  const char* e = getenv("YR_NGCF_SIDE_STREAM");
-  if (e && e[0] == '0') return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (state[dev] == 0) {
-    SideStream& x = pool[dev];
-    const bool ok = cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
-    state[dev] = ok ? 1 : -1;
-  }
-  return state[dev] == 1 ? &pool[dev] : nullptr;
-}
-
 extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
                                      const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
                                      float* step_loss, int prefix_done, yr_stream stream);
@@ -806,23 +822,24 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
     YR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }
   for (int l = 0; l <= L; ++l) YR_CUDA(cudaMemsetAsync(st->G[l], 0, sizeof(float) * (size_t)n * d, ms));
-  if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
   // Top layer: E_L is READ only at the <= 3B rows the batch touches (the tail) and dLoss/dE_L is non-zero only there.
   // So the last layer's forward (SpMM + transform) and backward run on those rows, and G_{L-1} += L^T T becomes a
   // scatter from them (same sums, different fp32 order). Needs the row scratch; E_L / LE_{L-1} keep stale values in
   // the other rows (yr_ngcf_propagate recomputes everything for validate / evaluate).
   const bool rows_path = st->row_flag && st->row_list && st->row_count && st->row_list_cap >= 3 * B && d == 64 &&
                          g_top_rows_mode;
-  if (rows_path) {
-    touched_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, s>>>(uid, pos, neg, B, st->nU, st->nI, st->row_flag,
-                                                                       st->row_list, st->row_count);
+  if (rows_path) {                                            // list of the batch rows: also off the critical path
+    touched_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, ms>>>(uid, pos, neg, B, st->nU, st->nI, st->row_flag,
+                                                                        st->row_list, st->row_count);
     YR_CHECK_LAUNCH();
   }
+  if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
   if (rows_path && g_dense_mode == 1) {
     for (int l = (prefix_done < L - 1 ? prefix_done : L - 1); l + 1 < L; ++l) {
       rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
       if (rc) return rc;
     }
+    if (side) YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));       // row list (and the cleared gradients) ready
     rc = yr_spmm_csr_rows(&st->L, d, st->E[L - 1], st->LE[L - 1], st->row_flag, s);
     if (rc) return rc;
     rc = yr_ngcf_dense_fwd_tc_launch(st->E[L - 1], st->LE[L - 1], st->W1[L - 1], st->W2[L - 1], slope, n, st->E[L], s,
@@ -842,11 +859,21 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
   for (int l = L - 1; l >= 0; --l) {
     if (!st->dW1[l] || !st->dW2[l]) return YR_ERR_BAD_ARG;
     if (rows_path && l == L - 1) {
-      rc = ngcf_layer_bwd_rows(st, l, slope, s);
+      rc = ngcf_layer_bwd_rows(st, l, slope, s, side);
       if (rc) return rc;
-      untouch_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, s>>>(st->row_flag, st->row_list, st->row_count);
+      reduce_pending = side != nullptr;
+      // re-arm the row scratch for the next step: behind the scatter, next to the following layers
+      cudaStream_t us = s;
+      if (side) {
+        YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));          // the reduce has read ws; also lets `fork` be reused
+        reduce_pending = false;
+        YR_CUDA(cudaEventRecord(side->fork, s));                  // scatter (reads row_flag) enqueued before this point
+        YR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        us = side->stream;
+      }
+      untouch_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, us>>>(st->row_flag, st->row_list, st->row_count);
       YR_CHECK_LAUNCH();
-      YR_CUDA(cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), s));
+      YR_CUDA(cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), us));
       continue;
     }
     // dense backward, then the reduction of its dW partials on the side stream underneath the transposed SpMM
