@@ -383,3 +383,29 @@ def test_per_batch_train_calls_with_prefetched_prefix_equal_one_call():
     assert isclose(total_a, total_b, rel_tol=1e-6)
     for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
         assert rel_fro(vb.cpu().numpy(), va.cpu().numpy()) < 1e-6, ka
+
+
+@pytest.mark.parametrize("layers", [1, 2, 4])
+def test_other_layer_counts_vs_port(layers):
+    """num_orders != 3: the row-sparse last layer is the ONLY layer at 1, the prefetched prefix has 0 / 1 / 3 layers."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    inter = syn.make_interactions(num_users=700, num_items=900, nnz=20_000, seed=4, n_clusters=4)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tpos, tneg = syn.sample_triples(split, inter.num_items, seed=42)
+    batches = syn.to_batches(tu, tpos, tneg, 1024)[:3]
+    torch.manual_seed(7)
+    tr = NGCFTrainer(cfg(optimizer="sgd", lr=0.05, num_orders=layers, batch_size=1024), inter.num_items, inter.num_users, L)
+    sd = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    port = tp.NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(layers)],
+                       [sd[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, "sgd", 0.05, 0.0)
+    total = sum(tr.train([b]) for b in batches)               # per-batch calls: exercises the prefetched prefix too
+    ptotal, psteps = port.train(batches)
+    assert isclose(total, ptotal, rel_tol=RTOL)
+    assert rel_fro(tr.model.embedding.weight.detach().cpu().numpy(), port.emb.detach().numpy()) < RTOL
+    for l in range(layers):
+        assert rel_fro(tr.model.W1[l].weight.detach().cpu().numpy(), port.W1[l].detach().numpy()) < RTOL
+        assert rel_fro(tr.model.W2[l].weight.detach().cpu().numpy(), port.W2[l].detach().numpy()) < RTOL
+    assert isclose(tr.validate(batches[:1]), port.validate(batches[:1]), rel_tol=RTOL)
