@@ -6,7 +6,7 @@
 //                             sparse gradient accumulate (vector RED), one optimizer update per touched row.
 //   yr_bpr_mf_validate      — MFTrainer.validate (reference trainers/mf_trainer.py:118-132)
 #include <stdlib.h>
-#include "common.cuh"
+#include "/root/repo/yelprecommendation_b200/csrc/common.cuh"
 
 namespace yr {
 
@@ -116,7 +116,7 @@ __global__ void bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* 
 // loss_acc (double[2]) sits right behind the counters (counters is 8 x int32 = 32 bytes; loss_acc at
 // byte offset 32) — the state struct hands us one 64-byte block for both.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrainThreads = 512;
+constexpr int kTrainThreads = 256;
 constexpr int kTrainWarps = kTrainThreads / 32;
 
 template <int VPL>
@@ -185,7 +185,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
         for (int i = 0; i < kTrainWarps; ++i) t += s_part[i];
         if (t != 0.0) atomicAdd(loss_acc + par, t);
       }
-      grid_sync(grid);
+      grid.sync();
       if (act) {
         red_row<VPL>(st.U + uu * D, lane, gu);
         red_row<VPL>(st.V + pp * D, lane, gp);
@@ -198,7 +198,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
         loss_acc[par ^ 1] = 0.0;
         if (s + 1 == n_steps) counters[4] = par ^ 1;
       }
-      if (s + 1 < n_steps) grid_sync(grid);
+      if (s + 1 < n_steps) grid.sync();
     }
     return;
   }
@@ -256,7 +256,9 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
       for (int i = 0; i < kTrainWarps; ++i) t += s_part[i];
       if (t != 0.0) atomicAdd(loss_acc + par, t);
     }
-    grid_sync(grid);
+    YR_PRE_SYNC
+    grid.sync();
+    YR_POST_SYNC
 
     // ---- phase 2: one optimizer update per row ----------------------------------------------
     OptScalars os;
@@ -287,7 +289,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
         const bool is_u = r0 < st.nU;
         const int64_t r = is_u ? r0 : r0 - st.nU;
         int32_t* flag = (is_u ? st.flagU : st.flagV) + r;
-        const bool touched = __ldcg(flag) != 0;
+        const bool touched = YR_FLAG_LD(flag) != 0;
         float* prow = (is_u ? st.U : st.V) + r * D;
         float* grow = (is_u ? st.gU : st.gV) + r * D;
         Row<VPL> pv = ld_row<VPL>(prow, lane), gv, mv, vv;
@@ -330,7 +332,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
       loss_acc[par ^ 1] = 0.0;
       if (s + 1 == n_steps) counters[4] = par ^ 1;
     }
-    if (s + 1 < n_steps) grid_sync(grid);
+    if (s + 1 < n_steps) grid.sync();
   }
 }
 

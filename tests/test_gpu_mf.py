@@ -177,3 +177,29 @@ def test_full_size_yelp_shape_vs_oracle(name, wd):
         touched[u] = True
         Ug = tr.model.user_embedding.weight.detach().cpu().numpy()
         assert np.array_equal(Ug[~touched], U0[~touched])
+
+
+@pytest.mark.parametrize("d", [32, 128, 256])
+@pytest.mark.parametrize("name,wd", [("sgd", 0.0), ("sgd", 1e-3), ("adam", 0.0)])
+def test_other_embedding_widths_vs_oracle(d, name, wd):
+    """embed_size 32 / 128 / 256 (1 / 4 / 8 floats per lane): register-resident SGD, scratch path (SGD + wd) and the
+    dense-semantics sweep, 6 steps of 1,024 triples with duplicates, against the C oracle."""
+    from yelprecommendation_b200.trainers import MFTrainer
+    rng = np.random.default_rng(d)
+    nU, nI, B, steps = 3000, 2500, 1024, 6
+    tr = MFTrainer(cfg(optimizer=name, lr=1e-2, weight_decay=wd, batch_size=B, embed_size=d), nI, nU)
+    U0 = tr.model.user_embedding.weight.detach().cpu().numpy().copy()
+    V0 = tr.model.item_embedding.weight.detach().cpu().numpy().copy()
+    u, p, n = rng.integers(0, nU, B * steps), rng.integers(0, nI, B * steps), rng.integers(0, nI, B * steps)
+    u[:32] = 5
+    b = batches_from(u, p, n, B)
+    total = tr.train(b)
+    orc = cport.MFTrainerOracle(U0, V0, name, 1e-2, wd)
+    ototal, osteps = orc.train([{k: v.numpy() for k, v in x.items()} for x in b])
+    assert isclose(total, ototal, rel_tol=RTOL)
+    Ug, Vg = (w.detach().cpu().numpy() for w in (tr.model.user_embedding.weight, tr.model.item_embedding.weight))
+    if name == "sgd":
+        assert rel_err(Ug, orc.U) < RTOL and rel_err(Vg, orc.V) < RTOL
+    else:
+        assert_adam_close(Ug, orc.U, "U")
+        assert_adam_close(Vg, orc.V, "V")

@@ -59,12 +59,13 @@ def assert_adam_close(a, b, what=""):
     1-ulp difference in the loss scalar or in the order duplicate rows are summed (atomics: varies run to run) into a
     ~1e-4 relative difference of its update. Measured on the Yelp-shape tables over repeated runs: 0-4 of 2.0 M
     elements exceed 1e-5*max after 12 steps at lr=1e-2, the worst at 2.3e-4*max. So: norm-wise 1e-5 (the parity bar),
-    at most 1e-5 of the elements beyond 1e-5*max, none beyond 1e-3*max (numerical notes)."""
+    at most 1e-5 of the elements (2 elements for tables under 200 k elements) beyond 1e-5*max, none beyond 1e-3*max
+    (numerical notes)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.abs(b).max()
     d = np.abs(a - b)
     assert rel_fro(a, b) < RTOL, (what, rel_fro(a, b))
-    assert (d > RTOL * scale).mean() <= 1e-5, (what, int((d > RTOL * scale).sum()))
+    assert (d > RTOL * scale).sum() <= max(2, 1e-5 * d.size), (what, int((d > RTOL * scale).sum()))
     assert d.max() <= 1e-3 * scale, (what, d.max() / scale)
 
 

@@ -55,6 +55,17 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Grid barrier with the calling warp re-converged on both sides. cooperative_groups' grid sync lets thread 0 of the CTA
+// poll the barrier word between two CTA barriers; when the compiler leaves warp 0 diverged after an `if (threadIdx.x == 0)`
+// block in front of it (seen for the d = 32 instantiation of the BPR-MF trainer on sm_100a), lanes 1..31 of that warp ran
+// into the next phase before the grid barrier had completed and read rows other CTAs were still writing
+// (scripts/probe_mf, notes/README.md). __syncwarp() after the barrier holds them until lane 0 is through.
+__device__ __forceinline__ void grid_sync(cg::grid_group& grid) {
+  __syncwarp();
+  grid.sync();
+  __syncwarp();
+}
+
 // Per-lane slice of an embedding row: VPL = d/32 contiguous floats starting at lane*VPL.
 template <int VPL> struct Row { float x[VPL]; };
 
