@@ -144,7 +144,8 @@ int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate
 /* Where the per-layer d x d transforms run: 1 (default) = forward on tensor cores, tcgen05.mma.kind::tf32 with the
  * 3xTF32 split (within the 1e-5 parity bar), backward on the FP32 pipe; 0 = FP32 pipe for both, one fma chain per
  * output (forward bit-comparable with the oracle); 2 = tensor cores for the backward too (correct, currently slower
- * than the FP32-pipe kernel: see csrc/ngcf_tc_bwd.cu). Process-wide. */
+ * than the FP32-pipe kernel: see csrc/ngcf_tc_bwd.cu). Process-wide. The tensor-core kernels are d = 64 only; the
+ * transforms accept d in {32, 64, 128} (YR_ERR_BAD_DIM otherwise) and run on the FP32 pipe off d = 64 in every mode. */
 int yr_ngcf_set_dense_mode(int mode);
 int yr_ngcf_get_dense_mode(void);
 /* yr_ngcf_train_step, top layer: 1 (default) = backward on the batch rows only (dLoss/dE_L is zero elsewhere) with

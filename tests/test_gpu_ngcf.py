@@ -409,3 +409,81 @@ def test_other_layer_counts_vs_port(layers):
         assert rel_fro(tr.model.W1[l].weight.detach().cpu().numpy(), port.W1[l].detach().numpy()) < RTOL
         assert rel_fro(tr.model.W2[l].weight.detach().cpu().numpy(), port.W2[l].detach().numpy()) < RTOL
     assert isclose(tr.validate(batches[:1]), port.validate(batches[:1]), rel_tol=RTOL)
+
+
+@pytest.mark.parametrize("d", [32, 128])
+def test_other_embedding_widths_layer_fwd_bwd_vs_oracle(d):
+    """embed_size 32 / 128: FP32-pipe dense transforms (the tensor-core kernels are d = 64 only). Forward bit-exact
+    against the C oracle (same fma chain), backward at 1e-5."""
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_laplacian, coo_to_csr, laplacian_to_csr
+    inter = syn.make_interactions(num_users=500, num_items=700, nnz=12_000, seed=d, n_clusters=4)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    n = inter.num_users + inter.num_items
+    Lc = L.coalesce()
+    idx, val = Lc.indices().numpy(), Lc.values().numpy()
+    csr, csrT = coo_to_csr(idx[0], idx[1], val, n), coo_to_csr(idx[1], idx[0], val, n)
+    dcsr = laplacian_to_csr(L, "cuda")
+    rng = np.random.default_rng(d)
+    E0 = rng.standard_normal((n, d)).astype(np.float32)
+    W1 = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+    W2 = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+    Gn = rng.standard_normal((n, d)).astype(np.float32)
+    G0 = rng.standard_normal((n, d)).astype(np.float32)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    En, LE = ops.ngcf_layer_fwd(dcsr, cu(E0), cu(W1), cu(W2))
+    Eo, LEo = cport.ngcf_layer_fwd(csr, E0, W1, W2)
+    assert np.array_equal(LE.cpu().numpy(), LEo)
+    assert np.array_equal(En.cpu().numpy(), Eo)
+    G = cu(G0.copy())
+    dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(E0), LE, En, cu(Gn), cu(W1), cu(W2), G)
+    Go, dW1o, dW2o = cport.ngcf_layer_bwd(csrT, E0, LEo, Eo, Gn, W1, W2, G0)
+    assert rel_fro(G.cpu().numpy(), Go) < RTOL
+    assert rel_fro(dW1.cpu().numpy(), dW1o) < RTOL and rel_fro(dW2.cpu().numpy(), dW2o) < RTOL
+
+
+@pytest.mark.parametrize("d,layers,name,lr", [(32, 3, "sgd", 0.05), (32, 2, "adam", 1e-3), (128, 1, "sgd", 0.05),
+                                              (128, 2, "adam", 1e-3)])
+def test_other_embedding_widths_trainer_vs_port(d, layers, name, lr):
+    """NGCFTrainer.train / validate / evaluate at embed_size 32 / 128 (BASELINE config 5 asks d = 128) against the
+    torch-CPU port; evaluation ids bit-exact against the C oracle on the concatenated embeddings."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr, build_laplacian
+    from yelprecommendation_b200.trainers import NGCFTrainer
+    inter = syn.make_interactions(num_users=700, num_items=900, nnz=20_000, seed=4, n_clusters=4)
+    L = build_laplacian(inter.user, inter.item, inter.rating, inter.num_users, inter.num_items)
+    split = syn.split_per_user(inter, seed=42)
+    tu, tpos, tneg = syn.sample_triples(split, inter.num_items, seed=42)
+    batches = syn.to_batches(tu, tpos, tneg, 1024)[:3]
+    torch.manual_seed(d + layers)
+    tr = NGCFTrainer(cfg(optimizer=name, lr=lr, num_orders=layers, batch_size=1024, embed_size=d), inter.num_items,
+                     inter.num_users, L)
+    sd = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    port = tp.NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(layers)],
+                       [sd[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, name, lr, 0.0)
+    total = tr.train(batches)
+    ptotal, psteps = port.train(batches)
+    assert isclose(total, ptotal, rel_tol=RTOL)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), psteps) < RTOL
+    tol = RTOL if name == "sgd" else 2e-5
+    assert rel_fro(tr.model.embedding.weight.detach().cpu().numpy(), port.emb.detach().numpy()) < tol
+    for l in range(layers):
+        assert rel_fro(tr.model.W1[l].weight.detach().cpu().numpy(), port.W1[l].detach().numpy()) < 10 * tol
+        assert rel_fro(tr.model.W2[l].weight.detach().cpu().numpy(), port.W2[l].detach().numpy()) < 10 * tol
+    assert isclose(tr.validate(batches[:1]), port.validate(batches[:1]), rel_tol=RTOL)
+    uid, pos, mask = syn.eval_lists(split, "valid")
+    ec = build_eval_csr(uid, pos, mask, inter.num_items)
+    from yelprecommendation_b200 import ops
+    if not ops.eval_width_supported(d * (layers + 1), 10):     # 384: beyond the evaluation kernels (DESIGN.md 3.5)
+        assert d * (layers + 1) > 256
+        with pytest.raises(NotImplementedError):
+            tr.evaluate(ec)
+        return
+    got = tr.evaluate(ec)
+    cat = ops.ngcf_concat(tr.propagate()[0]).cpu().numpy()
+    nU = inter.num_users
+    otopk, _, _, osums = cport.eval_topk_metrics(cat[:nU], cat[nU:], ec.eval_uid, ec.mask_ptr, ec.mask_idx, ec.act_ptr,
+                                                 ec.act_idx, 10)
+    assert np.array_equal(tr.last_topk.cpu().numpy(), otopk)
+    assert np.allclose(got, cport.metrics_from_sums(osums, ec.n_eval), rtol=1e-12)

@@ -63,13 +63,16 @@ def _ngcf_problem(seed=21, nu=1203, ni=958, nnz=30000, d=64, layers=3):
     return inter, L, batches, init
 
 
-@pytest.mark.parametrize("optname,lr,wd,layers", [("sgd", 0.05, 0.0, 3), ("adam", 1e-2, 1e-4, 3), ("adamw", 2e-3, 1e-2, 1)])
-def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers):
-    """Op-by-op sharded path (rectangular SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle."""
+@pytest.mark.parametrize("optname,lr,wd,layers,d", [("sgd", 0.05, 0.0, 3, 64), ("adam", 1e-2, 1e-4, 3, 64),
+                                                    ("adamw", 2e-3, 1e-2, 1, 64), ("sgd", 0.05, 0.0, 1, 128),
+                                                    ("adam", 1e-2, 1e-4, 3, 32)])
+def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers, d):
+    """Op-by-op sharded path (rectangular SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle;
+    d = 128 is BASELINE config 5's width (one layer: the tail kernels take concatenated widths up to 256)."""
     from oracle.torch_port import NGCFPort
     from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
-    inter, L, batches, init = _ngcf_problem(layers=layers)
-    cfg = SimpleNamespace(embed_size=64, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+    inter, L, batches, init = _ngcf_problem(layers=layers, d=d)
+    cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
     tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init)
     loss = tr.train(batches)
     port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],

@@ -21,8 +21,10 @@ struct DenseCfg {
   static constexpr int kColGroups = D / 4;
   static constexpr int kRowGroups = kThreads / kColGroups;
   static constexpr int TM = 4 * kRowGroups;                       // 64 for D=64
+  static constexpr int RO = D / kRowGroups;                       // dW rows (o) per thread: 1 / 4 / 16 for D = 32 / 64 / 128
   static constexpr size_t kSmemFwd = (size_t)(2 * D * TM + 2 * D * D) * sizeof(float);
   static constexpr size_t kSmemBwd = (size_t)(3 * TM * D + 2 * D * D) * sizeof(float);
+  static_assert(D == 32 || D == 64 || D == 128, "dense transforms: D in {32, 64, 128}");
 };
 
 template <int D>
@@ -111,7 +113,7 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
   // is graph row row_list[q], everything else is unchanged.
   using C = DenseCfg<D>;
   constexpr int TM = C::TM;
-  static_assert(C::kColGroups * C::kColGroups == C::kThreads, "dW tiling assumes D == 64");
+  constexpr int RO = C::RO;
   if (row_list) n = *row_count;
   extern __shared__ __align__(16) float smem[];
   float* dZs = smem;                    // [TM][D]
@@ -126,9 +128,9 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
     reinterpret_cast<float4*>(W1s)[idx] = __ldg(reinterpret_cast<const float4*>(W1) + idx);
     reinterpret_cast<float4*>(W2s)[idx] = __ldg(reinterpret_cast<const float4*>(W2) + idx);
   }
-  float dw1[4][4], dw2[4][4];
+  float dw1[RO][4], dw2[RO][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RO; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { dw1[i][j] = 0.f; dw2[i][j] = 0.f; }
 
@@ -207,17 +209,26 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       }
     }
 
-    // ---- dW1[o,i], dW2[o,i]: o = ty*4.., i = tx*4.. ; k = row (rows past n hold dZ = 0) ----
+    // ---- dW1[o,i], dW2[o,i]: o = ty*RO.., i = tx*4.. ; k = row (rows past n hold dZ = 0) ----
 #pragma unroll 4
     for (int r = 0; r < TM; ++r) {
-      const float4 dz = *reinterpret_cast<const float4*>(dZs + r * D + ty * 4);
+      float dzv[RO];
+      if constexpr (RO >= 4) {
+#pragma unroll
+        for (int i = 0; i < RO; i += 4) {
+          const float4 dz = *reinterpret_cast<const float4*>(dZs + r * D + ty * RO + i);
+          dzv[i] = dz.x; dzv[i + 1] = dz.y; dzv[i + 2] = dz.z; dzv[i + 3] = dz.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < RO; ++i) dzv[i] = dZs[r * D + ty * RO + i];
+      }
       const float4 s4 = *reinterpret_cast<const float4*>(Ss + r * D + tx * 4);
       const float4 p4 = *reinterpret_cast<const float4*>(Ps + r * D + tx * 4);
-      const float dzv[4] = {dz.x, dz.y, dz.z, dz.w};
       const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
       const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RO; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           dw1[i][j] = fmaf(dzv[i], sv[j], dw1[i][j]);
@@ -227,8 +238,8 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
   }
   float* my = ws + (size_t)blockIdx.x * 2 * D * D;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int o = ty * 4 + i;
+  for (int i = 0; i < RO; ++i) {
+    const int o = ty * RO + i;
     reinterpret_cast<float4*>(my + o * D)[tx] = make_float4(dw1[i][0], dw1[i][1], dw1[i][2], dw1[i][3]);
     reinterpret_cast<float4*>(my + D * D + o * D)[tx] = make_float4(dw2[i][0], dw2[i][1], dw2[i][2], dw2[i][3]);
   }
@@ -435,33 +446,61 @@ extern "C" int yr_ngcf_set_top_rows_mode(int mode) {
   return YR_OK;
 }
 
-extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
-                                 float slope, float* E_next, yr_stream stream) {
-  if (!E || !LE || !W1 || !W2 || !E_next || n < 0) return YR_ERR_BAD_ARG;
-  if (d != 64) return YR_ERR_BAD_DIM;
-  if (n == 0) return YR_OK;
-  if (g_dense_mode == 1)      // tcgen05 3xTF32 (ngcf_tc.cu)
-    return yr_ngcf_dense_fwd_tc_launch(E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
-  using C = DenseCfg<64>;
+template <int D>
+static int dense_fwd_fp32_launch(int64_t n, const float* E, const float* LE, const float* W1, const float* W2, float slope,
+                                 float* E_next, cudaStream_t s) {
+  using C = DenseCfg<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C::kSmemFwd));
+    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemFwd));
     attr_set = true;
   }
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
-  int64_t grid = (int64_t)yr_sm_count() * 3;
+  int64_t grid = (int64_t)yr_sm_count() * (D <= 64 ? 3 : 1);
   if (grid > n_tiles) grid = n_tiles;
-  ngcf_dense_fwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemFwd, (cudaStream_t)stream>>>(
-      E, LE, W1, W2, slope, n, E_next);
+  ngcf_dense_fwd_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmemFwd, s>>>(E, LE, W1, W2, slope, n, E_next);
   YR_CHECK_LAUNCH();
   return YR_OK;
+}
+
+template <int D>
+static int dense_bwd_fp32_launch(int64_t n, const float* E, const float* LE, const float* E_next, const float* G_next,
+                                 const float* W1, const float* W2, float slope, float* G, float* T, float* ws,
+                                 cudaStream_t s, int* n_parts) {
+  using C = DenseCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBwd));
+    attr_set = true;
+  }
+  const int64_t n_tiles = (n + C::TM - 1) / C::TM;
+  int64_t grid = (int64_t)yr_sm_count() * (D <= 64 ? kBwdCtasPerSm : 1);       // D = 128: 176 KB of shared memory per CTA
+  if (grid > n_tiles) grid = n_tiles;
+  ngcf_dense_bwd_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(E, LE, E_next, G_next, W1, W2, slope, n, G, T, ws,
+                                                                          nullptr, nullptr);
+  YR_CHECK_LAUNCH();
+  *n_parts = (int)grid;
+  return YR_OK;
+}
+
+extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
+                                 float slope, float* E_next, yr_stream stream) {
+  if (!E || !LE || !W1 || !W2 || !E_next || n < 0) return YR_ERR_BAD_ARG;
+  if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
+  if (n == 0) return YR_OK;
+  if (g_dense_mode == 1 && d == 64)      // tcgen05 3xTF32 (ngcf_tc.cu); other widths run on the FP32 pipe
+    return yr_ngcf_dense_fwd_tc_launch(E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
+  switch (d) {
+    case 32: return dense_fwd_fp32_launch<32>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
+    case 64: return dense_fwd_fp32_launch<64>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
+    default: return dense_fwd_fp32_launch<128>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
+  }
 }
 
 extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
                                  float slope, float* E_next, float* LE_save, yr_stream stream) {
   if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
-  if (d != 64) return YR_ERR_BAD_DIM;
+  if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
   if (rc) return rc;
   return yr_ngcf_dense_fwd(d, L->n_rows, E, LE_save, W1, W2, slope, E_next, stream);
@@ -476,25 +515,15 @@ static int dense_bwd_launch(int d, int64_t n, const float* E, const float* LE, c
                             const float* W1, const float* W2, float slope, float* G, float* T, void* ws, size_t ws_bytes,
                             cudaStream_t s, int* n_parts) {
   if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !ws || n <= 0) return YR_ERR_BAD_ARG;
-  if (d != 64) return YR_ERR_BAD_DIM;
+  if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
-  if (g_dense_mode == 1 && g_bwd_tc)            // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
+  if (g_dense_mode == 1 && g_bwd_tc && d == 64)            // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
     return yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
-  using C = DenseCfg<64>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C::kSmemBwd));
-    attr_set = true;
+  switch (d) {
+    case 32: return dense_bwd_fp32_launch<32>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
+    case 64: return dense_bwd_fp32_launch<64>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
+    default: return dense_bwd_fp32_launch<128>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
   }
-  const int64_t n_tiles = (n + C::TM - 1) / C::TM;
-  int64_t grid = (int64_t)yr_sm_count() * kBwdCtasPerSm;
-  if (grid > n_tiles) grid = n_tiles;
-  ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
-      E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, nullptr, nullptr);
-  YR_CHECK_LAUNCH();
-  *n_parts = (int)grid;
-  return YR_OK;
 }
 
 static int dense_bwd_reduce(int d, const void* ws, int n_parts, float* dW1, float* dW2, cudaStream_t s) {
