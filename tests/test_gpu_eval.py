@@ -102,6 +102,18 @@ def test_eval_random_vs_oracle(nU, nI, d, n_eval, K, mode):
         assert fallback_rows() <= max(1, n_eval // 50)       # the filter decides (almost) every row itself
 
 
+@pytest.mark.parametrize("nU,nI,d,n_eval,K", [(300, 1500, 512, 260, 10), (200, 900, 1024, 130, 10), (150, 700, 320, 77, 32),
+                                               (120, 600, 300, 129, 10), (100, 400, 1024, 1, 5)])
+def test_eval_wide_tables_vs_oracle(nU, nI, d, n_eval, K):
+    """Widths beyond the shared-memory user tile (the reference's mf_sweep_config.yaml goes to embed_size 1,024; NGCF
+    concatenates d * (num_orders + 1) columns): the tail of the transposed user tile is read from the HBM workspace.
+    Same fma chain -> ids, scores and metric terms stay bit-exact."""
+    rng = np.random.default_rng(nI + d)
+    U, V, csr = _random_problem(rng, nU, nI, d, n_eval)
+    check_vs_oracle(U, V, csr, K, "exact")
+    check_vs_oracle(U, V, csr, K, None)            # default dispatch must pick a kernel that takes the width
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_eval_heavy_masks_and_ties(mode):
     rng = np.random.default_rng(5)

@@ -179,11 +179,12 @@ def test_full_size_yelp_shape_vs_oracle(name, wd):
         assert np.array_equal(Ug[~touched], U0[~touched])
 
 
-@pytest.mark.parametrize("d", [32, 128, 256])
+@pytest.mark.parametrize("d", [32, 128, 256, 512, 1024])
 @pytest.mark.parametrize("name,wd", [("sgd", 0.0), ("sgd", 1e-3), ("adam", 0.0)])
 def test_other_embedding_widths_vs_oracle(d, name, wd):
-    """embed_size 32 / 128 / 256 (1 / 4 / 8 floats per lane): register-resident SGD, scratch path (SGD + wd) and the
-    dense-semantics sweep, 6 steps of 1,024 triples with duplicates, against the C oracle."""
+    """embed_size 32 ... 1,024 (the values of the reference's mf_sweep_config.yaml; 1 ... 32 floats per lane):
+    register-resident SGD (up to 256), scratch path and the dense-semantics sweep, 6 steps of 1,024 triples with
+    duplicates, against the C oracle; then validate and a full evaluation at that width."""
     from yelprecommendation_b200.trainers import MFTrainer
     rng = np.random.default_rng(d)
     nU, nI, B, steps = 3000, 2500, 1024, 6
@@ -201,5 +202,28 @@ def test_other_embedding_widths_vs_oracle(d, name, wd):
     if name == "sgd":
         assert rel_err(Ug, orc.U) < RTOL and rel_err(Vg, orc.V) < RTOL
     else:
-        assert_adam_close(Ug, orc.U, "U")
-        assert_adam_close(Vg, orc.V, "V")
+        assert_adam_close(Ug, orc.U, "U", touched=B * steps * d)
+        assert_adam_close(Vg, orc.V, "V", touched=2 * B * steps * d)
+    if wd == 0.0:
+        return
+    # validate + evaluate at this width (ids bit-exact against the oracle on the trainer's own tables)
+    assert isclose(tr.validate(b[:2]), orc_validate(Ug, Vg, b[:2]), rel_tol=RTOL)
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    uid = rng.integers(0, nU, 150)
+    pos = [rng.permutation(nI)[: int(rng.integers(1, 20))].tolist() for _ in uid]
+    mask = [rng.permutation(nI)[: int(rng.integers(0, 40))].tolist() for _ in uid]
+    ec = build_eval_csr(uid, pos, mask, nI)
+    got = tr.evaluate(ec)
+    otopk, _, _, osums = cport.eval_topk_metrics(Ug, Vg, ec.eval_uid, ec.mask_ptr, ec.mask_idx, ec.act_ptr, ec.act_idx, 10)
+    assert np.array_equal(tr.last_topk.cpu().numpy(), otopk)
+    assert np.allclose(got, cport.metrics_from_sums(osums, ec.n_eval), rtol=1e-12)
+
+
+def orc_validate(U, V, batches):
+    """Sum of batch-mean BPR losses on fixed tables (MFTrainer.validate, mf_trainer.py:118-132), float64 on the host."""
+    total = 0.0
+    for x in batches:
+        u, p, n = (x[k].numpy() for k in ("user_id", "pos_item", "neg_item"))
+        d = (U[u].astype(np.float64) * (V[p].astype(np.float64) - V[n].astype(np.float64))).sum(1)
+        total += float(np.mean(np.logaddexp(0.0, -d)))
+    return total

@@ -54,18 +54,20 @@ def rel_fro(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def assert_adam_close(a, b, what=""):
+def assert_adam_close(a, b, what="", touched=0):
     """Adam divides by sqrt(v)+eps: an element whose gradient is below eps=1e-8 (a cancelling g*p - g*n) turns a
     1-ulp difference in the loss scalar or in the order duplicate rows are summed (atomics: varies run to run) into a
     ~1e-4 relative difference of its update. Measured on the Yelp-shape tables over repeated runs: 0-4 of 2.0 M
     elements exceed 1e-5*max after 12 steps at lr=1e-2, the worst at 2.3e-4*max. So: norm-wise 1e-5 (the parity bar),
     at most 1e-5 of the elements (2 elements for tables under 200 k elements) beyond 1e-5*max, none beyond 1e-3*max
-    (numerical notes)."""
+    (numerical notes). Small tables hit by many updates (the width tests: 18 k row updates on 3,000 rows) pass
+    `touched` = number of element updates with a gradient; the same 2e-6 .. 5e-6 of THOSE are allowed (measured at
+    d = 256: 9 of 4.7 M)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.abs(b).max()
     d = np.abs(a - b)
     assert rel_fro(a, b) < RTOL, (what, rel_fro(a, b))
-    assert (d > RTOL * scale).sum() <= max(2, 1e-5 * d.size), (what, int((d > RTOL * scale).sum()))
+    assert (d > RTOL * scale).sum() <= max(2, 1e-5 * d.size, 5e-6 * touched), (what, int((d > RTOL * scale).sum()))
     assert d.max() <= 1e-3 * scale, (what, d.max() / scale)
 
 

@@ -25,7 +25,7 @@ int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t
                          const int32_t* mask_idx, const int32_t* act_ptr, const int32_t* act_idx,
                          const int32_t* act_nuniq, const double* inv_log2, int K, int64_t* topk_out,
                          float* topk_score, double* user_metrics, int32_t* err, const int32_t* row_list,
-                         const int32_t* n_rows_dev, yr_stream stream);
+                         const int32_t* n_rows_dev, yr_stream stream, void* ws = nullptr, size_t ws_bytes = 0);
 int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, const int32_t* act_nuniq,
                           int64_t n_eval, double* metric_sums, yr_stream stream);
 
@@ -66,7 +66,8 @@ __device__ __forceinline__ void grid_sync(cg::grid_group& grid) {
   __syncwarp();
 }
 
-// Per-lane slice of an embedding row: VPL = d/32 contiguous floats starting at lane*VPL.
+// Per-lane slice of an embedding row of d = 32 * VPL floats. VPL = 1 / 2: lane owns VPL contiguous floats; VPL >= 4: lane
+// owns float4 number j * 32 + lane for j < VPL / 4 (every warp access is one contiguous 512-byte run).
 template <int VPL> struct Row { float x[VPL]; };
 
 template <int VPL>
@@ -80,7 +81,7 @@ __device__ __forceinline__ Row<VPL> ld_row(const float* __restrict__ row, int la
   } else {
 #pragma unroll
     for (int j = 0; j < VPL / 4; ++j) {
-      float4 t = reinterpret_cast<const float4*>(row)[lane * (VPL / 4) + j];
+      float4 t = reinterpret_cast<const float4*>(row)[j * 32 + lane];
       r.x[4 * j + 0] = t.x; r.x[4 * j + 1] = t.y; r.x[4 * j + 2] = t.z; r.x[4 * j + 3] = t.w;
     }
   }
@@ -96,7 +97,7 @@ __device__ __forceinline__ void st_row(float* __restrict__ row, int lane, const 
   } else {
 #pragma unroll
     for (int j = 0; j < VPL / 4; ++j)
-      reinterpret_cast<float4*>(row)[lane * (VPL / 4) + j] =
+      reinterpret_cast<float4*>(row)[j * 32 + lane] =
           make_float4(r.x[4 * j + 0], r.x[4 * j + 1], r.x[4 * j + 2], r.x[4 * j + 3]);
   }
 }
@@ -111,7 +112,7 @@ __device__ __forceinline__ void red_row(float* __restrict__ row, int lane, const
   } else {
 #pragma unroll
     for (int j = 0; j < VPL / 4; ++j)
-      atomicAdd(reinterpret_cast<float4*>(row) + lane * (VPL / 4) + j,
+      atomicAdd(reinterpret_cast<float4*>(row) + j * 32 + lane,
                 make_float4(r.x[4 * j + 0], r.x[4 * j + 1], r.x[4 * j + 2], r.x[4 * j + 3]));
   }
 }
@@ -200,7 +201,11 @@ inline int yr_csr_ok(const yr_csr* A) {
 }
 
 inline int dim_vpl(int d) {
-  switch (d) { case 32: return 1; case 64: return 2; case 128: return 4; case 256: return 8; default: return 0; }
+  switch (d) {
+    case 32: return 1; case 64: return 2; case 128: return 4; case 256: return 8;
+    case 512: return 16; case 1024: return 32;     // BPR-MF only (the reference's mf_sweep_config.yaml goes to 1,024)
+    default: return 0;
+  }
 }
 
 }  // namespace yr

@@ -50,7 +50,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 struct EvalSmem {
   // dynamic layout (floats unless noted):
-  //   Us   [d_pad][kTU]
+  //   Us   [k_res][kTU]      k_res = d_pad when the whole user tile fits, else the largest multiple of kKC that does;
+  //                          rows k >= k_res of the transposed user tile are then read from UT (global) instead
   //   Vs   [kStages][kKC][kTI]
   //   topS [kTU][K], topI [kTU][K] (int)
   //   qkey [kQCap] (u32), qval [kQCap]
@@ -63,6 +64,53 @@ __host__ __device__ inline size_t eval_smem_bytes(int d_pad, int K) {
   size_t f = (size_t)d_pad * kTU + (size_t)kStages * kKC * kTI + 2 * (size_t)kTU * K + 2 * (size_t)kQCap +
              kMCap + 4 * (size_t)kTU;
   return f * 4 + kStages * 8 + 16 + 16;
+}
+
+// largest multiple of kKC <= d_pad whose [k][kTU] user tile fits 227 KB next to everything else
+inline int eval_resident_k(int d_pad, int K) {
+  for (int k = d_pad; k >= kKC; k -= kKC)
+    if (eval_smem_bytes(k, K) <= (size_t)227 * 1024) return k;
+  return 0;
+}
+inline int64_t eval_ldu(int64_t n_eval) { return (n_eval + kTU - 1) / kTU * kTU; }
+
+// UT[k][e] = Uemb[eval_uid[e]][k_res + k] for the rows of the user tile that do not fit shared memory (wide tables)
+__global__ void __launch_bounds__(256)
+gather_transpose_users_kernel(const float* __restrict__ Uemb, int64_t nU, int d, const int64_t* __restrict__ eval_uid,
+                              int64_t n_eval, int k_res, int k_rows, int64_t ldu, float* __restrict__ UT) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ldu) return;
+  int64_t uid = -1;
+  if (e < n_eval) { uid = eval_uid[e]; if (uid < 0 || uid >= nU) uid = -1; }     // a bad id is flagged by the main kernel
+  for (int k = blockIdx.y; k < k_rows; k += gridDim.y) {
+    const int kk = k_res + k;
+    UT[(size_t)k * ldu + e] = (uid >= 0 && kk < d) ? __ldg(Uemb + uid * d + kk) : 0.f;
+  }
+}
+
+// acc[i][j] += sum_k us[k][user_i] * vs[k][item_j] over one k-chunk, k ascending
+template <bool kGlobalU>
+__device__ __forceinline__ void eval_chunk_fma(float (&acc)[8][8], const float* __restrict__ us, int64_t ustride,
+                                               const float* __restrict__ vs, int tu, int ti) {
+#pragma unroll 4
+  for (int k = 0; k < kKC; ++k) {
+    float4 a0, a1;
+    if constexpr (kGlobalU) {
+      a0 = __ldg(reinterpret_cast<const float4*>(us + k * ustride + tu * 4));
+      a1 = __ldg(reinterpret_cast<const float4*>(us + k * ustride + 64 + tu * 4));
+    } else {
+      a0 = *reinterpret_cast<const float4*>(us + k * kTU + tu * 4);
+      a1 = *reinterpret_cast<const float4*>(us + k * kTU + 64 + tu * 4);
+    }
+    const float4 b0 = *reinterpret_cast<const float4*>(vs + k * kTI + ti * 4);
+    const float4 b1 = *reinterpret_cast<const float4*>(vs + k * kTI + 64 + ti * 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
 }
 
 __device__ __forceinline__ bool cand_better(float s_a, int i_a, float s_b, int i_b) {
@@ -78,13 +126,13 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
                  const int32_t* __restrict__ act_nuniq, const double* __restrict__ inv_log2, int K,
                  int64_t* __restrict__ topk_out, float* __restrict__ topk_score,
                  double* __restrict__ user_metrics, int32_t* err, const int32_t* __restrict__ row_list,
-                 const int32_t* __restrict__ n_rows_dev) {
+                 const int32_t* __restrict__ n_rows_dev, int k_res, const float* __restrict__ UT, int64_t ldu) {
   // optional indirection: evaluate only rows row_list[0 .. *n_rows_dev) (the tensor-core path's undecided rows)
   if (row_list) n_eval = *n_rows_dev;
   auto ROW = [&](int64_t t) -> int64_t { return row_list ? (int64_t)row_list[t] : t; };
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* Us = reinterpret_cast<float*>(smem_raw);
-  float* Vs = Us + (size_t)d_pad * kTU;
+  float* Vs = Us + (size_t)k_res * kTU;
   float* topS = Vs + (size_t)kStages * kKC * kTI;
   int* topI = reinterpret_cast<int*>(topS + (size_t)kTU * K);
   uint32_t* qkey = reinterpret_cast<uint32_t*>(topI + (size_t)kTU * K);
@@ -133,7 +181,7 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
   for (int64_t ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
     const int64_t e0 = ut * kTU;
     // ---- user tile: gather + transpose into Us[k][u]; reset per-user state ----
-    for (int idx = tid; idx < kTU * (d_pad / 4); idx += kEvalThreads) {
+    for (int idx = tid; idx < kTU * (k_res / 4); idx += kEvalThreads) {
       const int u = idx % kTU, c4 = idx / kTU;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int64_t e = e0 + u;
@@ -184,20 +232,8 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
         const int st = (int)(q % kStages);
         mbar_wait(bars + st, (uint32_t)((q / kStages) & 1));
         const float* vs = Vs + (size_t)st * kKC * kTI;
-        const float* us = Us + (size_t)ch * kKC * kTU;
-#pragma unroll 4
-        for (int k = 0; k < kKC; ++k) {
-          const float4 a0 = *reinterpret_cast<const float4*>(us + k * kTU + tu * 4);
-          const float4 a1 = *reinterpret_cast<const float4*>(us + k * kTU + 64 + tu * 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(vs + k * kTI + ti * 4);
-          const float4 b1 = *reinterpret_cast<const float4*>(vs + k * kTI + 64 + ti * 4);
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
+        if (ch * kKC < k_res) eval_chunk_fma<false>(acc, Us + (size_t)ch * kKC * kTU, kTU, vs, tu, ti);
+        else eval_chunk_fma<true>(acc, UT + (size_t)(ch * kKC - k_res) * ldu + e0, ldu, vs, tu, ti);
         __syncthreads();   // everyone is done with stage st
         if (tid == 0 && q + kStages < Q) issue(q + kStages);
       }
@@ -403,8 +439,11 @@ extern "C" int yr_transpose_items(const float* V, int64_t nI, int d, float* Vt, 
 }
 
 extern "C" size_t yr_eval_ws_bytes(int64_t n_eval, int d, int K) {
-  (void)n_eval; (void)d; (void)K;
-  return 256;   // v1 keeps all state in shared memory; the workspace is reserved for later versions
+  // tables up to ~288 floats wide keep all state in shared memory; wider ones spill the tail of the transposed user
+  // tile, [pad32(d) - k_res][round_up(n_eval, 128)] floats, to the workspace
+  if (n_eval <= 0 || d <= 0 || K <= 0 || K > kMaxK) return 256;
+  const int d_pad = pad32(d), k_res = eval_resident_k(d_pad, K);
+  return 256 + (size_t)(d_pad - k_res) * (size_t)eval_ldu(n_eval) * sizeof(float);
 }
 
 extern "C" int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* Vt, int64_t ldt,
@@ -415,10 +454,9 @@ extern "C" int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* 
                                     int64_t* topk_out, float* topk_score, double* user_metrics,
                                     double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
                                     yr_stream stream) {
-  (void)ws; (void)ws_bytes;
   int rc = yr_eval_exact_launch(Uemb, nU, Vt, ldt, nI, d, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx,
                                 act_nuniq, inv_log2, K, topk_out, topk_score, user_metrics, err, nullptr, nullptr,
-                                stream);
+                                stream, ws, ws_bytes);
   if (rc) return rc;
   return yr_eval_reduce_launch(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums, stream);
 }
@@ -430,7 +468,7 @@ int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t
                          const int32_t* mask_idx, const int32_t* act_ptr, const int32_t* act_idx,
                          const int32_t* act_nuniq, const double* inv_log2, int K, int64_t* topk_out,
                          float* topk_score, double* user_metrics, int32_t* err, const int32_t* row_list,
-                         const int32_t* n_rows_dev, yr_stream stream) {
+                         const int32_t* n_rows_dev, yr_stream stream, void* ws, size_t ws_bytes) {
   if (!Uemb || !Vt || !eval_uid || !mask_ptr || !mask_idx || !act_ptr || !act_idx || !act_nuniq ||
       !inv_log2 || !topk_out || !user_metrics)
     return YR_ERR_BAD_ARG;
@@ -439,15 +477,27 @@ int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t
   if (ldt % kTI != 0 || ldt < nI || (ldt & 3) != 0) return YR_ERR_BAD_ARG;   // tiles must not run off Vt
   if (n_eval == 0) return YR_OK;
   const int d_pad = pad32(d);
-  const size_t smem = eval_smem_bytes(d_pad, K);
-  if (smem > 227 * 1024) return YR_ERR_BAD_DIM;
+  const int k_res = eval_resident_k(d_pad, K);
+  if (k_res <= 0) return YR_ERR_BAD_DIM;
+  const size_t smem = eval_smem_bytes(k_res, K);
+  float* UT = nullptr;
+  const int64_t ldu = eval_ldu(n_eval);
+  if (k_res < d_pad) {            // wide table: rows k >= k_res of the transposed user tile live in the workspace
+    if (row_list) return YR_ERR_BAD_DIM;                     // (the tensor-core path, d <= 256, never gets here)
+    if (!ws || ws_bytes < yr_eval_ws_bytes(n_eval, d, K)) return YR_ERR_WORKSPACE;
+    UT = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + 256);
+    const int k_rows = d_pad - k_res;
+    dim3 g((unsigned)((ldu + 255) / 256), (unsigned)(k_rows < 64 ? k_rows : 64));
+    gather_transpose_users_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(Uemb, nU, d, eval_uid, n_eval, k_res, k_rows, ldu, UT);
+    YR_CHECK_LAUNCH();
+  }
   YR_CUDA(cudaFuncSetAttribute(eval_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_utiles = (n_eval + kTU - 1) / kTU;
   int64_t grid = yr_sm_count();
   if (grid > n_utiles) grid = n_utiles;
   eval_topk_kernel<<<(unsigned)grid, kEvalThreads, smem, (cudaStream_t)stream>>>(
       Uemb, nU, Vt, ldt, nI, d, d_pad, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq,
-      inv_log2, K, topk_out, topk_score, user_metrics, err, row_list, n_rows_dev);
+      inv_log2, K, topk_out, topk_score, user_metrics, err, row_list, n_rows_dev, k_res, UT, ldu);
   YR_CHECK_LAUNCH();
   return YR_OK;
 }

@@ -116,15 +116,20 @@ __global__ void bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* 
 // loss_acc (double[2]) sits right behind the counters (counters is 8 x int32 = 32 bytes; loss_acc at
 // byte offset 32) — the state struct hands us one 64-byte block for both.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrainThreads = 512;
-constexpr int kTrainWarps = kTrainThreads / 32;
+// 512-thread CTAs (half the CTAs at the grid barrier) up to d = 256; 256 threads beyond, where a thread holds up to
+// four rows of 16 / 32 floats (255 registers available).
+template <int VPL> struct TrainCfg {
+  static constexpr int kThreads = VPL > 8 ? 256 : 512;
+  static constexpr int kWarps = kThreads / 32;
+};
 
 template <int VPL>
-__global__ void __launch_bounds__(kTrainThreads)
+__global__ void __launch_bounds__(TrainCfg<VPL>::kThreads)
 bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
                     const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
                     int64_t n_triples, int B, double* loss_sum, float* step_loss) {
   constexpr int D = VPL * 32;
+  constexpr int kTrainWarps = TrainCfg<VPL>::kWarps;
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -143,7 +148,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
   // are applied as vector REDs of -lr * g straight into the tables — no gradient scratch, no touched-row list, no
   // second pass over the rows. Two grid barriers per step remain (every read of step s precedes every update of
   // step s, every update precedes the reads of step s + 1): the reference's sequential step semantics.
-  if (!dense && B <= nwarps) {
+  if (VPL <= 8 && !dense && B <= nwarps) {
     const float neg_lr = -(float)opt.lr;
     int64_t u = 0, p = 0, n = 0;
     if (gwarp < ((n_triples < B) ? (int)n_triples : B)) { u = uid[gwarp]; p = pos[gwarp]; n = neg[gwarp]; }
@@ -449,6 +454,7 @@ static int launch_train(const yr_mf_state* st, const yr_opt* opt, const int64_t*
   int dev = 0, sms = 0, occ = 0;
   YR_CUDA(cudaGetDevice(&dev));
   YR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  constexpr int kTrainThreads = TrainCfg<VPL>::kThreads, kTrainWarps = TrainCfg<VPL>::kWarps;
   YR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bpr_mf_train_kernel<VPL>, kTrainThreads, 0));
   if (occ < 1) return YR_ERR_COOP;
   const bool dense = (opt->kind != YR_OPT_SGD) || (opt->weight_decay != 0.0);
@@ -482,6 +488,8 @@ extern "C" int yr_bpr_mf_train(const yr_mf_state* st, const yr_opt* opt, const i
     case 2: return launch_train<2>(st, opt, uid, pos, neg, n_triples, B, loss_sum, step_loss, s);
     case 4: return launch_train<4>(st, opt, uid, pos, neg, n_triples, B, loss_sum, step_loss, s);
     case 8: return launch_train<8>(st, opt, uid, pos, neg, n_triples, B, loss_sum, step_loss, s);
+    case 16: return launch_train<16>(st, opt, uid, pos, neg, n_triples, B, loss_sum, step_loss, s);
+    case 32: return launch_train<32>(st, opt, uid, pos, neg, n_triples, B, loss_sum, step_loss, s);
     default: return YR_ERR_BAD_DIM;
   }
 }
@@ -500,6 +508,8 @@ extern "C" int yr_bpr_mf_validate(const float* U, const float* V, int64_t nU, in
     case 2: bpr_mf_validate_kernel<2><<<g, 256, 0, s>>>(U, V, nU, nI, uid, pos, neg, n_triples, B, loss_sum, step_loss, err); break;
     case 4: bpr_mf_validate_kernel<4><<<g, 256, 0, s>>>(U, V, nU, nI, uid, pos, neg, n_triples, B, loss_sum, step_loss, err); break;
     case 8: bpr_mf_validate_kernel<8><<<g, 256, 0, s>>>(U, V, nU, nI, uid, pos, neg, n_triples, B, loss_sum, step_loss, err); break;
+    case 16: bpr_mf_validate_kernel<16><<<g, 256, 0, s>>>(U, V, nU, nI, uid, pos, neg, n_triples, B, loss_sum, step_loss, err); break;
+    case 32: bpr_mf_validate_kernel<32><<<g, 256, 0, s>>>(U, V, nU, nI, uid, pos, neg, n_triples, B, loss_sum, step_loss, err); break;
     default: return YR_ERR_BAD_DIM;
   }
   YR_CHECK_LAUNCH();

@@ -253,15 +253,6 @@ def transpose_items(V: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return Vt, ldt
 
 
-def eval_width_supported(d: int, K: int) -> bool:
-    """Does yr_eval_topk_metrics (FP32 pipe) take this width? Mirrors eval_smem_bytes() in csrc/eval.cu: user tile
-    [pad32(d) x 128] + 3 item stages [32 x 128] + top-K lists + candidate queue + mask list, 227 KB per CTA."""
-    d_pad = (d + 31) // 32 * 32
-    floats = d_pad * 128 + 3 * 32 * 128 + 2 * 128 * K + 2 * 2048 + 1024 + 4 * 128
-    return d % 4 == 0 and 1 <= K <= 32 and 4 * floats + 3 * 8 + 32 <= 227 * 1024
-
-
-
 def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None, mode: str = None):
     """Returns (topk [n_eval x K] int64, topk_score, user_metrics [n_eval x 4] f64, sums [6] f64, err) on device.
 
@@ -295,10 +286,8 @@ def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCS
                                           dptr(ws), ws.numel(), dptr(err), stream_ptr(dev)), "yr_eval_topk_metrics_tc")
         eval_topk_metrics.last_fallback_rows = ws[4:8].view(I32)      # device int32[1]: rows sent to the exact kernel
         return topk[:n], tsc[:n], um[:n], sums, err
-    if not eval_width_supported(d, ecsr.K):
-        raise NotImplementedError(f"full-catalog evaluation: embedding width {d} (NGCF: embed_size * (num_orders + 1)) with "
-                                  f"K = {ecsr.K} does not fit the evaluation kernels (tensor cores: multiples of 32 up to "
-                                  f"256; FP32 pipe: a [width x 128 users] tile resident in 227 KB of shared memory)")
+    if d % 4 != 0:
+        raise NotImplementedError(f"full-catalog evaluation: embedding width {d} is not a multiple of 4")
     if Vt is None:
         Vt, ldt = transpose_items(Vemb)
     else:
