@@ -323,6 +323,9 @@ typedef struct yr_cdae_tensors {
 
 size_t yr_cdae_ws_bytes(int64_t B, int64_t nI);
 
+/* BaseModel._activation_module (models/base_model.py:10-14): the two names the reference knows. */
+enum yr_activation { YR_ACT_SIGMOID = 0, YR_ACT_IDENTITY = 1 };
+
 /* z[b,:] = sigmoid( Wh . (x[b,:] * keep[b,:]) + bh + Vu[uid[b]] )   (models/cdae.py:46-51; keep == NULL in eval
  * mode, else the dropout multiplier 0 or 1/(1-p) the caller drew — nn.Dropout's mask is supplied, not re-drawn).
  * x is the dense [B x nI] multi-hot `input_mask` exactly as the reference's DataLoader yields it.
@@ -331,6 +334,11 @@ size_t yr_cdae_ws_bytes(int64_t B, int64_t nI);
 int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, const int64_t* uid, const float* x,
                    const float* keep, int64_t B, float* z_out, int64_t ldz, void* ws, size_t ws_bytes,
                    int32_t* err, yr_stream stream);
+/* Same with cfg.hidden_activation given (yr_activation; the plain call is sigmoid). h = cfg.hidden_size must be one of
+ * 32, 64, 128, 256, 512, 1024 (the values of the reference's cdae_sweep_config.yaml), YR_ERR_BAD_DIM otherwise. */
+int yr_cdae_hidden_ex(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, int hidden_act, const int64_t* uid,
+                      const float* x, const float* keep, int64_t B, float* z_out, int64_t ldz, void* ws, size_t ws_bytes,
+                      int32_t* err, yr_stream stream);
 
 /* pred[b,i] = sigmoid( z[b,:] . Wo[i,:] + bo[i] )  — CDAE.forward's dense output (models/cdae.py:52). */
 int yr_cdae_output(const yr_cdae_tensors* P, int64_t nI, int h, const float* z, int64_t ldz, int64_t B,
@@ -346,6 +354,12 @@ int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const y
                  const int64_t* uid, const float* x, const float* keep, const float* target,
                  const float* negative_mask, int64_t B, double* loss, float* step_loss,
                  void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+/* Same with cfg.hidden_activation given (the output activation stays sigmoid: NSBCELoss needs probabilities). */
+int yr_cdae_step_ex(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                    const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                    const int64_t* uid, const float* x, const float* keep, const float* target,
+                    const float* negative_mask, int64_t B, double* loss, float* step_loss,
+                    void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
 
 /* NSBCELoss.forward on dense tensors (loss.py:12-16): mean BCE over positions where target + negative_mask != 0. */
 int yr_nsbce_loss(const float* pred, const float* target, const float* negative_mask, int64_t n, float* loss,

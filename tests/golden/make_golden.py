@@ -266,8 +266,7 @@ class _SuppliedDropout(torch.nn.Module):
         return x * k
 
 
-def golden_cdae():
-    from trainers.cdae_trainer import CDAETrainer as RefCDAETrainer
+def _cdae_problem():
     rng = np.random.default_rng(21)
     nU, nI, B, p = 80, 112, 16, 0.6
     inter = syn.make_interactions(num_users=nU, num_items=nI, nnz=1400, seed=6, n_clusters=4)
@@ -307,6 +306,41 @@ def golden_cdae():
     tb = batches({"user_id": None, "input_mask": train_m, "negative_mask": neg_train})[:n_steps]
     vb = batches({"user_id": None, "input_mask": train_m, "valid_mask": valid_m, "negative_mask": neg_valid})
     eb = batches({"user_id": None, "input_mask": train_m + valid_m, "test_mask": test_m})
+    return nU, nI, B, p, users, train_m, keeps, out, tb, vb, eb
+
+
+def golden_cdae_widths():
+    """hidden_size / hidden_activation values of the reference's cdae_sweep_config.yaml on the cdae_small problem
+    (same masks, batches and dropout multipliers): init, 3 train-step losses, final state, validate / evaluate."""
+    from trainers.cdae_trainer import CDAETrainer as RefCDAETrainer
+    nU, nI, B, p, users, train_m, keeps, _, tb, vb, eb = _cdae_problem()
+    t = torch.from_numpy
+    out = {}
+    for ci, (h, act, name, lr) in enumerate([(32, "identity", "adam", 1e-2), (128, "sigmoid", "sgd", 0.5),
+                                             (256, "identity", "adam", 1e-3)]):
+        torch.manual_seed(42 + ci)
+        tr = RefCDAETrainer(cfg(optimizer=name, lr=lr, hidden_size=h, corruption_level=p, hidden_activation=act,
+                                output_activation="sigmoid", negative_sampling=True, loss_name="bce"), nI, nU)
+        tr.model.dropout_layer = _SuppliedDropout([t(k) for k in keeps])
+        for k, v in tr.model.state_dict().items():
+            out[f"w{ci}_init_" + k] = v.detach().numpy().copy()
+        tr.model.eval()
+        out[f"w{ci}_pred_eval0"] = tr.model(t(users[:B].copy()), t(train_m[:B].copy())).detach().numpy()
+        losses = [tr.train([b]) for b in tb]
+        out[f"w{ci}_h"], out[f"w{ci}_act"], out[f"w{ci}_name"], out[f"w{ci}_lr"] = h, act, name, lr
+        out[f"w{ci}_losses"] = np.array(losses)
+        for k, v in tr.model.state_dict().items():
+            out[f"w{ci}_final_" + k] = v.detach().numpy().copy()
+        out[f"w{ci}_valid_after"] = np.array(tr.validate(vb))
+        out[f"w{ci}_test_after"] = np.array(tr.evaluate(eb))
+        print(f"cdae_widths[{ci}] h={h} act={act}: losses", out[f"w{ci}_losses"], "valid", out[f"w{ci}_valid_after"])
+    np.savez_compressed(os.path.join(HERE, "cdae_widths.npz"), **out)
+
+
+def golden_cdae():
+    from trainers.cdae_trainer import CDAETrainer as RefCDAETrainer
+    nU, nI, B, p, users, train_m, keeps, out, tb, vb, eb = _cdae_problem()
+    t = torch.from_numpy
     for ci, (name, lr) in enumerate([("adam", 1e-2), ("sgd", 0.5)]):
         torch.manual_seed(42)
         tr = RefCDAETrainer(cfg(optimizer=name, lr=lr, hidden_size=64, corruption_level=p, hidden_activation="sigmoid",
@@ -372,6 +406,9 @@ def golden_run_loop():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cdae_widths":
+        golden_cdae_widths()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cdae":
         golden_cdae()
         sys.exit(0)

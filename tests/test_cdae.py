@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import torch_port as tp
-from util import RTOL, cfg, load_npz, rel_err
+from util import RTOL, assert_adam_close, cfg, load_npz, rel_err
 
 KEYS = ["hidden_layer.weight", "hidden_layer.bias", "user_nodes.weight", "output_layer.weight", "output_layer.bias"]
 
@@ -120,3 +120,83 @@ def test_default_dropout_draw_and_bad_ids():
     bad["user_id"][0] = nU
     with pytest.raises(IndexError):
         tr.train([bad])
+
+
+# ---- hidden_size / hidden_activation values of the reference's cdae_sweep_config.yaml ---------------------------------
+def _width_case(wi):
+    g, nU, nI, B, tb, vb, eb, keeps, _ = _fixture()
+    w = load_npz("cdae_widths.npz")
+    init = {k: torch.from_numpy(w[f"w{wi}_init_" + k].copy()) for k in KEYS}
+    return w, nU, nI, B, tb, vb, eb, keeps, init, int(w[f"w{wi}_h"]), str(w[f"w{wi}_act"]), str(w[f"w{wi}_name"]), float(w[f"w{wi}_lr"])
+
+
+@pytest.mark.parametrize("wi", [0, 1, 2])
+def test_port_matches_reference_other_widths(wi):
+    """The port with hidden_size 32 / 128 / 256 and hidden_activation identity / sigmoid against the REAL reference
+    (fixture cdae_widths.npz, tests/golden/make_golden.py cdae_widths)."""
+    w, nU, nI, B, tb, vb, eb, keeps, init, h, act, name, lr = _width_case(wi)
+    port = tp.CDAEPort(init, name, lr, hidden_activation=act)
+    pred = port.forward(tb[0]["user_id"], tb[0]["input_mask"]).detach().numpy()
+    assert rel_err(pred, w[f"w{wi}_pred_eval0"]) < 1e-6
+    _, steps = port.train(tb, keeps)
+    assert rel_err(steps, w[f"w{wi}_losses"]) < 1e-6
+    for k, v in port.state_dict().items():
+        assert rel_err(v.detach().numpy(), w[f"w{wi}_final_" + k]) < 1e-5, k
+    assert np.allclose(port.validate(vb), w[f"w{wi}_valid_after"], rtol=1e-5)
+    assert np.allclose(port.evaluate(eb), w[f"w{wi}_test_after"], rtol=1e-6)
+
+
+def _width_trainer(nU, nI, init, h, act, name, lr):
+    from yelprecommendation_b200.trainers import CDAETrainer
+    tr = CDAETrainer(cfg(optimizer=name, lr=lr, hidden_size=h, corruption_level=0.6, hidden_activation=act,
+                         output_activation="sigmoid", negative_sampling=True, loss_name="bce"), nI, nU)
+    tr.model.load_state_dict(init)
+    return tr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wi", [0, 1, 2])
+def test_train_validate_evaluate_other_widths_vs_reference(wi):
+    w, nU, nI, B, tb, vb, eb, keeps, init, h, act, name, lr = _width_case(wi)
+    tr = _width_trainer(nU, nI, init, h, act, name, lr)
+    tr.model.eval()
+    pred = tr.model(tb[0]["user_id"], tb[0]["input_mask"])
+    assert rel_err(pred.cpu().numpy(), w[f"w{wi}_pred_eval0"]) < RTOL
+    total = tr.train(tb, keeps=keeps)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), w[f"w{wi}_losses"]) < RTOL
+    assert isclose(total, float(np.sum(w[f"w{wi}_losses"])), rel_tol=RTOL)
+    for k, v in tr.model.state_dict().items():
+        assert rel_err(v.cpu().numpy(), w[f"w{wi}_final_" + k]) < 2e-5, k
+    va = tr.validate(vb)
+    assert isclose(va[0], float(w[f"w{wi}_valid_after"][0]), rel_tol=2e-5)
+    te = tr.evaluate(eb)
+    port = tp.CDAEPort({k: v.detach().cpu() for k, v in tr.model.state_dict().items()}, hidden_activation=act)
+    (pm, ppred) = port._rank(eb, "test_mask")
+    same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ppred[r]) for r in range(nU))
+    assert same >= nU - max(2, nU // 20)
+    assert np.allclose(te, pm, rtol=0.08, atol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,act", [(512, "sigmoid"), (1024, "identity")])
+def test_widest_hidden_sizes_vs_port(h, act):
+    """hidden_size 512 / 1,024 (16 / 32 floats per lane; the user tile of the evaluation spills to HBM at 1,056 columns)."""
+    g, nU, nI, B, tb, vb, eb, keeps, _ = _fixture()
+    gen = torch.Generator().manual_seed(h)
+    r = lambda *s, a=1.0: (torch.rand(*s, generator=gen) * 2 - 1) * a
+    init = {"hidden_layer.weight": r(h, nI, a=(6.0 / (h + nI)) ** 0.5), "hidden_layer.bias": torch.rand(h, generator=gen),
+            "user_nodes.weight": torch.rand(nU, h, generator=gen) * 0.1, "output_layer.weight": r(nI, h, a=(6.0 / (h + nI)) ** 0.5),
+            "output_layer.bias": torch.rand(nI, generator=gen)}
+    tr = _width_trainer(nU, nI, init, h, act, "adam", 1e-3)
+    port = tp.CDAEPort(init, "adam", 1e-3, hidden_activation=act)
+    total = tr.train(tb, keeps=keeps)
+    ptotal, psteps = port.train(tb, keeps)
+    assert rel_err(tr.last_step_losses.cpu().numpy(), psteps) < RTOL
+    for k, v in tr.model.state_dict().items():       # Adam: norm-wise 1e-5, rare eps-amplified elements bounded (util.assert_adam_close)
+        assert_adam_close(v.cpu().numpy(), port.state_dict()[k].detach().numpy(), k, touched=v.numel() * 3)
+    va, pv = tr.validate(vb), port.validate(vb)
+    assert isclose(va[0], pv[0], rel_tol=2e-5)
+    te = tr.evaluate(eb)
+    (pm, ppred) = tp.CDAEPort({k: v.detach().cpu() for k, v in tr.model.state_dict().items()}, hidden_activation=act)._rank(eb, "test_mask")
+    same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ppred[r]) for r in range(nU))
+    assert same >= nU - max(2, nU // 20)

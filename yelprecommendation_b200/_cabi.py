@@ -27,7 +27,8 @@ SYMBOLS = (
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode", "yr_ngcf_set_top_rows_mode",
-    "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_output", "yr_cdae_step", "yr_nsbce_loss",
+    "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex",
+    "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
     "yr_sample_negatives", "yr_laplacian_ws_bytes", "yr_laplacian_build",
 )
@@ -151,10 +152,14 @@ def load() -> C.CDLL:
                                            p, p, p, p, p, sz, p, p]),
         "yr_cdae_ws_bytes": (sz, [i64, i64]),
         "yr_cdae_hidden": (C.c_int, [C.POINTER(YrCdaeTensors), i64, i64, i32, p, p, p, i64, p, i64, p, sz, p, p]),
+        "yr_cdae_hidden_ex": (C.c_int, [C.POINTER(YrCdaeTensors), i64, i64, i32, i32, p, p, p, i64, p, i64, p, sz, p, p]),
         "yr_cdae_output": (C.c_int, [C.POINTER(YrCdaeTensors), i64, i32, p, i64, i64, p, p]),
         "yr_cdae_step": (C.c_int, [C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors),
                                    C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, p, p, p, p, p, i64, p, p,
                                    p, sz, p, p]),
+        "yr_cdae_step_ex": (C.c_int, [C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors),
+                                      C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, i32, p, p, p, p, p, i64, p,
+                                      p, p, sz, p, p]),
         "yr_nsbce_loss": (C.c_int, [p, p, p, i64, p, p, sz, p]),
         "yr_laplacian_ws_bytes": (sz, [i64, i64, i64]),
         "yr_laplacian_build": (C.c_int, [p, p, p, i64, i64, i64, p, p, p, p, sz, p, p]),

@@ -12,6 +12,7 @@
 namespace yr {
 
 constexpr int kCdaeThreads = 256;
+constexpr int kCdaeMaxH = 1024;
 constexpr int kCompactThreads = 1024;   // 32 warps per row: the compaction is a latency chain, parallelism is what it needs
 
 struct CdaeWs {
@@ -31,7 +32,7 @@ static size_t cdae_ws_layout(int64_t B, int64_t nI, void* base, CdaeWs* w) {
   const size_t o_xc = take((size_t)B * 4), o_tc = take((size_t)B * 4), o_tot = take(16);
   const size_t o_xi = take((size_t)B * nI * 4), o_xv = take((size_t)B * nI * 4);
   const size_t o_ti = take((size_t)B * nI * 4), o_tv = take((size_t)B * nI * 4);
-  const size_t o_z = take((size_t)B * 256 * 4);
+  const size_t o_z = take((size_t)B * kCdaeMaxH * 4);
   if (w && base) {
     unsigned char* p = (unsigned char*)base;
     w->xin_cnt = (int32_t*)(p + o_xc); w->tgt_cnt = (int32_t*)(p + o_tc); w->total = (int32_t*)(p + o_tot);
@@ -125,19 +126,22 @@ cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep,
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// Block per batch row. H = hidden size (64). Phase 1: hidden activation from the compacted inputs.
+// Block per batch row. H = 32 * VPL = hidden size (32 ... 1,024: the values of the reference's cdae_sweep_config.yaml).
+// Phase 1: hidden activation (act: 0 sigmoid, 1 identity — models/base_model.py:10-14) from the compacted inputs.
 // Phase 2 (targets given): logits at the loss positions, BCE terms, and — if GRAD — every gradient.
-template <int H, bool GRAD>
+template <int VPL, bool GRAD>
 __global__ void __launch_bounds__(kCdaeThreads)
 cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, const int64_t* __restrict__ uid,
-                CdaeWs w, bool with_loss, float* __restrict__ z_out, int64_t ldz, double* loss_acc, int32_t* err) {
-  static_assert(H == 64, "row kernel is laid out for hidden_size 64");
+                CdaeWs w, bool with_loss, float* __restrict__ z_out, int64_t ldz, double* loss_acc, int32_t* err, int act) {
+  constexpr int H = VPL * 32;
   constexpr int NW = kCdaeThreads / 32;
+  constexpr int G = H >= kCdaeThreads ? 1 : kCdaeThreads / H;      // partial sums per hidden unit (4 at H = 64)
+  constexpr int KS = H >= kCdaeThreads ? kCdaeThreads : H;         // hidden units covered per pass of the CTA
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ float part[kCdaeThreads / H][H];   // 4 partial sums per hidden unit
-  __shared__ float z_s[H];
-  __shared__ float dz_s[NW][H];
+  __shared__ float part[G][H];
+  __shared__ __align__(16) float z_s[H];
+  __shared__ __align__(16) float dz_s[NW][H];
   __shared__ double loss_s[NW];
   int64_t u = uid[b];
   if (u < 0 || u >= nU) { if (tid == 0 && err) atomicExch(err, 1); u = 0; }
@@ -145,39 +149,51 @@ cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, c
   const int32_t* xi = w.xin_idx + (int64_t)b * nI;
   const float* xv = w.xin_val + (int64_t)b * nI;
 
-  // ---- hidden: z = sigmoid(bh + Vu[u] + sum_j xv_j * Wh[:, xi_j]) ; thread = (group g of 4, unit k of 64)
+  // ---- hidden: z = act(bh + Vu[u] + sum_j xv_j * Wh[:, xi_j]) ; thread = (group g of G, unit k)
   {
-    const int k = tid % H, g = tid / H;
-    float acc = 0.f;
-    for (int j = g; j < nx; j += kCdaeThreads / H) acc = fmaf(xv[j], __ldg(P.Wh + (int64_t)k * nI + xi[j]), acc);
-    part[g][k] = acc;
+    const int g = tid / KS;
+    for (int k = tid % KS; k < H; k += KS) {
+      float acc = 0.f;
+      for (int j = g; j < nx; j += G) acc = fmaf(xv[j], __ldg(P.Wh + (int64_t)k * nI + xi[j]), acc);
+      part[g][k] = acc;
+    }
   }
   __syncthreads();
-  if (tid < H) {
-    float pre = P.bh[tid] + P.Vu[u * H + tid];
-    pre += (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
-    const float z = sigmoidf_(pre);
-    z_s[tid] = z;
-    w.z[(int64_t)b * H + tid] = z;
-    if (z_out) z_out[(int64_t)b * ldz + tid] = z;
+  for (int k = tid; k < H; k += kCdaeThreads) {
+    float pre = P.bh[k] + P.Vu[u * H + k];
+    if constexpr (G == 4) {
+      pre += (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
+    } else {
+      float t = part[0][k];
+#pragma unroll
+      for (int g = 1; g < G; ++g) t += part[g][k];
+      pre += t;
+    }
+    const float z = act ? pre : sigmoidf_(pre);
+    z_s[k] = z;
+    w.z[(int64_t)b * H + k] = z;
+    if (z_out) z_out[(int64_t)b * ldz + k] = z;
   }
-  if (z_out && tid >= H && tid < ldz) z_out[(int64_t)b * ldz + tid] = (tid == H) ? 1.f : 0.f;
+  if (z_out)
+    for (int k = H + tid; k < ldz; k += kCdaeThreads) z_out[(int64_t)b * ldz + k] = (k == H) ? 1.f : 0.f;
   __syncthreads();
   if (!with_loss) return;
 
-  // ---- loss positions: warp per position, lanes hold 2 hidden units each ----
+  // ---- loss positions: warp per position, lanes hold VPL hidden units each (Row<VPL> slices) ----
   const int nt = w.tgt_cnt[b];
   const int32_t* ti = w.tgt_idx + (int64_t)b * nI;
   const float* tv = w.tgt_val + (int64_t)b * nI;
   const float inv_m = 1.f / (float)(*w.total);
-  const float2 zz = make_float2(z_s[2 * lane], z_s[2 * lane + 1]);
-  float2 dz = make_float2(0.f, 0.f);
+  const Row<VPL> zz = ld_row<VPL>(z_s, lane);
+  Row<VPL> dz;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) dz.x[i] = 0.f;
   double lsum = 0.0;
-  constexpr int UN = 4;                        // 4 positions per warp round: ids, then the 4 Wo rows, are in flight together
+  constexpr int UN = VPL <= 2 ? 4 : (VPL <= 8 ? 2 : 1);   // positions per warp round: their ids, then their Wo rows, are in flight together
   for (int j0 = warp * UN; j0 < nt; j0 += NW * UN) {
     int item[UN];
     float t[UN], bo[UN];
-    float2 wo[UN];
+    Row<VPL> wo[UN];
 #pragma unroll
     for (int q = 0; q < UN; ++q) {
       const bool in = j0 + q < nt;
@@ -187,27 +203,29 @@ cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, c
 #pragma unroll
     for (int q = 0; q < UN; ++q) {
       const int it = item[q] < 0 ? 0 : item[q];
-      wo[q] = __ldg(reinterpret_cast<const float2*>(P.Wo + (int64_t)it * H) + lane);
+      wo[q] = ld_row<VPL>(P.Wo + (int64_t)it * H, lane);
       bo[q] = __ldg(P.bo + it);
     }
 #pragma unroll
     for (int q = 0; q < UN; ++q) {
       if (item[q] < 0) continue;                                 // warp-uniform
-      const float logit = warp_sum(fmaf(zz.x, wo[q].x, zz.y * wo[q].y)) + bo[q];
+      const float logit = warp_sum(dot_partial<VPL>(zz, wo[q])) + bo[q];
       const float p = sigmoidf_(logit);
       // torch.nn.functional.binary_cross_entropy clamps both logs at -100
       const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
       lsum += (double)(-(t[q] * lp + (1.f - t[q]) * lq));
       if (GRAD) {
         const float dl = (p - t[q]) * inv_m;                     // d loss / d logit (mean over all loss positions)
-        dz.x = fmaf(dl, wo[q].x, dz.x); dz.y = fmaf(dl, wo[q].y, dz.y);
-        atomicAdd(reinterpret_cast<float2*>(Gr.Wo + (int64_t)item[q] * H) + lane, make_float2(dl * zz.x, dl * zz.y));
+        Row<VPL> gw;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) { dz.x[i] = fmaf(dl, wo[q].x[i], dz.x[i]); gw.x[i] = dl * zz.x[i]; }
+        red_row<VPL>(Gr.Wo + (int64_t)item[q] * H, lane, gw);
         if (lane == 0) atomicAdd(Gr.bo + item[q], dl);
       }
     }
   }
   if (lane == 0) loss_s[warp] = lsum;
-  if (GRAD) { dz_s[warp][2 * lane] = dz.x; dz_s[warp][2 * lane + 1] = dz.y; }
+  if (GRAD) st_row<VPL>(dz_s[warp], lane, dz);
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
@@ -215,22 +233,43 @@ cdae_row_kernel(yr_cdae_tensors P, yr_cdae_tensors Gr, int64_t nU, int64_t nI, c
     if (t != 0.0) atomicAdd(loss_acc, t);
   }
   if (!GRAD) return;
-  if (tid < H) {
+  for (int k = tid; k < H; k += kCdaeThreads) {
     float d = 0.f;
 #pragma unroll
-    for (int q = 0; q < NW; ++q) d += dz_s[q][tid];
-    const float z = z_s[tid];
-    const float dpre = d * z * (1.f - z);
-    z_s[tid] = dpre;                                            // reuse: z_s now holds d loss / d pre-activation
-    atomicAdd(Gr.bh + tid, dpre);
-    atomicAdd(Gr.Vu + u * H + tid, dpre);
+    for (int q = 0; q < NW; ++q) d += dz_s[q][k];
+    const float z = z_s[k];
+    const float dpre = act ? d : d * z * (1.f - z);
+    z_s[k] = dpre;                                              // reuse: z_s now holds d loss / d pre-activation
+    atomicAdd(Gr.bh + k, dpre);
+    atomicAdd(Gr.Vu + u * H + k, dpre);
   }
   __syncthreads();
   {
-    const int k = tid % H, g = tid / H;
-    const float dpre = z_s[k];
-    for (int j = g; j < nx; j += kCdaeThreads / H) atomicAdd(Gr.Wh + (int64_t)k * nI + xi[j], dpre * xv[j]);
+    const int g = tid / KS;
+    for (int k = tid % KS; k < H; k += KS) {
+      const float dpre = z_s[k];
+      for (int j = g; j < nx; j += G) atomicAdd(Gr.Wh + (int64_t)k * nI + xi[j], dpre * xv[j]);
+    }
   }
+}
+
+template <bool GRAD>
+static int launch_cdae_row(int h, int64_t B, cudaStream_t s, const yr_cdae_tensors& P, const yr_cdae_tensors& Gr, int64_t nU,
+                           int64_t nI, const int64_t* uid, const CdaeWs& w, bool with_loss, float* z_out, int64_t ldz,
+                           double* loss_acc, int32_t* err, int act) {
+#define YR_CDAE_ROW(V) cdae_row_kernel<V, GRAD><<<(unsigned)B, kCdaeThreads, 0, s>>>(P, Gr, nU, nI, uid, w, with_loss, z_out, ldz, loss_acc, err, act)
+  switch (dim_vpl(h)) {
+    case 1: YR_CDAE_ROW(1); break;
+    case 2: YR_CDAE_ROW(2); break;
+    case 4: YR_CDAE_ROW(4); break;
+    case 8: YR_CDAE_ROW(8); break;
+    case 16: YR_CDAE_ROW(16); break;
+    case 32: YR_CDAE_ROW(32); break;
+    default: return YR_ERR_BAD_DIM;
+  }
+#undef YR_CDAE_ROW
+  YR_CHECK_LAUNCH();
+  return YR_OK;
 }
 
 __global__ void cdae_finish_kernel(double* loss, const int32_t* total, float* step_loss) {
@@ -286,8 +325,15 @@ static int cdae_tensors_ok(const yr_cdae_tensors* t) {
 extern "C" int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, const int64_t* uid,
                               const float* x, const float* keep, int64_t B, float* z_out, int64_t ldz, void* ws,
                               size_t ws_bytes, int32_t* err, yr_stream stream) {
-  if (cdae_tensors_ok(P) || !uid || !x || !z_out || !ws || B <= 0 || nI <= 0 || ldz < h || ldz > 256) return YR_ERR_BAD_ARG;
-  if (h != 64) return YR_ERR_BAD_DIM;
+  return yr_cdae_hidden_ex(P, nU, nI, h, YR_ACT_SIGMOID, uid, x, keep, B, z_out, ldz, ws, ws_bytes, err, stream);
+}
+
+extern "C" int yr_cdae_hidden_ex(const yr_cdae_tensors* P, int64_t nU, int64_t nI, int h, int hidden_act,
+                                 const int64_t* uid, const float* x, const float* keep, int64_t B, float* z_out,
+                                 int64_t ldz, void* ws, size_t ws_bytes, int32_t* err, yr_stream stream) {
+  if (cdae_tensors_ok(P) || !uid || !x || !z_out || !ws || B <= 0 || nI <= 0 || ldz < h) return YR_ERR_BAD_ARG;
+  if (hidden_act != YR_ACT_SIGMOID && hidden_act != YR_ACT_IDENTITY) return YR_ERR_BAD_ARG;
+  if (!dim_vpl(h)) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_cdae_ws_bytes(B, nI)) return YR_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   CdaeWs w;
@@ -296,9 +342,7 @@ extern "C" int yr_cdae_hidden(const yr_cdae_tensors* P, int64_t nU, int64_t nI, 
   cdae_compact_kernel<<<(unsigned)B, kCompactThreads, 0, s>>>(x, keep, nullptr, nullptr, nI, w);
   YR_CHECK_LAUNCH();
   yr_cdae_tensors none = {};
-  cdae_row_kernel<64, false><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, none, nU, nI, uid, w, false, z_out, ldz, nullptr, err);
-  YR_CHECK_LAUNCH();
-  return YR_OK;
+  return launch_cdae_row<false>(h, B, s, *P, none, nU, nI, uid, w, false, z_out, ldz, nullptr, err, hidden_act);
 }
 
 extern "C" int yr_cdae_output(const yr_cdae_tensors* P, int64_t nI, int h, const float* z, int64_t ldz, int64_t B,
@@ -315,8 +359,18 @@ extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* gra
                             const int64_t* uid, const float* x, const float* keep, const float* target,
                             const float* negative_mask, int64_t B, double* loss, float* step_loss, void* ws,
                             size_t ws_bytes, int32_t* err, yr_stream stream) {
+  return yr_cdae_step_ex(P, grads, m, v, opt, nU, nI, h, YR_ACT_SIGMOID, uid, x, keep, target, negative_mask, B, loss,
+                         step_loss, ws, ws_bytes, err, stream);
+}
+
+extern "C" int yr_cdae_step_ex(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                               const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                               const int64_t* uid, const float* x, const float* keep, const float* target,
+                               const float* negative_mask, int64_t B, double* loss, float* step_loss, void* ws,
+                               size_t ws_bytes, int32_t* err, yr_stream stream) {
   if (cdae_tensors_ok(P) || !uid || !x || !target || !loss || !ws || B <= 0 || nI <= 0) return YR_ERR_BAD_ARG;
-  if (h != 64) return YR_ERR_BAD_DIM;
+  if (hidden_act != YR_ACT_SIGMOID && hidden_act != YR_ACT_IDENTITY) return YR_ERR_BAD_ARG;
+  if (!dim_vpl(h)) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_cdae_ws_bytes(B, nI)) return YR_ERR_WORKSPACE;
   const bool train = opt != nullptr;
   if (train) {
@@ -331,11 +385,9 @@ extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* gra
   cdae_compact_kernel<<<(unsigned)B, kCompactThreads, 0, s>>>(x, keep, target, negative_mask, nI, w);
   YR_CHECK_LAUNCH();
   yr_cdae_tensors none = {};
-  if (train)
-    cdae_row_kernel<64, true><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, *grads, nU, nI, uid, w, true, nullptr, 0, loss + 1, err);
-  else
-    cdae_row_kernel<64, false><<<(unsigned)B, kCdaeThreads, 0, s>>>(*P, none, nU, nI, uid, w, true, nullptr, 0, loss + 1, err);
-  YR_CHECK_LAUNCH();
+  int rrc = train ? launch_cdae_row<true>(h, B, s, *P, *grads, nU, nI, uid, w, true, nullptr, 0, loss + 1, err, hidden_act)
+                  : launch_cdae_row<false>(h, B, s, *P, none, nU, nI, uid, w, true, nullptr, 0, loss + 1, err, hidden_act);
+  if (rrc) return rrc;
   cdae_finish_kernel<<<1, 1, 0, s>>>(loss, w.total, step_loss);
   YR_CHECK_LAUNCH();
   if (!train) return YR_OK;

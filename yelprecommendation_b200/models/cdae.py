@@ -32,8 +32,15 @@ class CDAE(BaseModel):
         self.hidden_layer = nn.Linear(self.num_items, self.hidden_size, bias=True, dtype=torch.float32)
         self.user_nodes = nn.Embedding(self.num_users, self.hidden_size, dtype=torch.float32)
         self.output_layer = nn.Linear(self.hidden_size, self.num_items, bias=True, dtype=torch.float32)
-        if cfg.hidden_activation != "sigmoid" or cfg.output_activation != "sigmoid":
-            raise _cabi.YelprecError("the B200 CDAE kernels implement the reference's default sigmoid activations")
+        if cfg.hidden_activation not in ("sigmoid", "identity"):
+            raise _cabi.YelprecError(f"hidden_activation {cfg.hidden_activation!r}: the reference knows 'sigmoid' and 'identity'")
+        if cfg.output_activation != "sigmoid":
+            # NSBCELoss is a BCE on the output (loss.py:12-16): torch rejects anything that is not a probability
+            raise _cabi.YelprecError("the B200 CDAE kernels keep the reference's sigmoid output activation")
+        if cfg.hidden_size not in (32, 64, 128, 256, 512, 1024):
+            raise _cabi.YelprecError(f"hidden_size {cfg.hidden_size}: the CDAE kernels take 32, 64, 128, 256, 512, 1024 "
+                                     "(the values of the reference's cdae_sweep_config.yaml)")
+        self.hidden_act = 0 if cfg.hidden_activation == "sigmoid" else 1          # enum yr_activation
         self.hidden_activation = self._activation_module(cfg.hidden_activation)
         self.output_activation = self._activation_module(cfg.output_activation)
         self._init_weights()
@@ -80,10 +87,10 @@ class CDAE(BaseModel):
         err = torch.zeros(1, device=dev, dtype=I32)
         ws = self.workspace(B)
         st = self.tensors()
-        _cabi.check(lib.yr_cdae_hidden(C.byref(st), self.num_users, self.num_items, self.hidden_size,
+        _cabi.check(lib.yr_cdae_hidden_ex(C.byref(st), self.num_users, self.num_items, self.hidden_size, self.hidden_act,
                                        _cabi.dptr(user_id), _cabi.dptr(x), _cabi.dptr(keep) if keep is not None else None,
                                        B, _cabi.dptr(z), ldz, _cabi.dptr(ws), ws.numel(), _cabi.dptr(err),
-                                       _cabi.stream_ptr(dev)), "yr_cdae_hidden")
+                                       _cabi.stream_ptr(dev)), "yr_cdae_hidden_ex")
         if int(err.item()):
             raise IndexError("CDAE.forward: index out of range in self")
         return z

@@ -22,7 +22,9 @@ from ..models.cdae import CDAE
 from .base_trainer import BaseTrainer, FusedOptimizer, logger
 
 I32, I64, F32, F64 = torch.int32, torch.int64, torch.float32, torch.float64
-_LDZ = 96     # [z (64) | 1 | 0...]: logits = [z|1].[Wo|bo]^T with a width the tensor-core eval kernel accepts (d % 32 == 0)
+def _ldz(h: int) -> int:
+    """Width of [z (h) | 1 | 0...]: logits = [z|1].[Wo|bo]^T, padded to what the evaluation kernels like (d % 32 == 0)."""
+    return (h + 1 + 31) // 32 * 32
 
 
 class CDAETrainer(BaseTrainer):
@@ -72,14 +74,15 @@ class CDAETrainer(BaseTrainer):
         ws = m.workspace(B)
         P = m.tensors()
         opt = self.optimizer.opt_struct(self.optimizer.step_count + 1) if train else None
-        _cabi.check(lib.yr_cdae_step(C.byref(P), C.byref(g) if train else None,
+        _cabi.check(lib.yr_cdae_step_ex(C.byref(P), C.byref(g) if train else None,
                                      C.byref(mo) if (train and mo is not None) else None,
                                      C.byref(vo) if (train and vo is not None) else None,
                                      C.byref(opt) if train else None, self.num_users, self.num_items, m.hidden_size,
+                                     m.hidden_act,
                                      _cabi.dptr(user_id), _cabi.dptr(x), _cabi.dptr(keep) if keep is not None else None,
                                      _cabi.dptr(target), _cabi.dptr(negative_mask), B, _cabi.dptr(b["loss"]),
                                      _cabi.dptr(step_loss) if step_loss is not None else None, _cabi.dptr(ws), ws.numel(),
-                                     _cabi.dptr(b["err"]), _cabi.stream_ptr(dev)), "yr_cdae_step")
+                                     _cabi.dptr(b["err"]), _cabi.stream_ptr(dev)), "yr_cdae_step_ex")
         if train:
             self.optimizer.step_count += 1
 
@@ -116,13 +119,13 @@ class CDAETrainer(BaseTrainer):
         zs, mask_rows, act_rows = [], [], []
         for data in batches:
             x = data["input_mask"]
-            zs.append(m.hidden(data["user_id"], x, None, ldz=_LDZ))
+            zs.append(m.hidden(data["user_id"], x, None, ldz=_ldz(m.hidden_size)))
             xn, an = x.cpu().numpy(), data[actual_key].cpu().numpy()
             mask_rows.extend(np.nonzero(r)[0] for r in xn)
             act_rows.extend(np.nonzero(r)[0] for r in an)
         Z = torch.cat(zs)
         n = Z.shape[0]
-        V = torch.zeros(self.num_items, _LDZ, device=self.device, dtype=F32)
+        V = torch.zeros(self.num_items, _ldz(m.hidden_size), device=self.device, dtype=F32)
         V[:, : m.hidden_size] = m.output_layer.weight.data
         V[:, m.hidden_size] = m.output_layer.bias.data
         cat = lambda rows: np.concatenate(rows).astype(np.int32) if n else np.zeros(0, np.int32)
