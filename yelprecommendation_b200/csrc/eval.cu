@@ -90,7 +90,7 @@ gather_transpose_users_kernel(const float* __restrict__ Uemb, int64_t nU, int d,
 
 // acc[i][j] += sum_k us[k][user_i] * vs[k][item_j] over one k-chunk, k ascending
 template <bool kGlobalU>
-__device__ __forceinline__ void eval_chunk_fma(float (&acc)[8][8], const float* __restrict__ us, int64_t ustride,
+__device__ __forceinline__ void eval_chunk_fma(float2 (&acc)[8][4], const float* __restrict__ us, int64_t ustride,
                                                const float* __restrict__ vs, int tu, int ti) {
 #pragma unroll 4
   for (int k = 0; k < kKC; ++k) {
@@ -105,11 +105,12 @@ __device__ __forceinline__ void eval_chunk_fma(float (&acc)[8][8], const float* 
     const float4 b0 = *reinterpret_cast<const float4*>(vs + k * kTI + ti * 4);
     const float4 b1 = *reinterpret_cast<const float4*>(vs + k * kTI + 64 + ti * 4);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    // packed FFMA2: each component is exactly fmaf(av[i], b, acc) — the canonical chain, two scores per instruction
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), bv[j], acc[i][j]);
   }
 }
 
@@ -223,11 +224,11 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
         }
       }
       // ---- scores: acc[i][j] = sum_k Us[k][user_i] * Vs[k][item_j], k ascending ----
-      float acc[8][8];
+      float2 acc[8][4];                  // [user][item pair]: score (i, j) = acc[i][j >> 1].x / .y
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
       for (int ch = 0; ch < n_chunks; ++ch, ++q) {
         const int st = (int)(q % kStages);
         mbar_wait(bars + st, (uint32_t)((q / kStages) & 1));
@@ -261,7 +262,7 @@ eval_topk_kernel(const float* __restrict__ Uemb, int64_t nU, const float* __rest
       auto try_push = [&](int i, int j) {
         const int ul = (i < 4) ? tu * 4 + i : 64 + tu * 4 + (i - 4);
         const int item = i0 + ((j < 4) ? ti * 4 + j : 64 + ti * 4 + (j - 4));
-        float s = acc[i][j];
+        float s = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
         if (s >= thr[ul] && item < nI && e0 + ul < n_eval) {
           if (masked(ul, item)) s = kMaskValue;
           if (s >= thr[ul]) {

@@ -15,6 +15,11 @@ namespace yr {
 // 256 threads, tile = TM rows x D cols, thread = 4 rows x 4 cols, k runs 0..2D-1 as one fma chain
 // (first the W1 term, then the W2 term — the order the oracle restates).
 // ---------------------------------------------------------------------------------------------
+// Packed FP32 FMA (FFMA2, sm_100): two IEEE fmas per lane per instruction — each component is exactly fmaf(), so results
+// are bit-identical to the scalar chain while the FMA pipe does twice the work per issue slot (a 3-register FFMA issues
+// every other cycle per scheduler on Blackwell).
+__device__ __forceinline__ void fma2(float2& acc, float a, const float2 b) { acc = __ffma2_rn(make_float2(a, a), b, acc); }
+
 template <int D>
 struct DenseCfg {
   static constexpr int kThreads = 256;
@@ -63,31 +68,31 @@ ngcf_dense_fwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       As[(D + k + 2) * TM + r] = e.z * le.z; As[(D + k + 3) * TM + r] = e.w * le.w;
     }
     __syncthreads();
-    float acc[4][4];
+    float2 acc[4][2];                    // [row][column pair]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 8
     for (int k = 0; k < 2 * D; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(As + k * TM + ty * 4);
       const float4 w = *reinterpret_cast<const float4*>(Ws + k * D + tx * 4);
       const float av[4] = {a.x, a.y, a.z, a.w};
-      const float wv[4] = {w.x, w.y, w.z, w.w};
+      const float2 wv[2] = {make_float2(w.x, w.y), make_float2(w.z, w.w)};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) fma2(acc[i][j], av[i], wv[j]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t r = r0 + ty * 4 + i;
       if (r < n) {
         float4 o;
-        o.x = acc[i][0] > 0.f ? acc[i][0] : acc[i][0] * slope;
-        o.y = acc[i][1] > 0.f ? acc[i][1] : acc[i][1] * slope;
-        o.z = acc[i][2] > 0.f ? acc[i][2] : acc[i][2] * slope;
-        o.w = acc[i][3] > 0.f ? acc[i][3] : acc[i][3] * slope;
+        o.x = acc[i][0].x > 0.f ? acc[i][0].x : acc[i][0].x * slope;
+        o.y = acc[i][0].y > 0.f ? acc[i][0].y : acc[i][0].y * slope;
+        o.z = acc[i][1].x > 0.f ? acc[i][1].x : acc[i][1].x * slope;
+        o.w = acc[i][1].y > 0.f ? acc[i][1].y : acc[i][1].y * slope;
         reinterpret_cast<float4*>(Eout + r * D)[tx] = o;
       }
     }
@@ -128,25 +133,38 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
     reinterpret_cast<float4*>(W1s)[idx] = __ldg(reinterpret_cast<const float4*>(W1) + idx);
     reinterpret_cast<float4*>(W2s)[idx] = __ldg(reinterpret_cast<const float4*>(W2) + idx);
   }
-  float dw1[RO][4], dw2[RO][4];
+  float2 dw1[RO][2], dw2[RO][2];         // [o][column pair]
 #pragma unroll
   for (int i = 0; i < RO; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { dw1[i][j] = 0.f; dw2[i][j] = 0.f; }
+    for (int j = 0; j < 2; ++j) { dw1[i][j] = make_float2(0.f, 0.f); dw2[i][j] = make_float2(0.f, 0.f); }
 
   const int64_t n_tiles = (n + TM - 1) / TM;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = tile * TM;
     __syncthreads();
-    for (int idx = tid; idx < TM * (D / 4); idx += C::kThreads) {
+    // all global loads of the tile first (16 independent float4 per thread in flight), then the transforms
+    constexpr int kLd = TM * (D / 4) / C::kThreads;
+    float4 e4[kLd], le4[kLd], en4[kLd], g4[kLd];
+#pragma unroll
+    for (int q = 0; q < kLd; ++q) {
+      const int idx = tid + q * C::kThreads;
       const int r = idx / (D / 4), c4 = idx % (D / 4);
+      const bool ok = r0 + r < n;
+      const int64_t rr = ok ? r0 + r : r0;                                   // r0 < n: a valid row to read instead
+      const int64_t off = (row_list ? (int64_t)__ldg(row_list + rr) : rr) * D;
+      e4[q] = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
+      le4[q] = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
+      en4[q] = __ldg(reinterpret_cast<const float4*>(Enext + off) + c4);
+      g4[q] = __ldg(reinterpret_cast<const float4*>(Gnext + off) + c4);
+    }
+#pragma unroll
+    for (int q = 0; q < kLd; ++q) {
+      const int idx = tid + q * C::kThreads;
+      const int r = idx / (D / 4);
       float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), pv = sv, dz = sv;
       if (r0 + r < n) {
-        const int64_t off = (row_list ? (int64_t)row_list[r0 + r] : (r0 + r)) * D;
-        const float4 e = __ldg(reinterpret_cast<const float4*>(E + off) + c4);
-        const float4 le = __ldg(reinterpret_cast<const float4*>(LE + off) + c4);
-        const float4 en = __ldg(reinterpret_cast<const float4*>(Enext + off) + c4);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(Gnext + off) + c4);
+        const float4 e = e4[q], le = le4[q], en = en4[q], g = g4[q];
         dz.x = en.x > 0.f ? g.x : g.x * slope; dz.y = en.y > 0.f ? g.y : g.y * slope;
         dz.z = en.z > 0.f ? g.z : g.z * slope; dz.w = en.w > 0.f ? g.w : g.w * slope;
         sv = make_float4(le.x + e.x, le.y + e.y, le.z + e.z, le.w + e.w);
@@ -159,11 +177,11 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
     __syncthreads();
 
     // ---- dS, dP: rows ty*4.., cols tx*4.. ; k = o, four k per shared-memory round ----
-    float ds[4][4], dp[4][4];
+    float2 ds[4][2], dp[4][2];          // [row][column pair]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { ds[i][j] = 0.f; dp[i][j] = 0.f; }
+      for (int j = 0; j < 2; ++j) { ds[i][j] = make_float2(0.f, 0.f); dp[i][j] = make_float2(0.f, 0.f); }
 #pragma unroll 2
     for (int o = 0; o < D; o += 4) {
       float av[4][4];
@@ -176,36 +194,50 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       for (int k = 0; k < 4; ++k) {
         const float4 w1 = *reinterpret_cast<const float4*>(W1s + (o + k) * D + tx * 4);
         const float4 w2 = *reinterpret_cast<const float4*>(W2s + (o + k) * D + tx * 4);
-        const float w1v[4] = {w1.x, w1.y, w1.z, w1.w};
-        const float w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+        const float2 w1v[2] = {make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+        const float2 w2v[2] = {make_float2(w2.x, w2.y), make_float2(w2.z, w2.w)};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ds[i][j] = fmaf(av[i][k], w1v[j], ds[i][j]);
-            dp[i][j] = fmaf(av[i][k], w2v[j], dp[i][j]);
+          for (int j = 0; j < 2; ++j) {
+            fma2(ds[i][j], av[i][k], w1v[j]);
+            fma2(dp[i][j], av[i][k], w2v[j]);
           }
       }
     }
+    // epilogue two rows at a time: their E / LE / G loads (L1 / L2 hits: this CTA has just read the tile) are issued
+    // together, then T is stored and G updated — shared memory holds S and P instead of E and LE
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rl = ty * 4 + i;
-      int64_t r = r0 + rl;
-      if (r < n) {
-        if (row_list) r = row_list[r];
-        // E / LE again (L1/L2 hits: this CTA has just read the tile) — shared memory holds S and P instead
-        const float4 e = __ldg(reinterpret_cast<const float4*>(E + r * D) + tx);
-        const float4 le = __ldg(reinterpret_cast<const float4*>(LE + r * D) + tx);
+    for (int i0 = 0; i0 < 4; i0 += 2) {
+      float4 e[2], le[2], g[2];
+      int64_t rg[2];
+      bool ok[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t r = r0 + ty * 4 + i0 + h;
+        ok[h] = r < n;
+        const int64_t rr = ok[h] ? r : r0;
+        rg[h] = row_list ? (int64_t)__ldg(row_list + rr) : rr;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        e[h] = __ldg(reinterpret_cast<const float4*>(E + rg[h] * D) + tx);
+        le[h] = __ldg(reinterpret_cast<const float4*>(LE + rg[h] * D) + tx);
+        g[h] = *(reinterpret_cast<const float4*>(G + rg[h] * D) + tx);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!ok[h]) continue;
+        const int i = i0 + h;
         float4 t, dd;
-        t.x = fmaf(dp[i][0], e.x, ds[i][0]); t.y = fmaf(dp[i][1], e.y, ds[i][1]);
-        t.z = fmaf(dp[i][2], e.z, ds[i][2]); t.w = fmaf(dp[i][3], e.w, ds[i][3]);
-        dd.x = fmaf(dp[i][0], le.x, ds[i][0]); dd.y = fmaf(dp[i][1], le.y, ds[i][1]);
-        dd.z = fmaf(dp[i][2], le.z, ds[i][2]); dd.w = fmaf(dp[i][3], le.w, ds[i][3]);
-        reinterpret_cast<float4*>(T + r * D)[tx] = t;
-        float4* gp = reinterpret_cast<float4*>(G + r * D) + tx;
-        float4 g = *gp;
-        g.x += dd.x; g.y += dd.y; g.z += dd.z; g.w += dd.w;
-        *gp = g;
+        t.x = fmaf(dp[i][0].x, e[h].x, ds[i][0].x); t.y = fmaf(dp[i][0].y, e[h].y, ds[i][0].y);
+        t.z = fmaf(dp[i][1].x, e[h].z, ds[i][1].x); t.w = fmaf(dp[i][1].y, e[h].w, ds[i][1].y);
+        dd.x = fmaf(dp[i][0].x, le[h].x, ds[i][0].x); dd.y = fmaf(dp[i][0].y, le[h].y, ds[i][0].y);
+        dd.z = fmaf(dp[i][1].x, le[h].z, ds[i][1].x); dd.w = fmaf(dp[i][1].y, le[h].w, ds[i][1].y);
+        reinterpret_cast<float4*>(T + rg[h] * D)[tx] = t;
+        float4 gn = g[h];
+        gn.x += dd.x; gn.y += dd.y; gn.z += dd.z; gn.w += dd.w;
+        reinterpret_cast<float4*>(G + rg[h] * D)[tx] = gn;
       }
     }
 
@@ -225,14 +257,14 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
       }
       const float4 s4 = *reinterpret_cast<const float4*>(Ss + r * D + tx * 4);
       const float4 p4 = *reinterpret_cast<const float4*>(Ps + r * D + tx * 4);
-      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+      const float2 sv[2] = {make_float2(s4.x, s4.y), make_float2(s4.z, s4.w)};
+      const float2 pv[2] = {make_float2(p4.x, p4.y), make_float2(p4.z, p4.w)};
 #pragma unroll
       for (int i = 0; i < RO; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dw1[i][j] = fmaf(dzv[i], sv[j], dw1[i][j]);
-          dw2[i][j] = fmaf(dzv[i], pv[j], dw2[i][j]);
+        for (int j = 0; j < 2; ++j) {
+          fma2(dw1[i][j], dzv[i], sv[j]);
+          fma2(dw2[i][j], dzv[i], pv[j]);
         }
     }
   }
@@ -240,8 +272,8 @@ ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ LE,
 #pragma unroll
   for (int i = 0; i < RO; ++i) {
     const int o = ty * RO + i;
-    reinterpret_cast<float4*>(my + o * D)[tx] = make_float4(dw1[i][0], dw1[i][1], dw1[i][2], dw1[i][3]);
-    reinterpret_cast<float4*>(my + D * D + o * D)[tx] = make_float4(dw2[i][0], dw2[i][1], dw2[i][2], dw2[i][3]);
+    reinterpret_cast<float4*>(my + o * D)[tx] = make_float4(dw1[i][0].x, dw1[i][0].y, dw1[i][1].x, dw1[i][1].y);
+    reinterpret_cast<float4*>(my + D * D + o * D)[tx] = make_float4(dw2[i][0].x, dw2[i][0].y, dw2[i][1].x, dw2[i][1].y);
   }
 }
 
