@@ -204,6 +204,10 @@ def test_other_embedding_widths_vs_oracle(d, name, wd):
     else:
         assert_adam_close(Ug, orc.U, "U", touched=B * steps * d)
         assert_adam_close(Vg, orc.V, "V", touched=2 * B * steps * d)
+    # the kernel's invariant: gradient scratch and touched flags are all-zero again after every call (a row the sweep
+    # missed — the d = 32 grid-barrier bug, notes/README.md — would leave its gradient behind)
+    sc = tr._scratch
+    assert all(int(torch.count_nonzero(sc[k]).item()) == 0 for k in ("gU", "gV", "flagU", "flagV"))
     if wd == 0.0:
         return
     # validate + evaluate at this width (ids bit-exact against the oracle on the trainer's own tables)
