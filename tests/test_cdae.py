@@ -166,7 +166,10 @@ def test_train_validate_evaluate_other_widths_vs_reference(wi):
     assert rel_err(tr.last_step_losses.cpu().numpy(), w[f"w{wi}_losses"]) < RTOL
     assert isclose(total, float(np.sum(w[f"w{wi}_losses"])), rel_tol=RTOL)
     for k, v in tr.model.state_dict().items():
-        assert rel_err(v.cpu().numpy(), w[f"w{wi}_final_" + k]) < 2e-5, k
+        if name == "sgd":
+            assert rel_err(v.cpu().numpy(), w[f"w{wi}_final_" + k]) < 2e-5, k
+        else:       # Adam: norm-wise 1e-5 with bounded eps-amplified outliers (util.assert_adam_close)
+            assert_adam_close(v.cpu().numpy(), w[f"w{wi}_final_" + k], k, touched=v.numel() * 3)
     va = tr.validate(vb)
     assert isclose(va[0], float(w[f"w{wi}_valid_after"][0]), rel_tol=2e-5)
     te = tr.evaluate(eb)
