@@ -372,6 +372,9 @@ int yr_nsbce_loss(const float* pred, const float* target, const float* negative_
 /* Vt[k, i] = V[i, k] for i < nI; Vt is [d x ldt], ldt >= nI (padding columns are zero-filled). */
 int yr_transpose_items(const float* V, int64_t nI, int d, float* Vt, int64_t ldt, yr_stream stream);
 
+/* Workspace of yr_eval_topk_metrics: 256 bytes while the [pad32(d) x 128 users] tile fits shared memory (d up to 288 at
+ * K = 10); wider tables keep the tail of the transposed user tile here ((pad32(d) - resident rows) x round_up(n_eval, 128)
+ * floats). Any d that is a multiple of 4 is accepted. */
 size_t yr_eval_ws_bytes(int64_t n_eval, int d, int K);
 
 /* MFTrainer.evaluate / NGCFTrainer.evaluate fused: for eval row e (user eval_uid[e]) score every item
@@ -384,7 +387,7 @@ size_t yr_eval_ws_bytes(int64_t n_eval, int d, int K);
  *   topk_out [n_eval x K] int64 best first; user_metrics [n_eval x 4] double =
  *   (hits/K, hits/|set(A)| or 0, AP, NDCG) per row; metric_sums [6] double =
  *   (sum precision, sum recall, sum AP, sum NDCG, #rows with |set(A)|>0, #rows with len(A)>0).
- * The score matrix is never written to memory. */
+ * The score matrix is never written to memory. ws: yr_eval_ws_bytes(n_eval, d, K) bytes (YR_ERR_WORKSPACE if smaller). */
 int yr_eval_topk_metrics(const float* Uemb, int64_t nU, const float* Vt, int64_t ldt, int64_t nI, int d,
                          const int64_t* eval_uid, int64_t n_eval,
                          const int32_t* mask_ptr, const int32_t* mask_idx,

@@ -1,5 +1,5 @@
 // CDAE kernels (sm_100a) — BASELINE config 4: the reference's denoising auto-encoder
-//   models/cdae.py:46-52     out = sigmoid(Wo . sigmoid(Wh . dropout(x) + bh + Vu[u]) + bo)
+//   models/cdae.py:46-52     out = sigmoid(Wo . act(Wh . dropout(x) + bh + Vu[u]) + bo),  act = sigmoid | identity
 //   loss.py:7-16             NSBCELoss: BCE (mean) over the positions where target + negative_mask != 0
 //   trainers/cdae_trainer.py:36-54 (train step), :56-70 (validate loss)
 // The reference pushes dense [B x nI] tensors through two nn.Linear layers and materialises the dense output.
