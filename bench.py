@@ -578,6 +578,18 @@ def main():
                 "note": "op-by-op path (rectangular SpMM row block + yr_ngcf_dense_fwd/bwd); at this size (17.8 MB of rows, "
                         "1 ms step) the exchange is latency, the single-GPU fused step is the better choice"}
             del sn
+            # BASELINE config 5's width: d = 128 (one layer: the sharded tail kernels take d * (L + 1) <= 256), FP32-pipe transforms
+            sn = ShardedNGCFTrainer(cfg(seed=42, embed_size=128, num_orders=1), w.inter.num_items, w.inter.num_users, w.L)
+            accn.zero_()
+            for i in range(3):
+                sn.train_step(du[i * B:(i + 1) * B], dp[i * B:(i + 1) * B], dn[i * B:(i + 1) * B], accn)
+            barrier()
+            ms_sn = max_over_ranks(timed(lambda i: sn.train_step(du[(3 + i) * B:(4 + i) * B], dp[(3 + i) * B:(4 + i) * B],
+                                                                 dn[(3 + i) * B:(4 + i) * B], accn), n_sn)) / n_sn
+            extra["ngcf_sharded_d128_1layer"] = {"value": B / (ms_sn * 1e-3), "unit": UNIT, "ms_per_step": ms_sn,
+                                                 "scaling": "strong", "rows_per_gpu": sn.n_loc,
+                                                 "note": "same graph, embed_size 128 (config 5's width), num_orders 1"}
+            del sn
         except Exception as ex:
             extra["ngcf_sharded"] = {"error": repr(ex)}
 
