@@ -100,3 +100,22 @@ def test_row_sharded_mf_choreography_gloo_world2():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_SHARD_OK" in r.stdout
+
+
+def test_unsupported_widths_fail_loudly():
+    """No silent fallback: a width the kernels do not take raises at construction (INTEGRATION.md lists the widths)."""
+    from types import SimpleNamespace
+    from yelprecommendation_b200._cabi import YelprecError
+    from yelprecommendation_b200.models.cdae import CDAE
+    from yelprecommendation_b200.models.ngcf import NGCF
+    with pytest.raises(YelprecError):
+        NGCF(SimpleNamespace(embed_size=48, num_orders=2), 10, 12)
+    NGCF(SimpleNamespace(embed_size=128, num_orders=1), 10, 12)
+    base = dict(device="cuda", corruption_level=0.5, hidden_activation="sigmoid", output_activation="sigmoid")
+    with pytest.raises(YelprecError):
+        CDAE(SimpleNamespace(hidden_size=48, **base), 12, 10)
+    with pytest.raises(YelprecError):
+        CDAE(SimpleNamespace(hidden_size=64, **{**base, "hidden_activation": "relu"}), 12, 10)
+    with pytest.raises(YelprecError):
+        CDAE(SimpleNamespace(hidden_size=64, **{**base, "output_activation": "identity"}), 12, 10)
+    CDAE(SimpleNamespace(hidden_size=1024, **{**base, "hidden_activation": "identity"}), 12, 10)

@@ -21,6 +21,9 @@ _LEAKY_SLOPE = 0.01   # nn.functional.leaky_relu default, models/ngcf.py:72
 class NGCF(BaseModel):
     def __init__(self, cfg, num_users, num_items):
         super().__init__()
+        if cfg.embed_size not in (32, 64, 128):
+            from .. import _cabi
+            raise _cabi.YelprecError(f"NGCF embed_size {cfg.embed_size}: the propagation kernels take 32, 64 (tensor cores) or 128")
         self.cfg = cfg
         self.num_users = num_users
         self.num_items = num_items

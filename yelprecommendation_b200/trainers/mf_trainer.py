@@ -27,6 +27,9 @@ class MFTrainer(BaseTrainer):
         super().__init__(cfg)
         self.num_items = num_items
         self.num_users = num_users
+        if self.cfg.embed_size not in (32, 64, 128, 256, 512, 1024):
+            raise _cabi.YelprecError(f"MF embed_size {self.cfg.embed_size}: the fused trainer takes 32, 64, 128, 256, 512, 1024 "
+                                     "(the values of the reference's mf_sweep_config.yaml)")
         self.model = MatrixFactorization(self.cfg, num_users, num_items).to(self.device)
         self.optimizer: FusedOptimizer = self._optimizer(self.cfg.optimizer, self.model, self.cfg.lr,
                                                          self.cfg.weight_decay)
