@@ -48,3 +48,26 @@ def test_optimizer_name_errors_like_reference():
     with pytest.raises(NotImplementedError, match="Optimizer Not Exists"):
         FusedOptimizer("rmsprop", 1e-3)
     assert FusedOptimizer("AdamW", 1e-3, 0.1).name == "adamw"
+
+
+def test_pytorch_custom_ops_are_registered():
+    """north_star: the path drops in via PyTorch custom ops bound through the C ABI — torch.ops.yelprec.* exist with
+    tensor-only schemas, fake kernels (shape inference without a GPU) and autograd formulas."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from yelprecommendation_b200 import ops  # noqa: F401  (registers the ops)
+    want = {"mf_score": "yelprec::mf_score(Tensor U, Tensor V, Tensor uid, Tensor iid) -> Tensor",
+            "mf_score_bwd": "yelprec::mf_score_bwd(Tensor U, Tensor V, Tensor uid, Tensor iid, Tensor gout) -> (Tensor, Tensor)",
+            "bpr_loss": "yelprec::bpr_loss(Tensor pos, Tensor neg) -> Tensor",
+            "bpr_loss_bwd": "yelprec::bpr_loss_bwd(Tensor pos, Tensor neg, Tensor gloss) -> (Tensor, Tensor)",
+            "ngcf_layer": "yelprec::ngcf_layer(Tensor E, Tensor W1, Tensor W2, SymInt csr_handle, float slope) -> (Tensor, Tensor)"}
+    for name, schema in want.items():
+        assert str(getattr(torch.ops.yelprec, name).default._schema) == schema
+    with FakeTensorMode():
+        U, V = torch.empty(10, 64, device="cuda"), torch.empty(12, 64, device="cuda")
+        u = torch.empty(5, dtype=torch.int64, device="cuda")
+        assert torch.ops.yelprec.mf_score(U, V, u, u).shape == (5,)
+        assert torch.ops.yelprec.bpr_loss(torch.empty(5, device="cuda"), torch.empty(5, device="cuda")).shape == ()
+    # no CPU kernels: the product has no CPU path
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.yelprec.bpr_loss(torch.zeros(4), torch.zeros(4))

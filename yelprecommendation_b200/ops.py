@@ -11,6 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+from torch.library import custom_op
 
 from . import _cabi
 from ._cabi import YelprecError, check, dptr, stream_ptr
@@ -35,65 +36,117 @@ def _raise_if_err(err: torch.Tensor, what: str) -> None:
 # ----------------------------------------------------------------------------------------------------
 # MF score / BPR loss (autograd-capable, so an unmodified reference trainer can call loss.backward())
 # ----------------------------------------------------------------------------------------------------
-class _MFScore(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, U, V, uid, iid):
-        lib = _cabi.load()
-        Uc, Vc = U.detach().contiguous(), V.detach().contiguous()
-        out = torch.empty(uid.numel(), device=U.device, dtype=F32)
-        err = torch.zeros(1, device=U.device, dtype=I32)
-        check(lib.yr_mf_score(dptr(Uc, F32), dptr(Vc, F32), Uc.shape[0], Vc.shape[0], Uc.shape[1],
-                              dptr(uid, I64), dptr(iid, I64), uid.numel(), dptr(out), dptr(err),
-                              stream_ptr(U.device)), "yr_mf_score")
-        _raise_if_err(err, "MatrixFactorization.forward")
-        ctx.save_for_backward(Uc, Vc, uid, iid)
-        return out
+# Registered as PyTorch custom ops (torch.ops.yelprec.*): each op body is one call into the C ABI; the backward formulas
+# are custom ops as well, attached with register_autograd.
+@custom_op("yelprec::mf_score", mutates_args=(), device_types="cuda")
+def _op_mf_score(U: torch.Tensor, V: torch.Tensor, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
+    """MatrixFactorization.forward (models/mf.py:20-23) -> yr_mf_score."""
+    lib = _cabi.load()
+    Uc, Vc = U.detach().contiguous(), V.detach().contiguous()
+    uid, iid = uid.contiguous(), iid.contiguous()
+    out = torch.empty(uid.numel(), device=U.device, dtype=F32)
+    err = torch.zeros(1, device=U.device, dtype=I32)
+    check(lib.yr_mf_score(dptr(Uc, F32), dptr(Vc, F32), Uc.shape[0], Vc.shape[0], Uc.shape[1],
+                          dptr(uid, I64), dptr(iid, I64), uid.numel(), dptr(out), dptr(err),
+                          stream_ptr(U.device)), "yr_mf_score")
+    _raise_if_err(err, "MatrixFactorization.forward")
+    return out
 
-    @staticmethod
-    def backward(ctx, gout):
-        lib = _cabi.load()
-        U, V, uid, iid = ctx.saved_tensors
-        gU, gV = torch.zeros_like(U), torch.zeros_like(V)
-        gout = gout.contiguous().to(F32)
-        check(lib.yr_mf_score_bwd(dptr(U), dptr(V), U.shape[0], V.shape[0], U.shape[1], dptr(uid), dptr(iid),
-                                  uid.numel(), dptr(gout), dptr(gU), dptr(gV), stream_ptr(U.device)),
-              "yr_mf_score_bwd")
-        return gU, gV, None, None
+
+@_op_mf_score.register_fake
+def _(U, V, uid, iid):
+    return U.new_empty((uid.numel(),), dtype=F32)
+
+
+@custom_op("yelprec::mf_score_bwd", mutates_args=(), device_types="cuda")
+def _op_mf_score_bwd(U: torch.Tensor, V: torch.Tensor, uid: torch.Tensor, iid: torch.Tensor,
+                     gout: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _cabi.load()
+    U, V = U.detach().contiguous(), V.detach().contiguous()
+    uid, iid = uid.contiguous(), iid.contiguous()
+    gU, gV = torch.zeros_like(U), torch.zeros_like(V)
+    gout = gout.contiguous().to(F32)
+    check(lib.yr_mf_score_bwd(dptr(U, F32), dptr(V, F32), U.shape[0], V.shape[0], U.shape[1], dptr(uid, I64), dptr(iid, I64),
+                              uid.numel(), dptr(gout), dptr(gU), dptr(gV), stream_ptr(U.device)),
+          "yr_mf_score_bwd")
+    return gU, gV
+
+
+@_op_mf_score_bwd.register_fake
+def _(U, V, uid, iid, gout):
+    return torch.empty_like(U), torch.empty_like(V)
+
+
+def _mf_score_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _mf_score_backward(ctx, gout):
+    U, V, uid, iid = ctx.saved_tensors
+    gU, gV = _op_mf_score_bwd(U, V, uid, iid, gout)
+    return gU, gV, None, None
+
+
+_op_mf_score.register_autograd(_mf_score_backward, setup_context=_mf_score_setup)
 
 
 def mf_score(U: torch.Tensor, V: torch.Tensor, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
     uid, iid = _ids(uid, U.device), _ids(iid, U.device)
     if uid.numel() != iid.numel():
         raise RuntimeError(f"The size of tensor a ({uid.numel()}) must match the size of tensor b ({iid.numel()})")
-    return _MFScore.apply(U, V, uid, iid)
+    if not U.is_cuda:
+        raise YelprecError("MatrixFactorization.forward: expected CUDA tensors (no CPU fallback)")
+    return _op_mf_score(U, V, uid, iid)
 
 
-class _BPRLoss(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, pos, neg):
-        lib = _cabi.load()
-        pos, neg = pos.contiguous().to(F32), neg.contiguous().to(F32)
-        loss = torch.empty((), device=pos.device, dtype=F32)
-        check(lib.yr_bpr_loss_fwd(dptr(pos), dptr(neg), pos.numel(), dptr(loss), stream_ptr(pos.device)),
-              "yr_bpr_loss_fwd")
-        ctx.save_for_backward(pos, neg)
-        return loss
+@custom_op("yelprec::bpr_loss", mutates_args=(), device_types="cuda")
+def _op_bpr_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    """BPRLoss.forward (loss.py:25-27) -> yr_bpr_loss_fwd."""
+    lib = _cabi.load()
+    pos, neg = pos.detach().contiguous().to(F32), neg.detach().contiguous().to(F32)
+    loss = torch.empty((), device=pos.device, dtype=F32)
+    check(lib.yr_bpr_loss_fwd(dptr(pos), dptr(neg), pos.numel(), dptr(loss), stream_ptr(pos.device)),
+          "yr_bpr_loss_fwd")
+    return loss
 
-    @staticmethod
-    def backward(ctx, gloss):
-        lib = _cabi.load()
-        pos, neg = ctx.saved_tensors
-        gpos, gneg = torch.empty_like(pos), torch.empty_like(neg)
-        gloss = gloss.contiguous().to(F32)
-        check(lib.yr_bpr_loss_bwd(dptr(pos), dptr(neg), pos.numel(), dptr(gloss), dptr(gpos), dptr(gneg),
-                                  stream_ptr(pos.device)), "yr_bpr_loss_bwd")
-        return gpos, gneg
+
+@_op_bpr_loss.register_fake
+def _(pos, neg):
+    return pos.new_empty((), dtype=F32)
+
+
+@custom_op("yelprec::bpr_loss_bwd", mutates_args=(), device_types="cuda")
+def _op_bpr_loss_bwd(pos: torch.Tensor, neg: torch.Tensor, gloss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _cabi.load()
+    pos, neg = pos.detach().contiguous().to(F32), neg.detach().contiguous().to(F32)
+    gpos, gneg = torch.empty_like(pos), torch.empty_like(neg)
+    gloss = gloss.contiguous().to(F32)
+    check(lib.yr_bpr_loss_bwd(dptr(pos), dptr(neg), pos.numel(), dptr(gloss), dptr(gpos), dptr(gneg),
+                              stream_ptr(pos.device)), "yr_bpr_loss_bwd")
+    return gpos, gneg
+
+
+@_op_bpr_loss_bwd.register_fake
+def _(pos, neg, gloss):
+    return torch.empty_like(pos, dtype=F32), torch.empty_like(neg, dtype=F32)
+
+
+def _bpr_loss_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _bpr_loss_backward(ctx, gloss):
+    pos, neg = ctx.saved_tensors
+    return _op_bpr_loss_bwd(pos, neg, gloss)
+
+
+_op_bpr_loss.register_autograd(_bpr_loss_backward, setup_context=_bpr_loss_setup)
 
 
 def bpr_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
     if not pos.is_cuda:
         raise YelprecError("BPRLoss: expected CUDA tensors (no CPU fallback)")
-    return _BPRLoss.apply(pos, neg)
+    return _op_bpr_loss(pos, neg)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -139,25 +192,64 @@ def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01):
     return dW1, dW2
 
 
-class _NGCFLayer(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, E, W1, W2, csr, slope):
-        Ed, W1d, W2d = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
-        En, LE = ngcf_layer_fwd(csr, Ed, W1d, W2d, slope)
-        ctx.save_for_backward(Ed, LE, En, W1d, W2d)
-        ctx.csr, ctx.slope = csr, slope
-        return En
+# The graph travels as an integer handle (custom ops take tensors and scalars only): data.graph.LaplacianCSR objects are
+# registered by identity and live as long as the model that owns them.
+_CSR_REGISTRY = {}
 
-    @staticmethod
-    def backward(ctx, Gn):
-        E, LE, En, W1, W2 = ctx.saved_tensors
-        G = torch.zeros_like(E)
-        dW1, dW2 = ngcf_layer_bwd(ctx.csr, E, LE, En, Gn, W1, W2, G, ctx.slope)
-        return G, dW1, dW2, None, None
+
+def _csr_handle(csr) -> int:
+    h = id(csr)
+    _CSR_REGISTRY[h] = csr
+    return h
+
+
+@custom_op("yelprec::ngcf_layer", mutates_args=(), device_types="cuda")
+def _op_ngcf_layer(E: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, csr_handle: int,
+                   slope: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """NGCF.embedding_propagation (models/ngcf.py:60-72) -> yr_ngcf_layer_fwd. Returns (E_next, L E)."""
+    Ed, W1d, W2d = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
+    return ngcf_layer_fwd(_CSR_REGISTRY[csr_handle], Ed, W1d, W2d, slope)
+
+
+@_op_ngcf_layer.register_fake
+def _(E, W1, W2, csr_handle, slope):
+    return torch.empty_like(E), torch.empty_like(E)
+
+
+@custom_op("yelprec::ngcf_layer_bwd", mutates_args=(), device_types="cuda")
+def _op_ngcf_layer_bwd(E: torch.Tensor, LE: torch.Tensor, En: torch.Tensor, Gn: torch.Tensor, W1: torch.Tensor,
+                       W2: torch.Tensor, csr_handle: int, slope: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    E, W1, W2 = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
+    G = torch.zeros_like(E)
+    dW1, dW2 = ngcf_layer_bwd(_CSR_REGISTRY[csr_handle], E, LE.contiguous(), En.contiguous(), Gn.contiguous(), W1, W2, G, slope)
+    return G, dW1, dW2
+
+
+@_op_ngcf_layer_bwd.register_fake
+def _(E, LE, En, Gn, W1, W2, csr_handle, slope):
+    return torch.empty_like(E), torch.empty_like(W1), torch.empty_like(W2)
+
+
+def _ngcf_layer_setup(ctx, inputs, output):
+    E, W1, W2, csr_handle, slope = inputs
+    En, LE = output
+    ctx.save_for_backward(E, LE, En, W1, W2)
+    ctx.csr_handle, ctx.slope = csr_handle, slope
+
+
+def _ngcf_layer_backward(ctx, gEn, gLE):
+    E, LE, En, W1, W2 = ctx.saved_tensors
+    G, dW1, dW2 = _op_ngcf_layer_bwd(E, LE, En, gEn, W1, W2, ctx.csr_handle, ctx.slope)
+    return G, dW1, dW2, None, None
+
+
+_op_ngcf_layer.register_autograd(_ngcf_layer_backward, setup_context=_ngcf_layer_setup)
 
 
 def ngcf_layer(E, W1, W2, csr, slope=0.01):
-    return _NGCFLayer.apply(E, W1, W2, csr, slope)
+    if not E.is_cuda:
+        raise YelprecError("NGCF.embedding_propagation: expected CUDA tensors (no CPU fallback)")
+    return _op_ngcf_layer(E, W1, W2, _csr_handle(csr), float(slope))[0]
 
 
 def dense_opt_step(p, g, m, v, opt: _cabi.YrOpt):
