@@ -57,19 +57,21 @@ def rel_fro(a, b):
 def assert_adam_close(a, b, what="", touched=0):
     """Adam divides by sqrt(v)+eps: an element whose gradient is below eps=1e-8 (a cancelling g*p - g*n) turns a
     1-ulp difference in the loss scalar or in the order duplicate rows are summed (atomics: varies run to run) into a
-    ~1e-4 relative difference of its update. Measured on the Yelp-shape tables over repeated runs: 0-4 of 2.0 M
-    elements exceed 1e-5*max after 12 steps at lr=1e-2, the worst at 2.3e-4*max. So: norm-wise 1e-5 (the parity bar),
-    at most 1e-5 of the elements (10 elements for small tables: the count is Poisson, run-to-run 1 .. 3 at d = 32)
-    beyond 1e-5*max, none beyond 1e-2*max (the worst outlier is run-to-run: up to 2.3e-4*max at d = 64, 3.0e-3*max at
-    d = 1,024 in 2 of 25 repetitions — scripts/repeat_mf_width_test.py)
-    (numerical notes). Small tables hit by many updates (the width tests: 18 k row updates on 3,000 rows) pass
-    `touched` = number of element updates with a gradient; 2e-5 of THOSE are allowed (measured: 3 of 0.2 M at d = 32,
-    9 of 4.7 M at d = 256, 33 of 6.3 M at d = 1,024)."""
+    ~1e-4 relative difference of its update. The parity bar is therefore norm-wise: ||a-b||_F < 1e-5 ||b||_F (measured
+    worst over 60 runs at d = 32: 1.5e-6), with the outliers bounded in size (none beyond 1e-2*max; measured worst 1.6e-4*max
+    at d = 32, 3.0e-3*max at d = 1,024) and in number. The number beyond 1e-5*max is 0..3 per run (0..4 of 2.0 M on the
+    Yelp-shape tables) with rare bursts of a whole row (11 and 18 elements in 2 of 60 runs at d = 32, scripts/
+    adam_outlier_stats.py): an item that is the positive of one triple and the negative of another of the same user in one
+    batch gets a row gradient (g1 - g2) * u that cancels in every column at once, so the atomics' summation order decides
+    all of its columns together. Allowed: max(10, 1e-5 of the elements, 2e-5 of `touched` = the element updates that
+    carried a gradient) plus two full rows."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.abs(b).max()
     d = np.abs(a - b)
     assert rel_fro(a, b) < RTOL, (what, rel_fro(a, b))
-    assert (d > RTOL * scale).sum() <= max(10, 1e-5 * d.size, 2e-5 * touched), (what, int((d > RTOL * scale).sum()))
+    row = a.shape[-1] if a.ndim > 1 else 1
+    allowed = max(10, 1e-5 * d.size, 2e-5 * touched) + 2 * row
+    assert (d > RTOL * scale).sum() <= allowed, (what, int((d > RTOL * scale).sum()), allowed)
     assert d.max() <= 1e-2 * scale, (what, d.max() / scale)
 
 
