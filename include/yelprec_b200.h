@@ -141,22 +141,19 @@ int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */
 int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream);
 
-/* Where the per-layer d x d transforms run: 1 (default) = forward on tensor cores, tcgen05.mma.kind::tf32 with the
- * 3xTF32 split (within the 1e-5 parity bar), backward on the FP32 pipe; 0 = FP32 pipe for both, one fma chain per
- * output (forward bit-comparable with the oracle); 2 = tensor cores for the backward too (correct, currently slower
- * than the FP32-pipe kernel: see csrc/ngcf_tc_bwd.cu). Process-wide. The tensor-core kernels are d = 64 only; the
+/* Where the per-layer d x d transforms run (`dense_mode` argument / yr_ngcf_state.dense_mode — per call and per
+ * trainer state, nothing process-wide): YR_DENSE_TC_FWD (default of the Python mirrors) = forward on tensor cores,
+ * tcgen05.mma.kind::tf32 with the 3xTF32 split (within the 1e-5 parity bar), backward on the FP32 pipe;
+ * YR_DENSE_FP32 = FP32 pipe for both, one fma chain per output (forward bit-comparable with the oracle);
+ * YR_DENSE_TC = tensor cores for the backward too (csrc/ngcf_tc_bwd.cu). The tensor-core kernels are d = 64 only; the
  * transforms accept d in {32, 64, 128} (YR_ERR_BAD_DIM otherwise) and run on the FP32 pipe off d = 64 in every mode. */
-int yr_ngcf_set_dense_mode(int mode);
-int yr_ngcf_get_dense_mode(void);
-/* yr_ngcf_train_step, top layer: 1 (default) = backward on the batch rows only (dLoss/dE_L is zero elsewhere) with
- * G += L^T T as a scatter from those rows; 0 = the dense layer backward. Same sums, different fp32 order. */
-int yr_ngcf_set_top_rows_mode(int mode);
+enum yr_dense_mode { YR_DENSE_FP32 = 0, YR_DENSE_TC_FWD = 1, YR_DENSE_TC = 2 };
 
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
  *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
  * W1, W2 are nn.Linear weights [d x d] (out x in). LE_save [n x d] receives L E (kept for backward). */
 int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2, float slope,
-                      float* E_next, float* LE_save, yr_stream stream);
+                      float* E_next, float* LE_save, int dense_mode, yr_stream stream);
 
 /* Backward of one layer. G_next = dLoss/dE_next. LT is the CSR of L^T.
  *   dZ = G_next * leaky'(E_next); dS = dZ W1; dP = dZ W2;
@@ -167,17 +164,17 @@ size_t yr_ngcf_layer_bwd_ws_bytes(int d);
 int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
                       const float* G_next, const float* W1, const float* W2, float slope,
                       float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
-                      yr_stream stream);
+                      int dense_mode, yr_stream stream);
 
 /* The dense halves of the two calls above on n rows, WITHOUT the SpMM (models/ngcf.py:65-72 and its autograd):
  * the row-sharded trainer (BASELINE config 5) runs the SpMM on its row block of L against the all-gathered operand
  * and these on its local rows. yr_ngcf_dense_bwd: G += dS + dP*LE, T = dS + dP*E, dW1/dW2 overwritten. */
 int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
-                      float slope, float* E_next, yr_stream stream);
+                      float slope, float* E_next, int dense_mode, yr_stream stream);
 int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
                       const float* G_next, const float* W1, const float* W2, float slope,
                       float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
-                      yr_stream stream);
+                      int dense_mode, yr_stream stream);
 
 /* Tail of NGCF.bpr_forward + BPRLoss (models/ngcf.py:37-45, loss.py:25-27) and its backward:
  * rows u / nU+pos / nU+neg are gathered from every layer output E_l (l = 0..n_layers), the concatenated
@@ -226,6 +223,10 @@ typedef struct yr_ngcf_state {
   /* optional scratch for the row-sparse top-layer backward of yr_ngcf_train_step (all NULL/0 = dense everywhere):
    * row_flag [n] and row_count [1] zero between steps, row_list [row_list_cap], row_list_cap >= 3 * B */
   int32_t* row_flag; int32_t* row_list; int32_t* row_count; int64_t row_list_cap;
+  int32_t dense_mode;                 /* yr_dense_mode of this trainer's layers */
+  int32_t top_rows_mode;              /* yr_ngcf_train_step, top layer: 1 = backward on the batch rows only (dLoss/dE_L is zero
+                                         elsewhere) with G += L^T T as a scatter from those rows; 0 = the dense layer backward.
+                                         Same sums, different fp32 order. */
 } yr_ngcf_state;
 
 /* forward only: fills E[1..n_layers] (and LE[]) — used by validate / evaluate (propagate ONCE, not per user) */

@@ -24,9 +24,8 @@ G0 = np.zeros_like(E)
 Go, dW1o, dW2o = cport.ngcf_layer_bwd(ct, E, LE, En, Gn, W1, W2, G0)
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 for mode in (0, 1):
-    lib.yr_ngcf_set_dense_mode(mode)
     G = torch.zeros(n, 64, device="cuda")
-    dW1, dW2 = ops.ngcf_layer_bwd(csr, cu(E), cu(LE), cu(En), cu(Gn), cu(W1), cu(W2), G)
+    dW1, dW2 = ops.ngcf_layer_bwd(csr, cu(E), cu(LE), cu(En), cu(Gn), cu(W1), cu(W2), G, dense_mode=mode)
     torch.cuda.synchronize()
     print("mode", mode, "G", rel_err(G.cpu().numpy(), Go), "dW1", rel_err(dW1.cpu().numpy(), dW1o), "dW2", rel_err(dW2.cpu().numpy(), dW2o))
     if mode == 1:

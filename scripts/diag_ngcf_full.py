@@ -17,9 +17,9 @@ tu, tpos, tneg = syn.sample_triples(split, inter.num_items, seed=42)
 batches = syn.to_batches(tu, tpos, tneg, 2048)[:2]
 ref = None
 for rows, dense in ((1, 1), (0, 1), (1, 0), (0, 0)):
-    lib.yr_ngcf_set_top_rows_mode(rows); lib.yr_ngcf_set_dense_mode(dense)
     torch.manual_seed(5)
-    tr = NGCFTrainer(cfg(optimizer="sgd", lr=0.05, num_orders=3, batch_size=2048), inter.num_items, inter.num_users, L)
+    tr = NGCFTrainer(cfg(optimizer="sgd", lr=0.05, num_orders=3, batch_size=2048, ngcf_top_rows_mode=rows, ngcf_dense_mode=dense),
+                     inter.num_items, inter.num_users, L)
     sd = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
     if ref is None:
         port = tp.NGCFPort(sd["embedding.weight"], [sd[f"W1.{l}.weight"] for l in range(3)],

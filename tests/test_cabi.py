@@ -60,7 +60,7 @@ def test_pytorch_custom_ops_are_registered():
             "mf_score_bwd": "yelprec::mf_score_bwd(Tensor U, Tensor V, Tensor uid, Tensor iid, Tensor gout) -> (Tensor, Tensor)",
             "bpr_loss": "yelprec::bpr_loss(Tensor pos, Tensor neg) -> Tensor",
             "bpr_loss_bwd": "yelprec::bpr_loss_bwd(Tensor pos, Tensor neg, Tensor gloss) -> (Tensor, Tensor)",
-            "ngcf_layer": "yelprec::ngcf_layer(Tensor E, Tensor W1, Tensor W2, SymInt csr_handle, float slope) -> (Tensor, Tensor)"}
+            "ngcf_layer": "yelprec::ngcf_layer(Tensor E, Tensor W1, Tensor W2, SymInt csr_handle, float slope, SymInt dense_mode) -> (Tensor, Tensor)"}
     for name, schema in want.items():
         assert str(getattr(torch.ops.yelprec, name).default._schema) == schema
     with FakeTensorMode():

@@ -24,9 +24,9 @@ def _golden():
     return g, nU, nI, L, csr, csrT, g["ngcf_init_embedding.weight"], W1, W2
 
 
-def _trainer(g, nU, nI, L, name="sgd", lr=1e-2, wd=0.0):
+def _trainer(g, nU, nI, L, name="sgd", lr=1e-2, wd=0.0, **extra):
     from yelprecommendation_b200.trainers import NGCFTrainer
-    tr = NGCFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd, num_orders=3), nI, nU, L)
+    tr = NGCFTrainer(cfg(optimizer=name, lr=lr, weight_decay=wd, num_orders=3, **extra), nI, nU, L)
     sd = {k[len("ngcf_init_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("ngcf_init_")}
     tr.model.load_state_dict(sd)          # identical state_dict keys to the reference model
     return tr
@@ -53,18 +53,9 @@ def test_spmm_bit_exact_vs_oracle():
         assert np.array_equal(ya.cpu().numpy(), cport.spmm_csr(*ct, X, Y0))
 
 
-@pytest.fixture
-def fp32_dense():
-    """FP32-pipe dense transforms (bit-comparable with the oracle) for the duration of a test."""
-    from yelprecommendation_b200 import _cabi
-    lib = _cabi.load()
-    old = lib.yr_ngcf_get_dense_mode()
-    lib.yr_ngcf_set_dense_mode(0)
-    yield
-    lib.yr_ngcf_set_dense_mode(old)
-
-
-def test_layer_forward_bit_exact_vs_oracle_and_golden(fp32_dense):
+def test_layer_forward_bit_exact_vs_oracle_and_golden():
+    """dense_mode 0 (YR_DENSE_FP32): FP32-pipe transforms, bit-comparable with the oracle. The mode is an argument of the
+    call (per trainer: cfg.ngcf_dense_mode) — nothing process-wide."""
     from yelprecommendation_b200 import ops
     from yelprecommendation_b200.data.graph import laplacian_to_csr
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
@@ -72,7 +63,7 @@ def test_layer_forward_bit_exact_vs_oracle_and_golden(fp32_dense):
     E = torch.from_numpy(E0).cuda()
     Ec = E0
     for l in range(3):
-        En, LE = ops.ngcf_layer_fwd(dcsr, E, torch.from_numpy(W1[l]).cuda(), torch.from_numpy(W2[l]).cuda())
+        En, LE = ops.ngcf_layer_fwd(dcsr, E, torch.from_numpy(W1[l]).cuda(), torch.from_numpy(W2[l]).cuda(), dense_mode=0)
         Eo, LEo = cport.ngcf_layer_fwd(csr, Ec, W1[l], W2[l])
         assert np.array_equal(LE.cpu().numpy(), LEo)
         assert np.array_equal(En.cpu().numpy(), Eo)                      # same fma chain order -> bit-exact
@@ -86,7 +77,7 @@ def test_layer_forward_tensor_core_3xtf32():
     from yelprecommendation_b200 import _cabi, ops
     from yelprecommendation_b200.data import synthetic as syn
     from yelprecommendation_b200.data.graph import build_laplacian, laplacian_to_csr
-    assert _cabi.load().yr_ngcf_get_dense_mode() == 1
+    assert _cabi.YR_DENSE_TC_FWD == 1            # the default of ops.ngcf_layer_fwd / cfg.ngcf_dense_mode
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
     dcsr = laplacian_to_csr(L, "cuda")
     E, Ec = torch.from_numpy(E0).cuda(), E0
@@ -112,29 +103,20 @@ def test_layer_forward_tensor_core_3xtf32():
 @pytest.mark.parametrize("dense_mode", [1, 2])
 def test_layer_backward_vs_oracle_and_autograd_golden(dense_mode):
     """dense_mode 1: FP32-pipe backward kernel (default); 2: tcgen05 backward (3xTF32, MN-major operands for dW)."""
-    from yelprecommendation_b200 import _cabi, ops
+    from yelprecommendation_b200 import ops
     from yelprecommendation_b200.data.graph import laplacian_to_csr
-    lib = _cabi.load()
-    lib.yr_ngcf_set_dense_mode(dense_mode)
-    try:
-        _layer_backward_case(ops, laplacian_to_csr)
-    finally:
-        lib.yr_ngcf_set_dense_mode(1)
+    _layer_backward_case(ops, laplacian_to_csr, dense_mode)
 
 
 def test_train_steps_with_tensor_core_backward():
-    """Whole train steps (row-sparse last layer included) with the tcgen05 backward vs the reference golden."""
-    from yelprecommendation_b200 import _cabi
-    lib = _cabi.load()
-    lib.yr_ngcf_set_dense_mode(2)
-    try:
-        assert lib.yr_ngcf_get_dense_mode() == 2
-        test_train_steps_vs_reference_golden(1)
-    finally:
-        lib.yr_ngcf_set_dense_mode(1)
+    """Whole train steps (row-sparse last layer included) with the tcgen05 backward (cfg.ngcf_dense_mode = 2) vs the
+    reference golden; a second trainer built afterwards with the default config is unaffected (the mode is per trainer)."""
+    test_train_steps_vs_reference_golden(1, ngcf_dense_mode=2)
+    g, nU, nI, L, *_ = _golden()
+    assert _trainer(g, nU, nI, L)._state()[0].dense_mode == 1
 
 
-def _layer_backward_case(ops, laplacian_to_csr):
+def _layer_backward_case(ops, laplacian_to_csr, dense_mode=1):
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
     dcsr = laplacian_to_csr(L, "cuda")
     layers, LEs = [E0], []
@@ -148,7 +130,8 @@ def _layer_backward_case(ops, laplacian_to_csr):
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     for l in (2, 1, 0):
         G[l], dW1o, dW2o = cport.ngcf_layer_bwd(csrT, layers[l], LEs[l], layers[l + 1], G[l + 1], W1[l], W2[l], G[l])
-        dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(layers[l]), cu(LEs[l]), cu(layers[l + 1]), Gd[l + 1], cu(W1[l]), cu(W2[l]), Gd[l])
+        dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(layers[l]), cu(LEs[l]), cu(layers[l + 1]), Gd[l + 1], cu(W1[l]), cu(W2[l]), Gd[l],
+                                      dense_mode=dense_mode)
         assert rel_err(Gd[l].cpu().numpy(), G[l]) < RTOL
         assert rel_err(dW1.cpu().numpy(), dW1o) < RTOL and rel_err(dW2.cpu().numpy(), dW2o) < RTOL
         assert rel_err(dW1.cpu().numpy(), g[f"ngcf_grad_W1.{l}.weight"]) < 2e-5
@@ -157,10 +140,10 @@ def _layer_backward_case(ops, laplacian_to_csr):
 
 
 @pytest.mark.parametrize("ci", [0, 1, 2])
-def test_train_steps_vs_reference_golden(ci):
+def test_train_steps_vs_reference_golden(ci, **extra):
     g, nU, nI, L, *_ = _golden()
     name, (lr, wd) = str(g[f"ngcf_{ci}_name"]), g[f"ngcf_{ci}_cfg"]
-    tr = _trainer(g, nU, nI, L, name, float(lr), float(wd))
+    tr = _trainer(g, nU, nI, L, name, float(lr), float(wd), **extra)
     batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 128, limit=3)
     if ci == 0:
         assert isclose(tr.validate(batches), float(g["ngcf_valid0"]), rel_tol=RTOL)
@@ -177,22 +160,16 @@ def test_train_steps_vs_reference_golden(ci):
 @pytest.mark.parametrize("name,lr", [("sgd", 0.05), ("adam", 1e-3)])
 def test_row_sparse_top_layer_equals_dense_step(name, lr):
     """yr_ngcf_train_step: last-layer forward/backward on the <= 3B batch rows + scatter form of L^T T (default) vs the
-    dense layer everywhere (yr_ngcf_set_top_rows_mode(0)) — same sums in a different fp32 order: 1e-6 norm-wise here.
-    validate()/evaluate() after a row-sparse step must see a fully recomputed propagation (no stale rows)."""
-    from yelprecommendation_b200 import _cabi
-    lib = _cabi.load()
+    dense layer everywhere (cfg.ngcf_top_rows_mode = 0, per trainer) — same sums in a different fp32 order: 1e-6
+    norm-wise here. validate()/evaluate() after a row-sparse step must see a fully recomputed propagation (no stale rows)."""
     g, nU, nI, L, *_ = _golden()
     batches = batches_from(g["tri_u"], g["tri_p"], g["tri_n"], 128, limit=4)
     out = {}
     for mode in (1, 0):
-        lib.yr_ngcf_set_top_rows_mode(mode)
-        try:
-            tr = _trainer(g, nU, nI, L, name, lr, 0.0)
-            total = tr.train(batches)
-            sd = {k: v.detach().cpu().numpy().copy() for k, v in tr.model.state_dict().items()}
-            out[mode] = (total, tr.last_step_losses.cpu().numpy().copy(), sd, tr.validate(batches))
-        finally:
-            lib.yr_ngcf_set_top_rows_mode(1)
+        tr = _trainer(g, nU, nI, L, name, lr, 0.0, ngcf_top_rows_mode=mode)
+        total = tr.train(batches)
+        sd = {k: v.detach().cpu().numpy().copy() for k, v in tr.model.state_dict().items()}
+        out[mode] = (total, tr.last_step_losses.cpu().numpy().copy(), sd, tr.validate(batches))
     (ta, la, sa, va), (tb, lb, sb, vb) = out[1], out[0]
     assert isclose(ta, tb, rel_tol=1e-6) and rel_err(la, lb) < 1e-6 and isclose(va, vb, rel_tol=1e-6)
     for k in sb:

@@ -26,7 +26,6 @@ SYMBOLS = (
     "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
-    "yr_ngcf_set_dense_mode", "yr_ngcf_get_dense_mode", "yr_ngcf_set_top_rows_mode",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex",
     "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
@@ -34,6 +33,8 @@ SYMBOLS = (
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
+# yr_dense_mode: where the NGCF d x d transforms run (per call / per trainer state)
+YR_DENSE_FP32, YR_DENSE_TC_FWD, YR_DENSE_TC = 0, 1, 2
 OPT_KINDS = {"sgd": YR_OPT_SGD, "adam": YR_OPT_ADAM, "adamw": YR_OPT_ADAMW}
 
 _STATUS = {
@@ -94,7 +95,8 @@ class YrNgcfState(C.Structure):
                 ("E_dev", C.c_void_p), ("G_dev", C.c_void_p),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
                 ("loss", C.c_void_p), ("err", C.c_void_p),
-                ("row_flag", C.c_void_p), ("row_list", C.c_void_p), ("row_count", C.c_void_p), ("row_list_cap", C.c_int64)]
+                ("row_flag", C.c_void_p), ("row_list", C.c_void_p), ("row_count", C.c_void_p), ("row_list_cap", C.c_int64),
+                ("dense_mode", C.c_int32), ("top_rows_mode", C.c_int32)]
 
 
 class YelprecError(RuntimeError):
@@ -131,11 +133,11 @@ def load() -> C.CDLL:
         "yr_spmm_plan_size_h": (C.c_int, [p, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "yr_spmm_plan_fill_h": (C.c_int, [p, i64, p, p, p]),
         "yr_spmm_csr": (C.c_int, [C.POINTER(YrCsr), i32, p, p, i32, p]),
-        "yr_ngcf_layer_fwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, f32, p, p, p]),
+        "yr_ngcf_layer_fwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, f32, p, p, i32, p]),
         "yr_ngcf_layer_bwd_ws_bytes": (sz, [i32]),
-        "yr_ngcf_layer_bwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, p, p, p, f32, p, p, p, p, p, sz, p]),
-        "yr_ngcf_dense_fwd": (C.c_int, [i32, i64, p, p, p, p, f32, p, p]),
-        "yr_ngcf_dense_bwd": (C.c_int, [i32, i64, p, p, p, p, p, p, f32, p, p, p, p, p, sz, p]),
+        "yr_ngcf_layer_bwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, p, p, p, f32, p, p, p, p, p, sz, i32, p]),
+        "yr_ngcf_dense_fwd": (C.c_int, [i32, i64, p, p, p, p, f32, p, i32, p]),
+        "yr_ngcf_dense_bwd": (C.c_int, [i32, i64, p, p, p, p, p, p, f32, p, p, p, p, p, sz, i32, p]),
         "yr_ngcf_tail": (C.c_int, [p, p, i32, i64, i64, i32, p, p, p, i64, p, p, p, p, p, p]),
         "yr_dense_opt_step": (C.c_int, [p, p, p, p, i64, C.POINTER(YrOpt), p]),
         "yr_dense_opt_step_multi": (C.c_int, [i32, p, p, p, p, p, C.POINTER(YrOpt), i32, p]),
@@ -168,9 +170,6 @@ def load() -> C.CDLL:
         "yr_bpr_rows_grad": (C.c_int, [p, i32, i64, i64, i64, p, p, p]),
         "yr_shard_accumulate": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, i64, p, i64, p]),
         "yr_shard_step": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), i64, p]),
-        "yr_ngcf_set_dense_mode": (C.c_int, [i32]),
-        "yr_ngcf_get_dense_mode": (C.c_int, []),
-        "yr_ngcf_set_top_rows_mode": (C.c_int, [i32]),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),
         "yr_eval_tc_ws_bytes": (sz, [i64]),
         "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,

@@ -183,15 +183,30 @@ __device__ __forceinline__ void opt_update(const OptScalars& s, float& p, float 
 }
 
 inline int yr_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
+
+// cudaFuncSetAttribute is per DEVICE: remember which devices have been opted in (a process may drive several GPUs)
+struct AttrOnce {
+  bool done[64] = {};
+  template <typename K> int set(K kernel, int bytes) {
+    int dev = 0;
+    YR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      YR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return YR_OK;
+  }
+};
 
 inline int yr_csr_ok(const yr_csr* A) {
   if (!A || !A->rowptr || !A->col || !A->val || A->n_rows < 0 || A->n_chunks < 0) return YR_ERR_BAD_ARG;

@@ -344,11 +344,8 @@ extern "C" int yr_laplacian_build(const int64_t* user, const int64_t* item, cons
   YR_CHECK_LAUNCH();
   lap_sort_warp_kernel<<<g_r, 256, 0, s>>>(w.ptr, N, w.keys, w.listA, w.listB, w.listC, w.scratch_off + 1, w.counters);
   YR_CHECK_LAUNCH();
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(lap_sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLargeCap * 8));
-    attr_set = true;
-  }
+  static yr::AttrOnce attr;
+  { int rc_ = attr.set(lap_sort_smem_kernel, kSortLargeCap * 8); if (rc_) return rc_; }
   lap_sort_smem_kernel<<<sm * 8, 256, kSortSmallCap * 8, s>>>(w.ptr, w.listA, w.counters + 0, w.keys);
   YR_CHECK_LAUNCH();
   lap_sort_smem_kernel<<<sm, 1024, kSortLargeCap * 8, s>>>(w.ptr, w.listB, w.counters + 1, w.keys);

@@ -459,34 +459,17 @@ constexpr int kBwdCtasPerSm = 2;
 
 using namespace yr;
 
-// 0 = FP32 pipe (one fma chain per output, bit-comparable with the oracle), 1 = tensor cores (3xTF32 split)
-static int g_dense_mode = 1;
-static int g_bwd_tc = 0;       // mode 2: tensor cores for the backward transforms too (ngcf_tc_bwd.cu; slower, see there)
-extern "C" int yr_ngcf_set_dense_mode(int mode) {
-  if (mode == 2) { g_dense_mode = 1; g_bwd_tc = 1; return YR_OK; }
-  if (mode != 0 && mode != 1) return YR_ERR_BAD_ARG;
-  g_bwd_tc = 0;
-  g_dense_mode = mode;
-  return YR_OK;
-}
-extern "C" int yr_ngcf_get_dense_mode(void) { return g_bwd_tc ? 2 : g_dense_mode; }
-// 1 (default) = the top layer's backward of yr_ngcf_train_step runs on the batch rows only; 0 = dense (debug / A-B)
-static int g_top_rows_mode = 1;
-extern "C" int yr_ngcf_set_top_rows_mode(int mode) {
-  if (mode != 0 && mode != 1) return YR_ERR_BAD_ARG;
-  g_top_rows_mode = mode;
-  return YR_OK;
-}
+// yr_dense_mode (include/yelprec_b200.h) travels per call / per trainer state; nothing here is process-wide.
+static inline bool mode_ok(int m) { return m == YR_DENSE_FP32 || m == YR_DENSE_TC_FWD || m == YR_DENSE_TC; }
+static inline bool fwd_tc(int m) { return m != YR_DENSE_FP32; }
+static inline bool bwd_tc(int m) { return m == YR_DENSE_TC; }
 
 template <int D>
 static int dense_fwd_fp32_launch(int64_t n, const float* E, const float* LE, const float* W1, const float* W2, float slope,
                                  float* E_next, cudaStream_t s) {
   using C = DenseCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemFwd));
-    attr_set = true;
-  }
+  static AttrOnce attr;
+  { int rc_ = attr.set(ngcf_dense_fwd_kernel<D>, (int)C::kSmemFwd); if (rc_) return rc_; }
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
   int64_t grid = (int64_t)yr_sm_count() * (D <= 64 ? 3 : 1);
   if (grid > n_tiles) grid = n_tiles;
@@ -500,11 +483,8 @@ static int dense_bwd_fp32_launch(int64_t n, const float* E, const float* LE, con
                                  const float* W1, const float* W2, float slope, float* G, float* T, float* ws,
                                  cudaStream_t s, int* n_parts) {
   using C = DenseCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBwd));
-    attr_set = true;
-  }
+  static AttrOnce attr;
+  { int rc_ = attr.set(ngcf_dense_bwd_kernel<D>, (int)C::kSmemBwd); if (rc_) return rc_; }
   const int64_t n_tiles = (n + C::TM - 1) / C::TM;
   int64_t grid = (int64_t)yr_sm_count() * (D <= 64 ? kBwdCtasPerSm : 1);       // D = 128: 176 KB of shared memory per CTA
   if (grid > n_tiles) grid = n_tiles;
@@ -516,11 +496,11 @@ static int dense_bwd_fp32_launch(int64_t n, const float* E, const float* LE, con
 }
 
 extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* LE, const float* W1, const float* W2,
-                                 float slope, float* E_next, yr_stream stream) {
-  if (!E || !LE || !W1 || !W2 || !E_next || n < 0) return YR_ERR_BAD_ARG;
+                                 float slope, float* E_next, int dense_mode, yr_stream stream) {
+  if (!E || !LE || !W1 || !W2 || !E_next || n < 0 || !mode_ok(dense_mode)) return YR_ERR_BAD_ARG;
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (n == 0) return YR_OK;
-  if (g_dense_mode == 1 && d == 64)      // tcgen05 3xTF32 (ngcf_tc.cu); other widths run on the FP32 pipe
+  if (fwd_tc(dense_mode) && d == 64)      // tcgen05 3xTF32 (ngcf_tc.cu); other widths run on the FP32 pipe
     return yr_ngcf_dense_fwd_tc_launch(E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
   switch (d) {
     case 32: return dense_fwd_fp32_launch<32>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
@@ -530,12 +510,12 @@ extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* 
 }
 
 extern "C" int yr_ngcf_layer_fwd(const yr_csr* L, int d, const float* E, const float* W1, const float* W2,
-                                 float slope, float* E_next, float* LE_save, yr_stream stream) {
-  if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0) return YR_ERR_BAD_ARG;
+                                 float slope, float* E_next, float* LE_save, int dense_mode, yr_stream stream) {
+  if (!L || !E || !W1 || !W2 || !E_next || !LE_save || L->n_rows <= 0 || !mode_ok(dense_mode)) return YR_ERR_BAD_ARG;
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   int rc = yr_spmm_csr(L, d, E, LE_save, 0, stream);
   if (rc) return rc;
-  return yr_ngcf_dense_fwd(d, L->n_rows, E, LE_save, W1, W2, slope, E_next, stream);
+  return yr_ngcf_dense_fwd(d, L->n_rows, E, LE_save, W1, W2, slope, E_next, dense_mode, stream);
 }
 
 extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
@@ -545,11 +525,11 @@ extern "C" size_t yr_ngcf_layer_bwd_ws_bytes(int d) {
 // the dense backward kernel WITHOUT the reduction of its per-CTA dW partials (n_parts of them are left in ws)
 static int dense_bwd_launch(int d, int64_t n, const float* E, const float* LE, const float* E_next, const float* G_next,
                             const float* W1, const float* W2, float slope, float* G, float* T, void* ws, size_t ws_bytes,
-                            cudaStream_t s, int* n_parts) {
-  if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !ws || n <= 0) return YR_ERR_BAD_ARG;
+                            int dense_mode, cudaStream_t s, int* n_parts) {
+  if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !ws || n <= 0 || !mode_ok(dense_mode)) return YR_ERR_BAD_ARG;
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
-  if (g_dense_mode == 1 && g_bwd_tc && d == 64)            // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
+  if (bwd_tc(dense_mode) && d == 64)                       // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
     return yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
   switch (d) {
     case 32: return dense_bwd_fp32_launch<32>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
@@ -568,10 +548,11 @@ static int dense_bwd_reduce(int d, const void* ws, int n_parts, float* dW1, floa
 extern "C" int yr_ngcf_dense_bwd(int d, int64_t n, const float* E, const float* LE, const float* E_next,
                                  const float* G_next, const float* W1, const float* W2, float slope,
                                  float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
-                                 yr_stream stream) {
+                                 int dense_mode, yr_stream stream) {
   if (!dW1 || !dW2) return YR_ERR_BAD_ARG;
   int parts = 0;
-  int rc = dense_bwd_launch(d, n, E, LE, E_next, G_next, W1, W2, slope, G, T, ws, ws_bytes, (cudaStream_t)stream, &parts);
+  int rc = dense_bwd_launch(d, n, E, LE, E_next, G_next, W1, W2, slope, G, T, ws, ws_bytes, dense_mode, (cudaStream_t)stream,
+                            &parts);
   if (rc) return rc;
   return dense_bwd_reduce(d, ws, parts, dW1, dW2, (cudaStream_t)stream);
 }
@@ -669,7 +650,7 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
   const int d = st->d;
   using C = DenseCfg<64>;
   if (d != 64) return YR_ERR_BAD_DIM;
-  if (g_dense_mode == 1 && g_bwd_tc) {
+  if (bwd_tc(st->dense_mode)) {
     int parts = 0;
     int rc = yr_ngcf_dense_bwd_tc_launch(st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope,
                                          st->nU + st->nI, st->G[l], st->T, (float*)st->ws, &parts, s, st->row_list,
@@ -686,11 +667,8 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
   const int64_t cap = (int64_t)yr_sm_count() * kBwdCtasPerSm;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBwd));
-    attr_set = true;
-  }
+  static AttrOnce attr;
+  { int rc_ = attr.set(ngcf_dense_bwd_kernel<64>, (int)C::kSmemBwd); if (rc_) return rc_; }
   ngcf_dense_bwd_kernel<64><<<(unsigned)grid, C::kThreads, C::kSmemBwd, s>>>(
       st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope, st->nU + st->nI, st->G[l], st->T,
       (float*)st->ws, st->row_list, st->row_count);
@@ -723,9 +701,10 @@ static int rows_reduce(const yr_ngcf_state* st, int l, int parts, cudaStream_t s
 extern "C" int yr_ngcf_layer_bwd(const yr_csr* LT, int d, const float* E, const float* LE, const float* E_next,
                                  const float* G_next, const float* W1, const float* W2, float slope,
                                  float* G, float* T, float* dW1, float* dW2, void* ws, size_t ws_bytes,
-                                 yr_stream stream) {
+                                 int dense_mode, yr_stream stream) {
   if (!LT || LT->n_rows <= 0) return YR_ERR_BAD_ARG;
-  int rc = yr_ngcf_dense_bwd(d, LT->n_rows, E, LE, E_next, G_next, W1, W2, slope, G, T, dW1, dW2, ws, ws_bytes, stream);
+  int rc = yr_ngcf_dense_bwd(d, LT->n_rows, E, LE, E_next, G_next, W1, W2, slope, G, T, dW1, dW2, ws, ws_bytes, dense_mode,
+                             stream);
   if (rc) return rc;
   return yr_spmm_csr(LT, d, T, G, 1, stream);
 }
@@ -821,7 +800,7 @@ __global__ void concat_layers_kernel(const float* const* __restrict__ E_layers, 
 static int ngcf_state_ok(const yr_ngcf_state* st) {
   if (!st || st->n_layers < 1 || st->n_layers > YR_NGCF_MAX_LAYERS || st->nU <= 0 || st->nI <= 0)
     return YR_ERR_BAD_ARG;
-  if (yr_csr_ok(&st->L) || !st->E[0]) return YR_ERR_BAD_ARG;
+  if (yr_csr_ok(&st->L) || !st->E[0] || !mode_ok(st->dense_mode)) return YR_ERR_BAD_ARG;
   for (int l = 0; l < st->n_layers; ++l)
     if (!st->E[l + 1] || !st->LE[l] || !st->W1[l] || !st->W2[l]) return YR_ERR_BAD_ARG;
   return YR_OK;
@@ -832,7 +811,8 @@ extern "C" int yr_ngcf_propagate_prefix(const yr_ngcf_state* st, float slope, in
   if (rc) return rc;
   if (n_prefix < 0 || n_prefix > st->n_layers) return YR_ERR_BAD_ARG;
   for (int l = 0; l < n_prefix; ++l) {
-    rc = yr_ngcf_layer_fwd(&st->L, st->d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+    rc = yr_ngcf_layer_fwd(&st->L, st->d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], st->dense_mode,
+                           stream);
     if (rc) return rc;
   }
   return YR_OK;
@@ -843,7 +823,7 @@ extern "C" int yr_ngcf_propagate(const yr_ngcf_state* st, float slope, yr_stream
   if (rc) return rc;
   for (int l = 0; l < st->n_layers; ++l) {
     rc = yr_ngcf_layer_fwd(&st->L, st->d, st->E[l], st->W1[l], st->W2[l], slope,
-                           st->E[l + 1], st->LE[l], stream);
+                           st->E[l + 1], st->LE[l], st->dense_mode, stream);
     if (rc) return rc;
   }
   return YR_OK;
@@ -888,16 +868,17 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
   // scatter from them (same sums, different fp32 order). Needs the row scratch; E_L / LE_{L-1} keep stale values in
   // the other rows (yr_ngcf_propagate recomputes everything for validate / evaluate).
   const bool rows_path = st->row_flag && st->row_list && st->row_count && st->row_list_cap >= 3 * B && d == 64 &&
-                         g_top_rows_mode;
+                         st->top_rows_mode != 0;
   if (rows_path) {                                            // list of the batch rows: also off the critical path
     touched_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, ms>>>(uid, pos, neg, B, st->nU, st->nI, st->row_flag,
                                                                         st->row_list, st->row_count);
     YR_CHECK_LAUNCH();
   }
   if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
-  if (rows_path && g_dense_mode == 1) {
+  if (rows_path && fwd_tc(st->dense_mode)) {
     for (int l = (prefix_done < L - 1 ? prefix_done : L - 1); l + 1 < L; ++l) {
-      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], st->dense_mode,
+                           stream);
       if (rc) return rc;
     }
     if (side) YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));       // row list (and the cleared gradients) ready
@@ -908,7 +889,8 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
     if (rc) return rc;
   } else {
     for (int l = prefix_done; l < L; ++l) {
-      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], stream);
+      rc = yr_ngcf_layer_fwd(&st->L, d, st->E[l], st->W1[l], st->W2[l], slope, st->E[l + 1], st->LE[l], st->dense_mode,
+                           stream);
       if (rc) return rc;
     }
   }
@@ -941,7 +923,7 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
     if (side && reduce_pending) { YR_CUDA(cudaStreamWaitEvent(s, side->join, 0)); reduce_pending = false; }   // ws is free again
     int parts = 0;
     rc = dense_bwd_launch(d, n, st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope, st->G[l],
-                          st->T, st->ws, st->ws_bytes, s, &parts);
+                          st->T, st->ws, st->ws_bytes, st->dense_mode, s, &parts);
     if (rc) return rc;
     if (side) {
       YR_CUDA(cudaEventRecord(side->fork, s));

@@ -193,11 +193,8 @@ int yr_ngcf_dense_fwd_tc_launch(const float* E, const float* LE, const float* W1
                                 int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list,
                                 const int32_t* row_count, int64_t row_cap) {
   const size_t smem = 4 * 32768 + 4 * 16384 + 64 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static yr::AttrOnce attr;
+  { int rc_ = attr.set(ngcf_dense_fwd_tc_kernel, (int)smem); if (rc_) return rc_; }
   const int64_t n_tiles = ((row_list ? row_cap : n) + kFwdTM - 1) / kFwdTM;
   int64_t grid = yr_sm_count();
   if (grid > n_tiles) grid = n_tiles;

@@ -313,11 +313,8 @@ int yr_ngcf_dense_bwd_tc_launch(const float* E, const float* LE, const float* En
                                 const float* W2, float slope, int64_t n, float* G, float* T, float* ws, int* n_parts,
                                 cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
   const size_t smem = 229376 + 128 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YR_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static yr::AttrOnce attr;
+  { int rc_ = attr.set(ngcf_dense_bwd_tc_kernel, (int)smem); if (rc_) return rc_; }
   const int64_t n_tiles = ((row_list ? row_cap : n) + kBwdTM - 1) / kBwdTM;
   int64_t grid = yr_sm_count();
   if (grid > n_tiles) grid = n_tiles;

@@ -25,6 +25,10 @@ class NGCF(BaseModel):
             from .. import _cabi
             raise _cabi.YelprecError(f"NGCF embed_size {cfg.embed_size}: the propagation kernels take 32, 64 (tensor cores) or 128")
         self.cfg = cfg
+        # where the d x d transforms run (yr_dense_mode, include/yelprec_b200.h): per model, nothing process-wide
+        self.dense_mode = int(getattr(cfg, "ngcf_dense_mode", 1))
+        if self.dense_mode not in (0, 1, 2):
+            raise ValueError(f"ngcf_dense_mode {self.dense_mode} not in (0, 1, 2)")
         self.num_users = num_users
         self.num_items = num_items
         self.embedding = nn.Embedding(num_users + num_items, cfg.embed_size, dtype=torch.float32)
@@ -47,7 +51,8 @@ class NGCF(BaseModel):
         return val
 
     def embedding_propagation(self, last_embed: torch.Tensor, w1, w2, laplacian_matrix):
-        return ops.ngcf_layer(last_embed, w1.weight, w2.weight, self.csr(laplacian_matrix), _LEAKY_SLOPE)
+        return ops.ngcf_layer(last_embed, w1.weight, w2.weight, self.csr(laplacian_matrix), _LEAKY_SLOPE,
+                              self.dense_mode)
 
     def _layers(self, laplacian_matrix):
         outs = [self.embedding.weight]

@@ -165,18 +165,18 @@ def spmm_csr(A, X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=
     return out
 
 
-def ngcf_layer_fwd(csr, E, W1, W2, slope=0.01):
-    """csr: data.graph.LaplacianCSR."""
+def ngcf_layer_fwd(csr, E, W1, W2, slope=0.01, dense_mode: int = _cabi.YR_DENSE_TC_FWD):
+    """csr: data.graph.LaplacianCSR. dense_mode: yr_dense_mode (include/yelprec_b200.h)."""
     lib = _cabi.load()
     E, W1, W2 = E.contiguous(), W1.contiguous(), W2.contiguous()
     En, LE = torch.empty_like(E), torch.empty_like(E)
     st = csr.fwd.struct(E.shape[1])
     check(lib.yr_ngcf_layer_fwd(C.byref(st), E.shape[1], dptr(E, F32), dptr(W1, F32), dptr(W2, F32), float(slope),
-                                dptr(En), dptr(LE), stream_ptr(E.device)), "yr_ngcf_layer_fwd")
+                                dptr(En), dptr(LE), int(dense_mode), stream_ptr(E.device)), "yr_ngcf_layer_fwd")
     return En, LE
 
 
-def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01):
+def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01, dense_mode: int = _cabi.YR_DENSE_TC_FWD):
     """G (accumulated in place) += dLoss/dE; returns (dW1, dW2)."""
     lib = _cabi.load()
     d = E.shape[1]
@@ -187,14 +187,16 @@ def ngcf_layer_bwd(csr, E, LE, En, Gn, W1, W2, G, slope=0.01):
     st = csr.bwd.struct(d)
     check(lib.yr_ngcf_layer_bwd(C.byref(st), d, dptr(E.contiguous(), F32), dptr(LE, F32), dptr(En, F32),
                                 dptr(Gn.contiguous(), F32), dptr(W1.contiguous(), F32), dptr(W2.contiguous(), F32),
-                                float(slope), dptr(G, F32), dptr(T), dptr(dW1), dptr(dW2), dptr(ws), nbytes,
+                                float(slope), dptr(G, F32), dptr(T), dptr(dW1), dptr(dW2), dptr(ws), nbytes, int(dense_mode),
                                 stream_ptr(E.device)), "yr_ngcf_layer_bwd")
     return dW1, dW2
 
 
 # The graph travels as an integer handle (custom ops take tensors and scalars only): data.graph.LaplacianCSR objects are
 # registered by identity and live as long as the model that owns them.
-_CSR_REGISTRY = {}
+import weakref
+
+_CSR_REGISTRY = weakref.WeakValueDictionary()      # the owning model keeps the CSR alive; the registry never does
 
 
 def _csr_handle(csr) -> int:
@@ -205,51 +207,53 @@ def _csr_handle(csr) -> int:
 
 @custom_op("yelprec::ngcf_layer", mutates_args=(), device_types="cuda")
 def _op_ngcf_layer(E: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, csr_handle: int,
-                   slope: float) -> Tuple[torch.Tensor, torch.Tensor]:
+                   slope: float, dense_mode: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """NGCF.embedding_propagation (models/ngcf.py:60-72) -> yr_ngcf_layer_fwd. Returns (E_next, L E)."""
     Ed, W1d, W2d = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
-    return ngcf_layer_fwd(_CSR_REGISTRY[csr_handle], Ed, W1d, W2d, slope)
+    return ngcf_layer_fwd(_CSR_REGISTRY[csr_handle], Ed, W1d, W2d, slope, dense_mode)
 
 
 @_op_ngcf_layer.register_fake
-def _(E, W1, W2, csr_handle, slope):
+def _(E, W1, W2, csr_handle, slope, dense_mode):
     return torch.empty_like(E), torch.empty_like(E)
 
 
 @custom_op("yelprec::ngcf_layer_bwd", mutates_args=(), device_types="cuda")
 def _op_ngcf_layer_bwd(E: torch.Tensor, LE: torch.Tensor, En: torch.Tensor, Gn: torch.Tensor, W1: torch.Tensor,
-                       W2: torch.Tensor, csr_handle: int, slope: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                       W2: torch.Tensor, csr_handle: int, slope: float,
+                       dense_mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     E, W1, W2 = E.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
     G = torch.zeros_like(E)
-    dW1, dW2 = ngcf_layer_bwd(_CSR_REGISTRY[csr_handle], E, LE.contiguous(), En.contiguous(), Gn.contiguous(), W1, W2, G, slope)
+    dW1, dW2 = ngcf_layer_bwd(_CSR_REGISTRY[csr_handle], E, LE.contiguous(), En.contiguous(), Gn.contiguous(), W1, W2, G, slope,
+                              dense_mode)
     return G, dW1, dW2
 
 
 @_op_ngcf_layer_bwd.register_fake
-def _(E, LE, En, Gn, W1, W2, csr_handle, slope):
+def _(E, LE, En, Gn, W1, W2, csr_handle, slope, dense_mode):
     return torch.empty_like(E), torch.empty_like(W1), torch.empty_like(W2)
 
 
 def _ngcf_layer_setup(ctx, inputs, output):
-    E, W1, W2, csr_handle, slope = inputs
+    E, W1, W2, csr_handle, slope, dense_mode = inputs
     En, LE = output
     ctx.save_for_backward(E, LE, En, W1, W2)
-    ctx.csr_handle, ctx.slope = csr_handle, slope
+    ctx.csr_handle, ctx.slope, ctx.dense_mode = csr_handle, slope, dense_mode
 
 
 def _ngcf_layer_backward(ctx, gEn, gLE):
     E, LE, En, W1, W2 = ctx.saved_tensors
-    G, dW1, dW2 = _op_ngcf_layer_bwd(E, LE, En, gEn, W1, W2, ctx.csr_handle, ctx.slope)
-    return G, dW1, dW2, None, None
+    G, dW1, dW2 = _op_ngcf_layer_bwd(E, LE, En, gEn, W1, W2, ctx.csr_handle, ctx.slope, ctx.dense_mode)
+    return G, dW1, dW2, None, None, None
 
 
 _op_ngcf_layer.register_autograd(_ngcf_layer_backward, setup_context=_ngcf_layer_setup)
 
 
-def ngcf_layer(E, W1, W2, csr, slope=0.01):
+def ngcf_layer(E, W1, W2, csr, slope=0.01, dense_mode: int = _cabi.YR_DENSE_TC_FWD):
     if not E.is_cuda:
         raise YelprecError("NGCF.embedding_propagation: expected CUDA tensors (no CPU fallback)")
-    return _op_ngcf_layer(E, W1, W2, _csr_handle(csr), float(slope))[0]
+    return _op_ngcf_layer(E, W1, W2, _csr_handle(csr), float(slope), int(dense_mode))[0]
 
 
 def dense_opt_step(p, g, m, v, opt: _cabi.YrOpt):

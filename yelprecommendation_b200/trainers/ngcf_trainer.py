@@ -53,12 +53,13 @@ class NGCFTrainer(BaseTrainer):
         dev = self.device
         # the ctypes struct only holds pointers: rebuild it when one of them changed (load_state_dict, new optimizer state)
         key = (m.embedding.weight.data_ptr(), tuple(w.weight.data_ptr() for w in m.W1), tuple(w.weight.data_ptr() for w in m.W2),
-               id(self.laplacian_matrix), self._bufs is not None and self._bufs["E0_ptr"])
+               id(self.laplacian_matrix), self._bufs is not None and self._bufs["E0_ptr"],
+               int(m.dense_mode), int(getattr(self.cfg, "ngcf_top_rows_mode", 1)))
         hit = getattr(self, "_st_cache", None)
         if hit is not None and hit[0] == key:
             return hit[1], self._bufs
         st, b = self._build_state()
-        key = key[:4] + (b["E0_ptr"],)
+        key = key[:4] + (b["E0_ptr"],) + key[5:]
         self._st_cache = (key, st)
         return st, b
 
@@ -112,6 +113,8 @@ class NGCFTrainer(BaseTrainer):
         st.loss, st.err = p(b["loss"]), p(b["err"])
         st.row_flag, st.row_list, st.row_count = p(b["row_flag"]), p(b["row_list"]), p(b["row_count"])
         st.row_list_cap = b["row_list"].numel()
+        st.dense_mode = int(m.dense_mode)
+        st.top_rows_mode = int(getattr(self.cfg, "ngcf_top_rows_mode", 1))
         return st, b
 
     def _get_stager(self, dataloader) -> BatchStager:

@@ -44,6 +44,7 @@ class CabiNgcfShardKernels:
         self.device = device
         self.lib = _cabi.load()
         self._ws = None
+        self.dense_mode = _cabi.YR_DENSE_TC_FWD
 
     def _st(self):
         return _cabi.stream_ptr(self.device)
@@ -57,7 +58,8 @@ class CabiNgcfShardKernels:
     def dense_fwd(self, E, LE, W1, W2, out):
         d = E.shape[1]
         _cabi.check(self.lib.yr_ngcf_dense_fwd(d, E.shape[0], _cabi.dptr(E, F32), _cabi.dptr(LE, F32), _cabi.dptr(W1, F32),
-                                               _cabi.dptr(W2, F32), _SLOPE, _cabi.dptr(out, F32), self._st()), "yr_ngcf_dense_fwd")
+                                               _cabi.dptr(W2, F32), _SLOPE, _cabi.dptr(out, F32), self.dense_mode, self._st()),
+                    "yr_ngcf_dense_fwd")
 
     def dense_bwd(self, E, LE, En, Gn, W1, W2, G, T, dW1, dW2):
         d = E.shape[1]
@@ -67,7 +69,7 @@ class CabiNgcfShardKernels:
         p = _cabi.dptr
         _cabi.check(self.lib.yr_ngcf_dense_bwd(d, E.shape[0], p(E, F32), p(LE, F32), p(En, F32), p(Gn, F32), p(W1, F32),
                                                p(W2, F32), _SLOPE, p(G, F32), p(T, F32), p(dW1, F32), p(dW2, F32),
-                                               p(self._ws), nbytes, self._st()), "yr_ngcf_dense_bwd")
+                                               p(self._ws), nbytes, self.dense_mode, self._st()), "yr_ngcf_dense_bwd")
 
     def gather_rows(self, T, lo, hi, total, ids, R, col_off, err):
         """R[:, col_off : col_off + d] = T[ids - lo] for owned ids, zeros elsewhere. R: [n x ld] fp32."""
