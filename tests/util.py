@@ -73,22 +73,3 @@ def assert_adam_close(a, b, what="", touched=0):
     allowed = max(10, 1e-5 * d.size, 2e-5 * touched) + 2 * row
     assert (d > RTOL * scale).sum() <= allowed, (what, int((d > RTOL * scale).sum()), allowed)
     assert d.max() <= 1e-2 * scale, (what, d.max() / scale)
-
-
-def topk_agreement(ours, ref, scores_for_row=None, tol=2e-6):
-    """Rows where the top-K id lists differ; a row is 'explained' if the reference's own scores of the swapped
-    items are within fp32 reduction noise of each other (tie order is NumPy's in the reference, quirk Q5)."""
-    diff = [r for r in range(len(ref)) if not np.array_equal(ours[r], ref[r])]
-    unexplained = []
-    for r in diff:
-        if scores_for_row is None:
-            unexplained.append(r)
-            continue
-        s = scores_for_row(r)
-        a, b = np.asarray(ours[r]), np.asarray(ref[r])
-        ok = sorted(a.tolist()) == sorted(b.tolist()) or True
-        sa, sb = s[a], s[b]
-        scale = max(np.abs(sb).max(), 1e-30)
-        if not (np.abs(sa - sb).max() / scale <= tol and ok):
-            unexplained.append(r)
-    return diff, unexplained

@@ -839,9 +839,11 @@ extern "C" int yr_ngcf_train_step(const yr_ngcf_state* st, const yr_opt* opt, fl
   return yr_ngcf_train_step_ex(st, opt, slope, uid, pos, neg, B, step_loss, 0, stream);
 }
 
-extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
-                                     const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
-                                     float* step_loss, int prefix_done, yr_stream stream) {
+// *rows_armed is true while row_flag / row_list / row_count hold the current batch (set after touched_rows_kernel,
+// cleared once the re-arming kernels are enqueued): the wrapper below re-arms them on every early error return.
+static int train_step_body(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                           const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                           float* step_loss, int prefix_done, yr_stream stream, bool* rows_armed) {
   int rc = ngcf_state_ok(st);
   if (rc) return rc;
   if (prefix_done < 0 || prefix_done > st->n_layers) return YR_ERR_BAD_ARG;
@@ -873,6 +875,7 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
     touched_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, ms>>>(uid, pos, neg, B, st->nU, st->nI, st->row_flag,
                                                                         st->row_list, st->row_count);
     YR_CHECK_LAUNCH();
+    *rows_armed = true;
   }
   if (side) YR_CUDA(cudaEventRecord(side->join, side->stream));
   if (rows_path && fwd_tc(st->dense_mode)) {
@@ -917,6 +920,7 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
       untouch_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, us>>>(st->row_flag, st->row_list, st->row_count);
       YR_CHECK_LAUNCH();
       YR_CUDA(cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), us));
+      *rows_armed = false;
       continue;
     }
     // dense backward, then the reduction of its dW partials on the side stream underneath the transposed SpMM
@@ -957,6 +961,25 @@ extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt,
     if (rc) return rc;
   }
   return YR_OK;
+}
+
+extern "C" int yr_ngcf_train_step_ex(const yr_ngcf_state* st, const yr_opt* opt, float slope,
+                                     const int64_t* uid, const int64_t* pos, const int64_t* neg, int64_t B,
+                                     float* step_loss, int prefix_done, yr_stream stream) {
+  bool rows_armed = false;
+  const int rc = train_step_body(st, opt, slope, uid, pos, neg, B, step_loss, prefix_done, stream, &rows_armed);
+  if (rc == YR_OK) return rc;
+  // Error exit in the middle of a step: join the helper stream and re-arm the row scratch, so that a later step does
+  // not find rows still flagged (atomicExch would return 1 and those rows would silently drop out of row_list).
+  cudaStream_t s = (cudaStream_t)stream;
+  if (SideStream* side = side_stream()) {
+    if (cudaEventRecord(side->join, side->stream) == cudaSuccess) cudaStreamWaitEvent(s, side->join, 0);
+  }
+  if (rows_armed && st && st->row_flag && st->row_list && st->row_count) {
+    untouch_rows_kernel<<<(unsigned)((3 * B + 255) / 256), 256, 0, s>>>(st->row_flag, st->row_list, st->row_count);
+    cudaMemsetAsync(st->row_count, 0, sizeof(int32_t), s);
+  }
+  return rc;
 }
 
 extern "C" int yr_ngcf_concat(const float* const* E_layers, int n_layers, int64_t n, int d, float* out,

@@ -319,6 +319,23 @@ class DeviceEvalCSR:
         self.inv_log2 = t(inv_log2_table(K))
         self.K = K
 
+    @classmethod
+    def from_device(cls, eval_uid, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq, K: int) -> "DeviceEvalCSR":
+        """Built from tensors that already live on the device (int64 uid, int32 CSR pieces; mask ids ascending per row,
+        act ids in their original order, act_nuniq = |set(row)|)."""
+        from .data.graph import inv_log2_table
+        out = object.__new__(cls)
+        dev = eval_uid.device
+        pad = lambda t: t.contiguous() if t.numel() else torch.zeros(1, dtype=I32, device=dev)
+        out.n_eval = int(eval_uid.numel())
+        out.eval_uid = eval_uid.to(I64).contiguous()
+        out.mask_ptr, out.mask_idx = mask_ptr.to(I32).contiguous(), pad(mask_idx.to(I32))
+        out.act_ptr, out.act_idx = act_ptr.to(I32).contiguous(), pad(act_idx.to(I32))
+        out.act_nuniq = pad(act_nuniq.to(I32))
+        out.inv_log2 = torch.from_numpy(np.ascontiguousarray(inv_log2_table(K))).to(dev)
+        out.K = K
+        return out
+
     def slice(self, lo: int, hi: int) -> "DeviceEvalCSR":
         """Rows [lo, hi) — user sharding across GPUs (no communication until the metric sums)."""
         out = object.__new__(DeviceEvalCSR)

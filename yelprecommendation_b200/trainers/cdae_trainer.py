@@ -16,7 +16,6 @@ import numpy as np
 import torch
 
 from .. import _cabi, ops
-from ..data.graph import EvalCSR
 from ..loss import NSBCELoss
 from ..models.cdae import CDAE
 from .base_trainer import BaseTrainer, FusedOptimizer, logger
@@ -113,26 +112,46 @@ class CDAETrainer(BaseTrainer):
         return self._loss_sum()
 
     # ------------------------------------------------------------------------------------------
-    def _rank(self, batches, actual_key):
-        """Top-K + metrics over all rows of a dataloader: hidden activations per batch, one fused ranking pass."""
+    # ---- ranking: streamed batch by batch (the reference streams too, cdae_trainer.py:123-144) -----------------------
+    def _rank_begin(self):
+        return {"z": [], "mask": [], "act": [], "n": 0}
+
+    @staticmethod
+    def _rows_of(mask: torch.Tensor):
+        """Dense multi-hot [B x nI] (already on the device) -> (count per row [B] int64, column ids int32, row-major)."""
+        nz = mask != 0
+        return nz.sum(dim=1), nz.nonzero(as_tuple=False)[:, 1].to(I32)
+
+    def _rank_add(self, acc, user_id, x_dev: torch.Tensor, actual_dev: torch.Tensor) -> None:
+        """Hidden activations of one batch + the CSR pieces of its mask / ground-truth rows; nothing of size
+        B x num_items outlives the batch."""
         m = self.model
-        zs, mask_rows, act_rows = [], [], []
-        for data in batches:
-            x = data["input_mask"]
-            zs.append(m.hidden(data["user_id"], x, None, ldz=_ldz(m.hidden_size)))
-            xn, an = x.cpu().numpy(), data[actual_key].cpu().numpy()
-            mask_rows.extend(np.nonzero(r)[0] for r in xn)
-            act_rows.extend(np.nonzero(r)[0] for r in an)
-        Z = torch.cat(zs)
-        n = Z.shape[0]
-        V = torch.zeros(self.num_items, _ldz(m.hidden_size), device=self.device, dtype=F32)
+        acc["z"].append(m.hidden(user_id, x_dev, None, ldz=_ldz(m.hidden_size)))
+        acc["mask"].append(self._rows_of(x_dev))
+        acc["act"].append(self._rows_of(actual_dev))
+        acc["n"] += int(x_dev.shape[0])
+
+    def _rank_finish(self, acc):
+        """One fused top-K + metrics pass over every accumulated row."""
+        m, n, dev = self.model, acc["n"], self.device
+        if n == 0:
+            raise ZeroDivisionError("division by zero")       # what metric.py does on an empty evaluation set
+        Z = torch.cat(acc["z"])
+        V = torch.zeros(self.num_items, _ldz(m.hidden_size), device=dev, dtype=F32)
         V[:, : m.hidden_size] = m.output_layer.weight.data
         V[:, m.hidden_size] = m.output_layer.bias.data
-        cat = lambda rows: np.concatenate(rows).astype(np.int32) if n else np.zeros(0, np.int32)
-        ptr = lambda rows: np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
-        csr = EvalCSR(np.arange(n, dtype=np.int64), ptr(mask_rows), cat(mask_rows), ptr(act_rows), cat(act_rows),
-                      np.array([len(r) for r in act_rows], dtype=np.int32))
-        ecsr = ops.DeviceEvalCSR(csr, self.device, int(self.cfg.top_n))
+
+        def csr(parts):
+            cnt = torch.cat([c for c, _ in parts])
+            idx = torch.cat([i for _, i in parts])
+            ptr = torch.zeros(n + 1, device=dev, dtype=I64)
+            ptr[1:] = torch.cumsum(cnt, 0)
+            return ptr.to(I32), idx, cnt.to(I32)
+
+        mask_ptr, mask_idx, _ = csr(acc["mask"])
+        act_ptr, act_idx, act_cnt = csr(acc["act"])
+        ecsr = ops.DeviceEvalCSR.from_device(torch.arange(n, device=dev, dtype=I64), mask_ptr, mask_idx, act_ptr, act_idx,
+                                             act_cnt, int(self.cfg.top_n))
         topk, _, _, sums, err = ops.eval_topk_metrics(Z, V, ecsr)
         self.last_topk = topk
         sums_h = sums.cpu()
@@ -141,18 +160,23 @@ class CDAETrainer(BaseTrainer):
     def validate(self, valid_dataloader) -> tuple:
         self.model.eval()
         self._state()[0]["loss"].zero_()
-        batches = list(valid_dataloader)
-        for data in batches:
+        acc = self._rank_begin()
+        for data in valid_dataloader:                         # one pass: loss step + hidden activations per batch
             x = data["input_mask"].to(self.device, dtype=F32)
-            tgt = x + data["valid_mask"].to(self.device, dtype=F32)          # train + valid 1 (cdae_trainer.py:67)
-            self._step(data["user_id"], x, None, tgt, data["negative_mask"], False)
-        valid_loss = self._loss_sum() if batches else 0
-        p, r, mp, nd = self._rank(batches, "valid_mask")
+            vm = data["valid_mask"].to(self.device, dtype=F32)
+            self._step(data["user_id"], x, None, x + vm, data["negative_mask"], False)   # train + valid 1 (cdae_trainer.py:67)
+            self._rank_add(acc, data["user_id"], x, vm)
+        valid_loss = self._loss_sum() if acc["n"] else 0
+        p, r, mp, nd = self._rank_finish(acc)
         return (valid_loss, p, r, mp, nd)
 
     def evaluate(self, test_dataloader) -> tuple:
         self.model.eval()
-        result = self._rank(list(test_dataloader), "test_mask")
+        acc = self._rank_begin()
+        for data in test_dataloader:
+            x = data["input_mask"].to(self.device, dtype=F32)
+            self._rank_add(acc, data["user_id"], x, data["test_mask"].to(self.device, dtype=F32))
+        result = self._rank_finish(acc)
         k = self.cfg.top_n
         logger.info(f"[Trainer] Test > precision@{k} : {result[0]:.4f} / Recall@{k}: {result[1]:.4f} / "
                     f"MAP@{k}: {result[2]:.4f} / NDCG@{k}: {result[3]:.4f}")

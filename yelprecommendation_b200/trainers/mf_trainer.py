@@ -148,13 +148,14 @@ class MFTrainer(BaseTrainer):
 
     # ------------------------------------------------------------------------------------------
     def _eval_csr(self, eval_data) -> ops.DeviceEvalCSR:
-        key = (id(eval_data), getattr(eval_data, "shape", None), int(self.cfg.top_n))
-        hit = self._eval_cache.get(key)
-        if hit is None:
+        # the cache entry holds the frame itself and is compared by identity (an id() alone can be recycled); a frame
+        # that is mutated in place between calls must be passed as a new object
+        hit = self._eval_cache.get("entry")
+        if hit is None or hit[0] is not eval_data or hit[1] != int(self.cfg.top_n):
             csr = eval_data if hasattr(eval_data, "eval_uid") else eval_csr_from_frame(eval_data, self.num_items)
-            hit = ops.DeviceEvalCSR(csr, self.device, int(self.cfg.top_n))
-            self._eval_cache = {key: hit}
-        return hit
+            hit = (eval_data, int(self.cfg.top_n), ops.DeviceEvalCSR(csr, self.device, int(self.cfg.top_n)))
+            self._eval_cache = {"entry": hit}
+        return hit[2]
 
     def evaluate(self, eval_data, mode="valid") -> tuple:
         """eval_data: the reference's DataFrame (index user_id, list columns pos_items / mask_items) or a prebuilt

@@ -181,12 +181,11 @@ class NGCFTrainer(BaseTrainer):
         if prepropagate_state is not None and self.model.training:
             self._prepropagate(prepropagate_state)
         h[2].synchronize()
-        reset = False
         v = float(h[0][0])
         if int(h[1][0]) != 0:
+            # like the other fused trainers, the step that saw the bad id has already been applied (the reference raises
+            # before its update); INTEGRATION.md states this difference
             ops._raise_if_err(b["err"], "NGCFTrainer")
-        if reset:
-            b["loss"].zero_()
         return v
 
     def train(self, train_dataloader) -> float:
@@ -246,13 +245,13 @@ class NGCFTrainer(BaseTrainer):
             rows = np.random.randint(eval_data.shape[0], size=100)
             sub = eval_data.iloc[rows, :]
             return ops.DeviceEvalCSR(eval_csr_from_frame(sub, self.num_items), self.device, int(self.cfg.top_n))
-        key = (id(eval_data), getattr(eval_data, "shape", None), int(self.cfg.top_n))
-        hit = self._eval_cache.get(key)
-        if hit is None:
+        # the cache entry holds the frame itself and is compared by identity (an id() alone can be recycled)
+        hit = self._eval_cache.get("entry")
+        if hit is None or hit[0] is not eval_data or hit[1] != int(self.cfg.top_n):
             csr = eval_data if isinstance(eval_data, EvalCSR) else eval_csr_from_frame(eval_data, self.num_items)
-            hit = ops.DeviceEvalCSR(csr, self.device, int(self.cfg.top_n))
-            self._eval_cache = {key: hit}
-        return hit
+            hit = (eval_data, int(self.cfg.top_n), ops.DeviceEvalCSR(csr, self.device, int(self.cfg.top_n)))
+            self._eval_cache = {"entry": hit}
+        return hit[2]
 
     def evaluate(self, eval_data, mode="valid") -> tuple:
         self.model.eval()
