@@ -73,26 +73,33 @@ int yr_bpr_loss_fwd(const float* pos, const float* neg, int64_t B, float* loss, 
 int yr_bpr_loss_bwd(const float* pos, const float* neg, int64_t B, const float* gloss,
                     float* gpos, float* gneg, yr_stream stream);
 
-/* State of the fused trainer: parameters, optimizer moments and the sparse-accumulate scratch.
- * gU/gV/flagU/flagV must be all-zero on first use; every call leaves them all-zero again. */
+/* State of the fused trainer: parameters, optimizer moments and scratch.
+ * flagU / flagV must be all-zero on first use; every call leaves them all-zero again. */
 typedef struct yr_mf_state {
   float *U, *V;             /* [nU x d], [nI x d] */
   float *mU, *vU, *mV, *vV; /* Adam exp_avg / exp_avg_sq, same shapes (unused for SGD, may be NULL) */
-  float *gU, *gV;           /* gradient scratch rows (only touched rows ever become non-zero) */
-  int32_t *flagU, *flagV;   /* [nU], [nI] touched flags */
-  int32_t *rows;            /* [3*B] unique touched rows of the current step */
-  int32_t *counters;        /* 64-byte block, 8-byte aligned, zero on first use: 8 x int32 counters + 2 x double loss accumulators */
+  int32_t *flagU, *flagV;   /* [nU], [nI]: row -> position of its segment in the step's sorted id lists (dense-semantics steps) */
+  int32_t *counters;        /* 64-byte block, zero on first use (parity of the next step) */
   int32_t *err;             /* [1] sticky bad-id flag (reference: IndexError from nn.Embedding) */
+  void *ws; size_t ws_bytes;/* >= yr_bpr_mf_train_ws_bytes(n_triples, B, d) of the call: sorted id lists of every batch,
+                               per-triple gradient rows of one step, per-CTA loss partials */
   int64_t nU, nI;
   int32_t d;
+  int32_t deterministic;    /* != 0: plain-SGD steps also take the ordered (atomics-free) path, see below */
 } yr_mf_state;
 
 /* MFTrainer.train hot loop (trainers/mf_trainer.py:100-116) for `n_triples` pre-collated triples cut
  * into consecutive batches of B (last one short, as DataLoader keeps it, train.py:76): per batch
  * forward x2, BPR loss, gradient with duplicate rows summed, ONE optimizer update per row
  * (SGD / Adam / AdamW with torch dense semantics), all inside one persistent cooperative kernel.
+ * Summation order of duplicate rows = the reference's on the CPU: per embedding call sequentially in batch order
+ * (embedding_dense_backward), then the two calls added (AccumulateGrad); the loss is a fixed-order double sum.
+ * Results are bit-identical from run to run and to oracle/yr_oracle.c — except plain SGD (wd = 0) with
+ * B <= resident warps and deterministic == 0, which keeps gradients in registers and applies them as vector REDs
+ * (duplicates summed in arrival order, ulp-level differences).
  * loss_sum (double, device) += sum over batches of the batch-mean loss (quirk Q1);
  * step_loss (float, device, may be NULL) receives every batch mean. */
+size_t yr_bpr_mf_train_ws_bytes(int64_t n_triples, int32_t B, int d);
 int yr_bpr_mf_train(const yr_mf_state* st, const yr_opt* opt,
                     const int64_t* uid, const int64_t* pos, const int64_t* neg,
                     int64_t n_triples, int32_t B, double* loss_sum, float* step_loss,

@@ -34,11 +34,44 @@ void orc_mf_score(const float* U, const float* V, int d, const int64_t* uid, con
   for (int64_t b = 0; b < B; ++b) out[b] = dot_chain(U + uid[b] * d, V + iid[b] * d, d);
 }
 
-/* ---- BPRLoss.forward, loss.py:25-27; logsigmoid as ATen computes it ------------------------------ */
-static float neg_logsigmoid(float x) { return log1pf(expf(-fabsf(x))) - fminf(x, 0.f); }
+/* ---- BPRLoss.forward, loss.py:25-27; logsigmoid as ATen computes it ------------------------------
+ * exp / log1p are taken CORRECTLY ROUNDED to fp32 (double evaluation, one rounding): the one definition the CUDA
+ * kernels (common.cuh: exp_cr / log1p_cr) and this file can share bit for bit. glibc's expf, CUDA's expf and ATen's
+ * Sleef kernels each differ from it (and from each other) by at most 1 ulp. */
+static float exp_cr(float x) { return (float)exp((double)x); }
+static float log1p_cr(float x) { return (float)log1p((double)x); }
+static float neg_logsigmoid(float x) { return log1p_cr(exp_cr(-fabsf(x))) - fminf(x, 0.f); }
 static float neg_logsigmoid_grad(float x) {
-  const float z = expf(-fabsf(x));
-  return -((x < 0.f) ? 1.f - z / (1.f + z) : z / (1.f + z));
+  const float z = exp_cr(-fabsf(x));
+  const float q = z / (1.f + z);
+  return -((x < 0.f) ? 1.f - q : q);
+}
+
+/* The trainers' row dot product as the kernels form it (common.cuh: dot_partial + warp_sum): lane l of a warp owns
+ * d/32 elements of the row (d <= 64: the contiguous elements l*d/32 ..; d >= 128: the float4 number j*32 + l of every
+ * 128-float4 group j), runs one fma chain over them, and the 32 partials are combined by the xor butterfly
+ * 16, 8, 4, 2, 1 (every lane ends with the same value). d must be a multiple of 32. */
+static float dot_warp(const float* a, const float* b, int d) {
+  float s[32], t[32];
+  const int vpl = d / 32;
+  for (int l = 0; l < 32; ++l) {
+    float acc = 0.f;
+    if (vpl <= 2) {
+      for (int j = 0; j < vpl; ++j) acc = fmaf(a[l * vpl + j], b[l * vpl + j], acc);
+    } else {
+      for (int j = 0; j < vpl / 4; ++j)
+        for (int c = 0; c < 4; ++c) {
+          const int k = 4 * (j * 32 + l) + c;
+          acc = fmaf(a[k], b[k], acc);
+        }
+    }
+    s[l] = acc;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) t[l] = s[l] + s[l ^ o];
+    memcpy(s, t, sizeof(s));
+  }
+  return s[0];
 }
 
 float orc_bpr_loss(const float* pos, const float* neg, int64_t B) {
@@ -81,29 +114,40 @@ void orc_dense_opt_step(float* p, const float* g_in, float* m, float* v, int64_t
   }
 }
 
-/* ---- MFTrainer.train, one batch (trainers/mf_trainer.py:104-114): dense grads like autograd -------- */
-/* gU/gV: caller-provided zeroed dense scratch [nU*d],[nI*d]; returns the batch-mean loss. */
+/* ---- MFTrainer.train, one batch (trainers/mf_trainer.py:104-114): dense grads like autograd --------
+ * Gradient of a table row = what torch's CPU autograd produces: every embedding CALL (pos_pred = model(u, pos),
+ * neg_pred = model(u, neg), trainers/mf_trainer.py:106-107) yields a dense gradient in which the rows of the batch are
+ * summed sequentially in batch order (ATen embedding_dense_backward_cpu), and AccumulateGrad adds the two calls.
+ * The row products are single rounded multiplications (g*p, -(g*n), g*u, -(g*u)).
+ * gU/gV: caller-provided zeroed dense scratch [nU*d],[nI*d] (first call's part); the second call's part uses a
+ * private scratch. Returns the batch-mean loss. */
 float orc_mf_train_step(float* U, float* V, int64_t nU, int64_t nI, int d, float* mU, float* vU, float* mV,
                         float* vV, float* gU, float* gV, const int64_t* uid, const int64_t* pos,
                         const int64_t* neg, int64_t B, const orc_opt* o) {
   double lacc = 0.0;
   const float inv_b = 1.f / (float)B;
+  float* gU2 = (float*)calloc((size_t)(nU * d), sizeof(float));
+  float* gV2 = (float*)calloc((size_t)(nI * d), sizeof(float));
   for (int64_t b = 0; b < B; ++b) {
     const float* u = U + uid[b] * d;
     const float* p = V + pos[b] * d;
     const float* n = V + neg[b] * d;
-    const float x = dot_chain(u, p, d) - dot_chain(u, n, d);
+    const float x = ((d % 32) == 0 ? dot_warp(u, p, d) : dot_chain(u, p, d)) -
+                    ((d % 32) == 0 ? dot_warp(u, n, d) : dot_chain(u, n, d));
     lacc += (double)neg_logsigmoid(x);
     const float g = neg_logsigmoid_grad(x) * inv_b;
-    float* gu = gU + uid[b] * d;
-    float* gp = gV + pos[b] * d;
-    float* gn = gV + neg[b] * d;
+    float* gu = gU + uid[b] * d;  float* gu2 = gU2 + uid[b] * d;
+    float* gp = gV + pos[b] * d;  float* gn2 = gV2 + neg[b] * d;
     for (int k = 0; k < d; ++k) {
-      gu[k] += g * p[k] - g * n[k]; /* user row gathered twice (Q2) */
-      gp[k] += g * u[k];
-      gn[k] -= g * u[k];
+      gu[k] = gu[k] + g * p[k];      /* positive call */
+      gu2[k] = gu2[k] - g * n[k];    /* negative call: rows -(g*n), user row gathered twice (Q2) */
+      gp[k] = gp[k] + g * u[k];
+      gn2[k] = gn2[k] - g * u[k];
     }
   }
+  for (int64_t i = 0; i < nU * d; ++i) gU[i] = gU[i] + gU2[i];
+  for (int64_t i = 0; i < nI * d; ++i) gV[i] = gV[i] + gV2[i];
+  free(gU2); free(gV2);
   orc_dense_opt_step(U, gU, mU, vU, nU * d, o);
   orc_dense_opt_step(V, gV, mV, vV, nI * d, o);
   memset(gU, 0, sizeof(float) * (size_t)(nU * d));

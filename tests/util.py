@@ -54,6 +54,20 @@ def rel_fro(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+def assert_update_close(a, b, p0, what="", tol=1e-4):
+    """Parity of the UPDATE (p - p0), not of the table: max |(a - p0) - (b - p0)| <= tol * max |b - p0|. An SGD step moves a
+    table by ~1e-4 of its scale, so a table-relative 1e-5 resolves the update only to ~5 %; this resolves it to 1e-4 (plus
+    the one ulp of the table value that fp32 storage itself costs)."""
+    b32 = np.asarray(b, dtype=np.float32)
+    a, b, p0 = (np.asarray(x, dtype=np.float64) for x in (a, b, p0))
+    den = max(np.abs(b - p0).max(), 1e-30)
+    # both tables are fp32: one ulp of the TABLE value (6e-8 |p|, i.e. ~3e-4 of such an update) is below what either side can
+    # represent, so it is taken off before the update-relative bar applies
+    excess = np.maximum(np.abs(a - b) - np.spacing(np.abs(b32)).astype(np.float64), 0.0)
+    err = excess.max() / den
+    assert err <= tol, (what, err)
+
+
 def assert_adam_close(a, b, what="", touched=0):
     """Adam divides by sqrt(v)+eps: an element whose gradient is below eps=1e-8 (a cancelling g*p - g*n) turns a
     1-ulp difference in the loss scalar or in the order duplicate rows are summed (atomics: varies run to run) into a

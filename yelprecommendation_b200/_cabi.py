@@ -19,7 +19,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB
 SYMBOLS = (
     "yr_version", "yr_device_sm_count",
     "yr_mf_score", "yr_mf_score_bwd", "yr_bpr_loss_fwd", "yr_bpr_loss_bwd",
-    "yr_bpr_mf_train", "yr_bpr_mf_validate",
+    "yr_bpr_mf_train_ws_bytes", "yr_bpr_mf_train", "yr_bpr_mf_validate",
     "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
@@ -51,10 +51,10 @@ class YrOpt(C.Structure):
 class YrMfState(C.Structure):
     _fields_ = [("U", C.c_void_p), ("V", C.c_void_p),
                 ("mU", C.c_void_p), ("vU", C.c_void_p), ("mV", C.c_void_p), ("vV", C.c_void_p),
-                ("gU", C.c_void_p), ("gV", C.c_void_p),
                 ("flagU", C.c_void_p), ("flagV", C.c_void_p),
-                ("rows", C.c_void_p), ("counters", C.c_void_p), ("err", C.c_void_p),
-                ("nU", C.c_int64), ("nI", C.c_int64), ("d", C.c_int32)]
+                ("counters", C.c_void_p), ("err", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+                ("nU", C.c_int64), ("nI", C.c_int64), ("d", C.c_int32), ("deterministic", C.c_int32)]
 
 
 YR_SPMM_CHUNK = 128
@@ -128,6 +128,7 @@ def load() -> C.CDLL:
         "yr_mf_score_bwd": (C.c_int, [p, p, i64, i64, i32, p, p, i64, p, p, p, p]),
         "yr_bpr_loss_fwd": (C.c_int, [p, p, i64, p, p]),
         "yr_bpr_loss_bwd": (C.c_int, [p, p, i64, p, p, p, p]),
+        "yr_bpr_mf_train_ws_bytes": (sz, [i64, i32, i32]),
         "yr_bpr_mf_train": (C.c_int, [C.POINTER(YrMfState), C.POINTER(YrOpt), p, p, p, i64, i32, p, p, p]),
         "yr_bpr_mf_validate": (C.c_int, [p, p, i64, i64, i32, p, p, p, i64, i32, p, p, p, p]),
         "yr_spmm_plan_size_h": (C.c_int, [p, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

@@ -88,6 +88,25 @@ __device__ __forceinline__ Row<VPL> ld_row(const float* __restrict__ row, int la
   return r;
 }
 
+// same slices through L2 only (ld.global.cg): rows other SMs rewrite every step inside one persistent kernel
+template <int VPL>
+__device__ __forceinline__ Row<VPL> ld_row_cg(const float* __restrict__ row, int lane) {
+  Row<VPL> r;
+  if constexpr (VPL == 1) {
+    r.x[0] = __ldcg(row + lane);
+  } else if constexpr (VPL == 2) {
+    float2 t = __ldcg(reinterpret_cast<const float2*>(row) + lane);
+    r.x[0] = t.x; r.x[1] = t.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VPL / 4; ++j) {
+      float4 t = __ldcg(reinterpret_cast<const float4*>(row) + j * 32 + lane);
+      r.x[4 * j + 0] = t.x; r.x[4 * j + 1] = t.y; r.x[4 * j + 2] = t.z; r.x[4 * j + 3] = t.w;
+    }
+  }
+  return r;
+}
+
 template <int VPL>
 __device__ __forceinline__ void st_row(float* __restrict__ row, int lane, const Row<VPL>& r) {
   if constexpr (VPL == 1) {
@@ -125,15 +144,23 @@ __device__ __forceinline__ float dot_partial(const Row<VPL>& a, const Row<VPL>& 
   return s;
 }
 
+// exp / log1p as CORRECTLY ROUNDED fp32 (double-precision evaluation rounded once): the one definition the device and the
+// CPU oracle can share bit for bit — libm's expf, CUDA's expf and ATen's Sleef kernels all differ from each other in
+// the last ulp, and under Adam a 1-ulp change of the loss gradient is amplified on elements with |grad| ~ eps
+// (DESIGN.md section 4). Every implementation above is within 1 ulp of this value.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float log1p_cr(float x) { return (float)log1p((double)x); }
+
 // -logsigmoid(x) with torch's formulation: logsigmoid(x) = min(x,0) - log1p(exp(-|x|))
 // (aten/src/ATen/native/cpu/Activation.cpp log_sigmoid_cpu_kernel); loss.py:25-27.
 __device__ __forceinline__ float neg_logsigmoid(float x) {
-  return log1pf(expf(-fabsf(x))) - fminf(x, 0.f);
+  return __fsub_rn(log1p_cr(exp_cr(-fabsf(x))), fminf(x, 0.f));
 }
 // d(-logsigmoid(x))/dx = -sigmoid(-x), in torch's backward formulation.
 __device__ __forceinline__ float neg_logsigmoid_grad(float x) {
-  const float z = expf(-fabsf(x));
-  const float s = (x < 0.f) ? 1.f - z / (1.f + z) : z / (1.f + z);   // sigmoid(-x)
+  const float z = exp_cr(-fabsf(x));
+  const float q = __fdiv_rn(z, __fadd_rn(1.f, z));
+  const float s = (x < 0.f) ? __fsub_rn(1.f, q) : q;   // sigmoid(-x)
   return -s;
 }
 
@@ -164,6 +191,8 @@ __device__ __forceinline__ void opt_scalars_for_step(OptScalars& s, const yr_opt
   s.decay = (float)(1.0 - o.lr * o.weight_decay);
 }
 
+// Every operation is an explicit IEEE round-to-nearest intrinsic (no reliance on the compiler's fma contraction), so the
+// C oracle (oracle/yr_oracle.c, orc_dense_opt_step) reproduces it bit for bit.
 __device__ __forceinline__ void opt_update(const OptScalars& s, float& p, float g, float& m, float& v) {
   if (s.kind == YR_OPT_SGD) {
     if (s.wd != 0.f) g = fmaf(p, s.wd, g);            // grad.add(param, alpha=wd)
@@ -171,15 +200,15 @@ __device__ __forceinline__ void opt_update(const OptScalars& s, float& p, float 
     return;
   }
   if (s.kind == YR_OPT_ADAMW) {
-    p = p * s.decay;                                  // param.mul_(1 - lr*wd)
+    p = __fmul_rn(p, s.decay);                        // param.mul_(1 - lr*wd)
   } else if (s.wd != 0.f) {
     g = fmaf(p, s.wd, g);                             // grad.add(param, alpha=wd)
   }
-  m = fmaf(s.w_lerp, g - m, m);                       // exp_avg.lerp_(grad, 1-beta1)
-  v = v * s.beta2;                                    // exp_avg_sq.mul_(beta2)
-  v = v + (s.omb2 * g) * g;                           //   .addcmul_(grad, grad, value=1-beta2)
-  const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;  // (sqrt(v)/sqrt(bc2)).add_(eps)
-  p = p + (-s.step_size * m) / denom;                 // param.addcdiv_(m, denom, value=-step_size)
+  m = fmaf(s.w_lerp, __fsub_rn(g, m), m);             // exp_avg.lerp_(grad, 1-beta1)
+  v = __fmul_rn(v, s.beta2);                          // exp_avg_sq.mul_(beta2)
+  v = fmaf(__fmul_rn(s.omb2, g), g, v);               //   .addcmul_(grad, grad, value=1-beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);   // (sqrt(v)/sqrt(bc2)).add_(eps)
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s.step_size, m), denom));              // param.addcdiv_(m, denom, value=-step_size)
 }
 
 inline int yr_sm_count() {

@@ -10,6 +10,7 @@
 //
 // At Yelp shape X (17.85 MB) is L2-resident; the 3.12 M gathered rows are 800 MB of L2->SM traffic per SpMM
 // against 61 MB of algorithmic HBM traffic, so this kernel lives on L2 latency / bandwidth, not on HBM.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace yr {
@@ -26,8 +27,54 @@ __device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
   acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
 }
 
+// Last arriver of a split row: left-to-right sum of the row's chunk partials (fixed order whatever the arrival order).
+// Kept out of line: it runs for a handful of rows per launch and must not cost the gather loop its registers.
 template <int D, bool ACC>
-__global__ void __launch_bounds__(256, D <= 64 ? 3 : 2)
+__device__ __noinline__ void spmm_finish_split(const yr_csr& A, float* __restrict__ Y, int row, int split_idx, int sl) {
+  using C = SpmmCfg<D>;
+  constexpr int VPT = C::VPT;
+  const int p0 = A.split_ptr[split_idx], p1 = A.split_ptr[split_idx + 1];
+  const float4* P4 = reinterpret_cast<const float4*>(A.partials);
+  float4 tot[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) tot[v] = __ldcg(P4 + (int64_t)p0 * C::kVec + sl * VPT + v);
+  int p = p0 + 1;
+  for (; p + 8 <= p1; p += 8) {
+    float4 x[8][VPT];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) x[q][v] = __ldcg(P4 + (int64_t)(p + q) * C::kVec + sl * VPT + v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        tot[v].x += x[q][v].x; tot[v].y += x[q][v].y; tot[v].z += x[q][v].z; tot[v].w += x[q][v].w;
+      }
+  }
+  for (; p < p1; ++p) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const float4 x = __ldcg(P4 + (int64_t)p * C::kVec + sl * VPT + v);
+      tot[v].x += x.x; tot[v].y += x.y; tot[v].z += x.z; tot[v].w += x.w;
+    }
+  }
+  float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D);
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    if (ACC) {
+      const float4 y = y4[sl * VPT + v];
+      tot[v].x = y.x + tot[v].x; tot[v].y = y.y + tot[v].y; tot[v].z = y.z + tot[v].z; tot[v].w = y.w + tot[v].w;
+    }
+    y4[sl * VPT + v] = tot[v];
+  }
+}
+
+// THREADS / MINB: CTA size and CTAs per SM the register allocation is bounded for; U: neighbour rows in flight per group;
+// DIRECT: every lane reads the column index / value of a non-zero itself (one broadcast L1 access per group) instead of
+// one coalesced read per LPR non-zeros followed by shuffles. The summation order is the same for every variant.
+template <int D, bool ACC, int THREADS, int MINB, int U, bool DIRECT>
+__global__ void __launch_bounds__(THREADS, MINB)
 spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, const int32_t* __restrict__ row_flag) {
   using C = SpmmCfg<D>;
   constexpr int LPR = C::LPR, VPT = C::VPT, CPW = C::CPW;
@@ -55,36 +102,64 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, 
 #pragma unroll
       for (int v = 0; v < VPT; ++v) acc[v] = reinterpret_cast<const float4*>(Y + (int64_t)row * D)[sl * VPT + v];
     }
-    int maxlen = len;
+    if constexpr (DIRECT) {
+      for (int j0 = 0; j0 < len; j0 += U) {
+        float4 x[U][VPT];
+        float a[U];
+        int cq[U];
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, o));
-    for (int j0 = 0; j0 < maxlen; j0 += LPR) {
-      const int j = j0 + sl;
-      const int cc = (j < len) ? __ldg(A.col + s + j) : -1;
-      const float aa = (j < len) ? __ldg(A.val + s + j) : 0.f;
-#pragma unroll
-      for (int t = 0; t < LPR; t += 8) {
-        if (j0 + t >= maxlen) break;
-        float4 x[8][VPT];
-        float a[8];
-        int cq[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          cq[q] = __shfl_sync(kFull, cc, t + q, LPR);
-          a[q] = __shfl_sync(kFull, aa, t + q, LPR);
+        for (int q = 0; q < U; ++q) {
+          const bool in = j0 + q < len;
+          cq[q] = in ? __ldg(A.col + s + j0 + q) : -1;
+          a[q] = in ? __ldg(A.val + s + j0 + q) : 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < U; ++q) {
           if (cq[q] >= 0) {
 #pragma unroll
             for (int v = 0; v < VPT; ++v) x[q][v] = __ldg(X4 + (int64_t)cq[q] * C::kVec + sl * VPT + v);
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < U; ++q) {
           if (cq[q] >= 0) {
 #pragma unroll
             for (int v = 0; v < VPT; ++v) fma4(acc[v], a[q], x[q][v]);
+          }
+        }
+      }
+    } else {
+      int maxlen = len;
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, o));
+      for (int j0 = 0; j0 < maxlen; j0 += LPR) {
+        const int j = j0 + sl;
+        const int cc = (j < len) ? __ldg(A.col + s + j) : -1;
+        const float aa = (j < len) ? __ldg(A.val + s + j) : 0.f;
+#pragma unroll
+        for (int t = 0; t < LPR; t += U) {
+          if (j0 + t >= maxlen) break;
+          float4 x[U][VPT];
+          float a[U];
+          int cq[U];
+#pragma unroll
+          for (int q = 0; q < U; ++q) {
+            cq[q] = __shfl_sync(kFull, cc, t + q, LPR);
+            a[q] = __shfl_sync(kFull, aa, t + q, LPR);
+          }
+#pragma unroll
+          for (int q = 0; q < U; ++q) {
+            if (cq[q] >= 0) {
+#pragma unroll
+              for (int v = 0; v < VPT; ++v) x[q][v] = __ldg(X4 + (int64_t)cq[q] * C::kVec + sl * VPT + v);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < U; ++q) {
+            if (cq[q] >= 0) {
+#pragma unroll
+              for (int v = 0; v < VPT; ++v) fma4(acc[v], a[q], x[q][v]);
+            }
           }
         }
       }
@@ -109,59 +184,48 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, 
       last = __shfl_sync(kFull, last, 0, LPR);
       if (last) {
         __threadfence();
-        const int p0 = A.split_ptr[split_idx], p1 = A.split_ptr[split_idx + 1];
-        const float4* P4 = reinterpret_cast<const float4*>(A.partials);
-        float4 tot[VPT];
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) tot[v] = __ldcg(P4 + (int64_t)p0 * C::kVec + sl * VPT + v);
-        int p = p0 + 1;
-        for (; p + 8 <= p1; p += 8) {
-          float4 x[8][VPT];
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) x[q][v] = __ldcg(P4 + (int64_t)(p + q) * C::kVec + sl * VPT + v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) {
-              tot[v].x += x[q][v].x; tot[v].y += x[q][v].y; tot[v].z += x[q][v].z; tot[v].w += x[q][v].w;
-            }
-        }
-        for (; p < p1; ++p) {
-#pragma unroll
-          for (int v = 0; v < VPT; ++v) {
-            const float4 x = __ldcg(P4 + (int64_t)p * C::kVec + sl * VPT + v);
-            tot[v].x += x.x; tot[v].y += x.y; tot[v].z += x.z; tot[v].w += x.w;
-          }
-        }
-        float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D);
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-          if (ACC) {
-            const float4 y = y4[sl * VPT + v];
-            tot[v].x = y.x + tot[v].x; tot[v].y = y.y + tot[v].y; tot[v].z = y.z + tot[v].z; tot[v].w = y.w + tot[v].w;
-          }
-          y4[sl * VPT + v] = tot[v];
-        }
+        spmm_finish_split<D, ACC>(A, Y, row, split_idx, sl);
         if (sl == 0) A.split_count[split_idx] = 0;         // re-arm for the next call
       }
     }
   }
 }
 
+template <int D, int THREADS, int MINB, int U, bool DIRECT>
+static int launch_spmm_v(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s, const int32_t* row_flag) {
+  using C = SpmmCfg<D>;
+  const int wpb = THREADS / 32;
+  int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
+  const int64_t cap = (int64_t)yr_sm_count() * 8 * 32;
+  if (blocks > cap) blocks = cap;
+  if (accumulate) spmm_chunk_kernel<D, true, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
+  else spmm_chunk_kernel<D, false, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
+// YR_SPMM_VARIANT (experiments; the default is the measured best, profiles/README.md): same arithmetic in every variant.
+static int spmm_variant() {
+  const char* e = getenv("YR_SPMM_VARIANT");      // read per launch: a getenv is nanoseconds next to a kernel launch
+  return (e && *e) ? atoi(e) : -1;
+}
+
 template <int D>
 static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s,
                        const int32_t* row_flag = nullptr) {
-  using C = SpmmCfg<D>;
-  const int threads = 256, wpb = threads / 32;
-  int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
-  const int64_t cap = (int64_t)yr_sm_count() * 8 * 16;
-  if (blocks > cap) blocks = cap;
-  if (accumulate) spmm_chunk_kernel<D, true><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y, row_flag);
-  else spmm_chunk_kernel<D, false><<<(unsigned)blocks, threads, 0, s>>>(*A, X, Y, row_flag);
-  YR_CHECK_LAUNCH();
-  return YR_OK;
+  constexpr int MB = D <= 64 ? 3 : 2;
+  switch (spmm_variant()) {
+    case 1: return launch_spmm_v<D, 128, 2 * MB, 8, false>(A, X, Y, accumulate, s, row_flag);
+    case 2: return launch_spmm_v<D, 128, 8, 8, false>(A, X, Y, accumulate, s, row_flag);
+    case 3: return launch_spmm_v<D, 128, 2 * MB, 8, true>(A, X, Y, accumulate, s, row_flag);
+    case 4: return launch_spmm_v<D, 128, 8, 8, true>(A, X, Y, accumulate, s, row_flag);
+    case 5: return launch_spmm_v<D, 256, 4, 8, true>(A, X, Y, accumulate, s, row_flag);
+    case 6: return launch_spmm_v<D, 128, 8, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 7: return launch_spmm_v<D, 64, 16, 8, true>(A, X, Y, accumulate, s, row_flag);
+    case 8: return launch_spmm_v<D, 128, 10, 8, true>(A, X, Y, accumulate, s, row_flag);
+    case 9: return launch_spmm_v<D, 256, 4, 8, false>(A, X, Y, accumulate, s, row_flag);
+    default: return launch_spmm_v<D, 256, MB, 8, false>(A, X, Y, accumulate, s, row_flag);
+  }
 }
 
 }  // namespace yr
@@ -201,6 +265,24 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     }
     split_row_h[sr] = (int32_t)r;
     split_ptr_h[++sr] = (int32_t)slot;
+  }
+  // short rows: YR_SPMM_PLAN_SORT=1 emits them longest first (counting sort by length), so that the chunks that share a
+  // warp / CTA have equal lengths; default is row order. Either way every row is one chain: results do not change.
+  const char* e = getenv("YR_SPMM_PLAN_SORT");
+  if (e && e[0] == '1') {
+    int64_t start[YR_SPMM_CHUNK + 2] = {0};
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+      if (len <= YR_SPMM_CHUNK) ++start[YR_SPMM_CHUNK - len + 1];      // bucket 0 = longest
+    }
+    for (int k = 0; k <= YR_SPMM_CHUNK; ++k) start[k + 1] += start[k];
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+      if (len > YR_SPMM_CHUNK) continue;
+      int32_t* d = chunk_desc_h + 4 * (c + start[YR_SPMM_CHUNK - len]++);
+      d[0] = (int32_t)r; d[1] = rowptr_h[r]; d[2] = (int32_t)len; d[3] = -1;
+    }
+    return YR_OK;
   }
   for (int64_t r = 0; r < n_rows; ++r) {
     const int64_t len = rowptr_h[r + 1] - rowptr_h[r];

@@ -44,28 +44,31 @@ class MFTrainer(BaseTrainer):
         return BPRLoss()
 
     # ------------------------------------------------------------------------------------------
-    def _state(self, batch_cap: int):
-        """Device scratch of the fused kernel (allocated once; all-zero invariant kept by the kernel)."""
+    def _state(self, batch_cap: int, n_triples: int = 0):
+        """Device scratch of the fused kernel (allocated once; the flags' all-zero invariant is kept by the kernel)."""
         U, V = self.model.user_embedding.weight, self.model.item_embedding.weight
         dev = self.device
         if self._scratch is None or self._scratch["cap"] < batch_cap or self._scratch["U_ptr"] != U.data_ptr():
             z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
             sc = {"cap": batch_cap, "U_ptr": U.data_ptr(),
-                  "gU": z(*U.shape), "gV": z(*V.shape), "flagU": z(U.shape[0], dt=I32), "flagV": z(V.shape[0], dt=I32),
-                  "rows": z(3 * batch_cap, dt=I32), "counters": z(16, dt=I32), "err": z(1, dt=I32),
-                  "loss_sum": z(1, dt=F64)}
+                  "flagU": z(U.shape[0], dt=I32), "flagV": z(V.shape[0], dt=I32), "counters": z(16, dt=I32),
+                  "err": z(1, dt=I32), "loss_sum": z(1, dt=F64), "ws": None}
             if self.optimizer.needs_moments and "U" not in self.optimizer.state:
                 self.optimizer.state["U"] = (z(*U.shape), z(*U.shape))
                 self.optimizer.state["V"] = (z(*V.shape), z(*V.shape))
             self._scratch = sc
         sc = self._scratch
+        need = _cabi.load().yr_bpr_mf_train_ws_bytes(max(int(n_triples), 1), int(batch_cap), int(U.shape[1]))
+        if sc["ws"] is None or sc["ws"].numel() < need:
+            sc["ws"] = torch.empty(need, device=dev, dtype=torch.uint8)
         mU = vU = mV = vV = None
         if self.optimizer.needs_moments:
             (mU, vU), (mV, vV) = self.optimizer.state["U"], self.optimizer.state["V"]
         p = _cabi.dptr
-        st = _cabi.YrMfState(p(U.data, F32), p(V.data, F32), p(mU), p(vU), p(mV), p(vV), p(sc["gU"]), p(sc["gV"]),
-                             p(sc["flagU"]), p(sc["flagV"]), p(sc["rows"]), p(sc["counters"]), p(sc["err"]),
-                             U.shape[0], V.shape[0], U.shape[1])
+        st = _cabi.YrMfState(p(U.data, F32), p(V.data, F32), p(mU), p(vU), p(mV), p(vV),
+                             p(sc["flagU"]), p(sc["flagV"]), p(sc["counters"]), p(sc["err"]),
+                             p(sc["ws"]), sc["ws"].numel(), U.shape[0], V.shape[0], U.shape[1],
+                             1 if getattr(self.cfg, "deterministic", False) else 0)
         return st, sc
 
     def _get_stager(self, dataloader) -> BatchStager:
@@ -87,7 +90,7 @@ class MFTrainer(BaseTrainer):
         stays on the device (read it with `.loss_sum()`)."""
         lib = _cabi.load()
         n = int(uid.numel())
-        st, sc = self._state(batch_size)
+        st, sc = self._state(batch_size, n)
         n_steps = (n + batch_size - 1) // batch_size
         opt = self.optimizer.opt_struct(self.optimizer.step_count + 1)
         _cabi.check(lib.yr_bpr_mf_train(C.byref(st), C.byref(opt), _cabi.dptr(uid, I64), _cabi.dptr(pos, I64),
