@@ -265,6 +265,22 @@ int yr_laplacian_build(const int64_t* user, const int64_t* item, const float* ra
                        int64_t num_users, int64_t num_items, int32_t* rowptr, int32_t* col, float* val,
                        void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
 
+/* ---- Scaled synthetic graph (BASELINE config 5) ------------------------------------------------------
+ * The reference has no generator (it reads Yelp's review.json); this is the input producer of the scaled benchmark.
+ * yr_synth_user_rows: for every user u the SORTED, DUPLICATE-FREE item list of a synthetic bipartite graph: the number of
+ * draws is log-normal (exp(mu + sigma z), clipped to [min_deg, max_deg <= 1024]), every draw is an item rank from a
+ * Zipf(zipf_alpha) law mapped to an id by a fixed permutation. Philox4x32-10 streams keyed by (seed, user): the same graph
+ * on every rank. Two calls: rowptr == NULL -> cnt_out[u] = list length; rowptr given (exclusive scan of the counts) ->
+ * items_out[rowptr[u] ..] = the list. */
+int yr_synth_user_rows(uint64_t seed, int64_t num_users, int64_t num_items, double zipf_alpha, double mu, double sigma,
+                       int32_t min_deg, int32_t max_deg, const int32_t* rowptr, int32_t* cnt_out, int32_t* items_out,
+                       yr_stream stream);
+/* Values of L = (D^-1/2 A) D^-1/2 for a BINARY adjacency given as CSR structure (any row block of it):
+ * val[k] = (dinv[row] * 1) * dinv[col[k]], dinv = 1 / sqrt(deg) in fp32 — data/datasets/ngcf_data_pipeline.py:34-42.
+ * row_node[r] (NULL = r) and col_node[k] index the node degrees `deg`. */
+int yr_laplacian_binary_values(const int32_t* rowptr, int64_t n_rows, const int32_t* row_node, const int32_t* col_node,
+                               const int32_t* deg, float* val, yr_stream stream);
+
 /* ---- Negative sampler -----------------------------------------------------------------
  * MFDataset._negative_sampling (data/datasets/mf_dataset.py:18-22): for every training interaction t one item
  * drawn uniformly from the items NOT in the user's positive list. pos_ptr/pos_idx: CSR of the users' `pos_items`

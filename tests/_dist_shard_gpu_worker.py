@@ -64,6 +64,30 @@ def main():
                 rel = float((got - ref).norm() / ref.norm())
                 assert rel < 1e-5, (optname, "W", l, rel)
         assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+    # ---- BASELINE config 5 in miniature: device-built ScaledGraph, d = 128 x 3 layers, N ranks vs ONE rank of own code
+    from yelprecommendation_b200.data.scaled import make_scaled_graph
+    sg = make_scaled_graph(6000, 1500, 150_000, seed=5, device="cuda")
+    rng = np.random.default_rng(0)
+    B = 8192
+    batches = [{"user_id": torch.from_numpy(rng.integers(0, 6000, B)), "pos_item": torch.from_numpy(rng.integers(0, 1500, B)),
+                "neg_item": torch.from_numpy(rng.integers(0, 1500, B))} for _ in range(2)]
+    g = torch.Generator().manual_seed(4)
+    init = {"embedding.weight": torch.randn(7500, 128, generator=g) * 0.3}
+    for l in range(3):
+        init[f"W1.{l}.weight"] = (torch.rand(128, 128, generator=g) * 2 - 1) / 11
+        init[f"W2.{l}.weight"] = (torch.rand(128, 128, generator=g) * 2 - 1) / 11
+    cfg = SimpleNamespace(embed_size=128, num_orders=3, optimizer="adam", lr=1e-2, weight_decay=0.0, seed=1)
+    trN = ShardedNGCFTrainer(cfg, 1500, 6000, sg, init=init)                       # all ranks, 4 row panels each
+    lossN = trN.train(batches)
+    EN = trN.gather_embedding().cpu()
+    if rank == 0:
+        # the same model on ONE rank (solo=True: world 1, no collectives) for the N-GPU vs 1-GPU parity of own code
+        tr1 = ShardedNGCFTrainer(cfg, 1500, 6000, sg, init=init, n_panels=1, solo=True)
+        loss1 = tr1.train(batches)
+        E1 = tr1.gather_embedding().cpu()
+        rel = float((EN - E1).norm() / E1.norm())
+        assert rel < 1e-5, ("N-GPU vs 1-GPU", rel)
+        assert abs(lossN - loss1) < 1e-5 * abs(loss1), (lossN, loss1)
     dist.barrier()
     if rank == 0:
         print("DIST_SHARD_GPU_OK")

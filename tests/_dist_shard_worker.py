@@ -89,9 +89,12 @@ class CpuNgcfShardKernels:
     yr_shard_accumulate / yr_dense_opt_step on CPU tensors. Test infrastructure only."""
 
     def make_csr(self, rowptr, col, val):
+        """rowptr: absolute offsets into col / val (row panels share the block's arrays)"""
+        rowptr = np.asarray(rowptr, dtype=np.int64)
         n = len(rowptr) - 1
         rows = np.repeat(np.arange(n), np.diff(rowptr))
-        return (n, torch.from_numpy(rows.astype(np.int64)), torch.from_numpy(col.astype(np.int64)), torch.from_numpy(val))
+        sl = slice(int(rowptr[0]), int(rowptr[-1]))
+        return (n, torch.from_numpy(rows.astype(np.int64)), torch.as_tensor(col)[sl].to(torch.int64), torch.as_tensor(val)[sl])
 
     def spmm(self, A, X, out, accumulate):
         n, rows, cols, vals = A

@@ -65,15 +65,17 @@ def _ngcf_problem(seed=21, nu=1203, ni=958, nnz=30000, d=64, layers=3):
 
 @pytest.mark.parametrize("optname,lr,wd,layers,d", [("sgd", 0.05, 0.0, 3, 64), ("adam", 1e-2, 1e-4, 3, 64),
                                                     ("adamw", 2e-3, 1e-2, 1, 64), ("sgd", 0.05, 0.0, 1, 128),
-                                                    ("adam", 1e-2, 1e-4, 3, 32)])
+                                                    ("adam", 1e-2, 1e-4, 3, 32), ("sgd", 0.05, 0.0, 3, 128),
+                                                    ("adam", 1e-2, 0.0, 3, 128)])
 def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers, d):
-    """Op-by-op sharded path (rectangular SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle;
-    d = 128 is BASELINE config 5's width (one layer: the tail kernels take concatenated widths up to 256)."""
+    """Op-by-op sharded path (row panels of the SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle;
+    d = 128 with 3 layers (concatenated width 512) is BASELINE config 5's model."""
     from oracle.torch_port import NGCFPort
     from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
     inter, L, batches, init = _ngcf_problem(layers=layers, d=d)
     cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
-    tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init)
+    tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init, n_panels=3)
+    assert len(tr.panels) == 3
     loss = tr.train(batches)
     port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
                     [init[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, optname, lr, wd)
@@ -94,3 +96,94 @@ def test_sharded_trainer_nccl_world2():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_SHARD_GPU_OK" in r.stdout
+
+
+# ---- BASELINE config 5 inputs built on the device (data/scaled.py) --------------------------------------------------
+def _small_scaled(nU=3000, nI=700, nnz=60_000):
+    from yelprecommendation_b200.data.scaled import make_scaled_graph
+    return make_scaled_graph(nU, nI, nnz, seed=5, device="cuda")
+
+
+def test_scaled_graph_generator_properties():
+    """Philox generator kernel: sorted duplicate-free item lists, every user >= min_deg draws, requested size within 1 %,
+    Zipf head (the most popular item is far above the mean), and the same graph on every call (counter-based)."""
+    g = _small_scaled()
+    ptr, items = g.user_ptr.cpu().numpy().astype(np.int64), g.user_items.cpu().numpy()
+    assert ptr[0] == 0 and ptr[-1] == items.size and abs(items.size - 60_000) <= 0.01 * 60_000
+    assert items.min() >= 0 and items.max() < 700
+    for u in (0, 1, 17, 2999):
+        row = items[ptr[u]:ptr[u + 1]]
+        assert row.size >= 1 and np.all(np.diff(row) > 0)
+    lens = np.diff(ptr)
+    starts = ptr[:-1]
+    inner = np.ones(items.size, bool)
+    inner[starts] = False
+    assert np.all(np.diff(items)[inner[1:]] > 0)                        # strictly ascending inside every row
+    deg = np.bincount(items, minlength=700)
+    assert deg.max() > 8 * deg.mean() and lens.max() > 3 * lens.mean()
+    g2 = _small_scaled()
+    assert torch.equal(g.user_ptr, g2.user_ptr) and torch.equal(g.user_items, g2.user_items)
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_shard_laplacian_blocks_equal_the_reference_laplacian(world):
+    """Row blocks cut on the device (shard_laplacian: binary ratings, yr_laplacian_binary_values) re-assembled in the
+    reference's node order == data.graph.build_laplacian of the same interactions (pinned to the reference,
+    tests/test_oracle_golden.py) bit for bit; the COO entry point gives the same blocks."""
+    from yelprecommendation_b200.data.graph import build_laplacian, coo_to_csr
+    from yelprecommendation_b200.data.scaled import ShardLayout, shard_laplacian, shard_laplacian_from_coo
+    g = _small_scaled()
+    nU, nI = g.num_users, g.num_items
+    ptr, items = g.user_ptr.cpu().numpy().astype(np.int64), g.user_items.cpu().numpy().astype(np.int64)
+    users = np.repeat(np.arange(nU), np.diff(ptr))
+    L = build_laplacian(users, items, np.ones(items.size), nU, nI)
+    idx, val = L.indices().numpy(), L.values().numpy()
+    rp_ref, ci_ref, va_ref = coo_to_csr(idx[0], idx[1], val, nU + nI)
+    lay = ShardLayout(nU, nI, world)
+    pos_of_node = lay.node_pos(torch.arange(nU + nI)).numpy()
+    node_of_pos = np.full(world * lay.per, -1, np.int64)
+    node_of_pos[pos_of_node] = np.arange(nU + nI)
+    seen = 0
+    for rank in range(world):
+        rp, ci, va = (t.cpu().numpy() for t in shard_laplacian(g, lay, rank))
+        rp2, ci2, va2 = (t.cpu().numpy() for t in shard_laplacian_from_coo(L, lay, rank, "cuda"))
+        assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(va, va2)
+        for r in range(lay.per):
+            node = node_of_pos[rank * lay.per + r]
+            if node < 0:
+                assert rp[r + 1] == rp[r]
+                continue
+            a, b = rp_ref[node], rp_ref[node + 1]
+            assert np.array_equal(node_of_pos[ci[rp[r]:rp[r + 1]]], ci_ref[a:b])
+            assert np.array_equal(va[rp[r]:rp[r + 1]], va_ref[a:b])
+            seen += b - a
+    assert seen == ci_ref.size
+
+
+def test_sharded_ngcf_on_scaled_graph_world1_matches_port():
+    """ShardedNGCFTrainer fed with a ScaledGraph (device-built blocks, row panels) vs the torch-CPU port on the same graph."""
+    from oracle.torch_port import NGCFPort
+    from yelprecommendation_b200.data.graph import build_laplacian
+    from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
+    g = _small_scaled()
+    nU, nI, d, layers = g.num_users, g.num_items, 128, 3
+    ptr, items = g.user_ptr.cpu().numpy().astype(np.int64), g.user_items.cpu().numpy().astype(np.int64)
+    users = np.repeat(np.arange(nU), np.diff(ptr))
+    L = build_laplacian(users, items, np.ones(items.size), nU, nI)
+    rng = np.random.default_rng(0)
+    B = 4096
+    batches = [{"user_id": torch.from_numpy(rng.integers(0, nU, B)), "pos_item": torch.from_numpy(rng.integers(0, nI, B)),
+                "neg_item": torch.from_numpy(rng.integers(0, nI, B))} for _ in range(2)]
+    gen = torch.Generator().manual_seed(3)
+    init = {"embedding.weight": torch.randn(nU + nI, d, generator=gen) * 0.3}
+    for l in range(layers):
+        init[f"W1.{l}.weight"] = (torch.rand(d, d, generator=gen) * 2 - 1) / 11
+        init[f"W2.{l}.weight"] = (torch.rand(d, d, generator=gen) * 2 - 1) / 11
+    cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer="adam", lr=1e-2, weight_decay=0.0, seed=1)
+    tr = ShardedNGCFTrainer(cfg, nI, nU, g, init=init, n_panels=4)
+    loss = tr.train(batches)
+    port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
+                    [init[f"W2.{l}.weight"] for l in range(layers)], nU, L, "adam", 1e-2, 0.0)
+    ref_loss, _ = port.train(batches)
+    assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss)
+    assert rel_fro(tr.gather_embedding().cpu(), port.emb.detach()) < 2e-5

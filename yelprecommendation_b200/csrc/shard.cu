@@ -174,6 +174,8 @@ extern "C" int yr_bpr_rows_grad(const float* R, int d, int64_t B, int64_t b0, in
     case 2: bpr_rows_grad_kernel<2><<<g, 256, 0, s>>>(R, B, b0, b1, G, loss_acc); break;
     case 4: bpr_rows_grad_kernel<4><<<g, 256, 0, s>>>(R, B, b0, b1, G, loss_acc); break;
     case 8: bpr_rows_grad_kernel<8><<<g, 256, 0, s>>>(R, B, b0, b1, G, loss_acc); break;
+    case 16: bpr_rows_grad_kernel<16><<<g, 256, 0, s>>>(R, B, b0, b1, G, loss_acc); break;      // NGCF: d * (layers + 1) = 512
+    case 32: bpr_rows_grad_kernel<32><<<g, 256, 0, s>>>(R, B, b0, b1, G, loss_acc); break;
     default: return YR_ERR_BAD_DIM;
   }
   YR_CHECK_LAUNCH();

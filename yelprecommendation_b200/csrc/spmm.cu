@@ -213,18 +213,20 @@ static int spmm_variant() {
 template <int D>
 static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s,
                        const int32_t* row_flag = nullptr) {
-  constexpr int MB = D <= 64 ? 3 : 2;
+  // Default = the measured best of the sweep in profiles/r02_spmm_sweep.txt (B200, Yelp-shape graph): 128-thread CTAs
+  // bounded to 64 registers (8 CTAs = 32 warps per SM), 4 neighbour rows in flight per group, direct index loads:
+  // 55.8 us at d = 64 / 111 us at d = 128 against 85.5 / 216 us for the round-1 shape (variant 0).
   switch (spmm_variant()) {
-    case 1: return launch_spmm_v<D, 128, 2 * MB, 8, false>(A, X, Y, accumulate, s, row_flag);
-    case 2: return launch_spmm_v<D, 128, 8, 8, false>(A, X, Y, accumulate, s, row_flag);
-    case 3: return launch_spmm_v<D, 128, 2 * MB, 8, true>(A, X, Y, accumulate, s, row_flag);
-    case 4: return launch_spmm_v<D, 128, 8, 8, true>(A, X, Y, accumulate, s, row_flag);
-    case 5: return launch_spmm_v<D, 256, 4, 8, true>(A, X, Y, accumulate, s, row_flag);
-    case 6: return launch_spmm_v<D, 128, 8, 4, true>(A, X, Y, accumulate, s, row_flag);
-    case 7: return launch_spmm_v<D, 64, 16, 8, true>(A, X, Y, accumulate, s, row_flag);
-    case 8: return launch_spmm_v<D, 128, 10, 8, true>(A, X, Y, accumulate, s, row_flag);
-    case 9: return launch_spmm_v<D, 256, 4, 8, false>(A, X, Y, accumulate, s, row_flag);
-    default: return launch_spmm_v<D, 256, MB, 8, false>(A, X, Y, accumulate, s, row_flag);
+    case 0: return launch_spmm_v<D, 256, (D <= 64 ? 3 : 2), 8, false>(A, X, Y, accumulate, s, row_flag);
+    case 1: return launch_spmm_v<D, 128, 8, 4, false>(A, X, Y, accumulate, s, row_flag);
+    case 2: return launch_spmm_v<D, 128, 12, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 3: return launch_spmm_v<D, 128, 16, 2, true>(A, X, Y, accumulate, s, row_flag);
+    case 4: return launch_spmm_v<D, 64, 16, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 5: return launch_spmm_v<D, 256, 4, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 7: return launch_spmm_v<D, 128, 10, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 8: return launch_spmm_v<D, 128, 8, 6, true>(A, X, Y, accumulate, s, row_flag);
+    case 9: return launch_spmm_v<D, 128, 6, 8, true>(A, X, Y, accumulate, s, row_flag);
+    default: return launch_spmm_v<D, 128, 8, 4, true>(A, X, Y, accumulate, s, row_flag);
   }
 }
 
@@ -266,10 +268,11 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     split_row_h[sr] = (int32_t)r;
     split_ptr_h[++sr] = (int32_t)slot;
   }
-  // short rows: YR_SPMM_PLAN_SORT=1 emits them longest first (counting sort by length), so that the chunks that share a
-  // warp / CTA have equal lengths; default is row order. Either way every row is one chain: results do not change.
+  // short rows are emitted longest first (counting sort by length), so that the chunks that share a warp / CTA have
+  // equal lengths (85 -> 60 us on the Yelp-shape graph, profiles/r02_spmm_sweep.txt); YR_SPMM_PLAN_SORT=0 keeps row
+  // order. Either way every row is one chain: results do not change.
   const char* e = getenv("YR_SPMM_PLAN_SORT");
-  if (e && e[0] == '1') {
+  if (!(e && e[0] == '0')) {
     int64_t start[YR_SPMM_CHUNK + 2] = {0};
     for (int64_t r = 0; r < n_rows; ++r) {
       const int64_t len = rowptr_h[r + 1] - rowptr_h[r];

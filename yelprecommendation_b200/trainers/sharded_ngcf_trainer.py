@@ -1,24 +1,29 @@
 """Row-sharded NGCF training across GPUs (BASELINE config 5): 1-D row partition of the Laplacian,
 of the node-embedding table and of its optimizer state; the 2·num_orders d x d weights are replicated.
 
-Rank r owns node rows [r*per, min((r+1)*per, N)), per = ceil(N / world) (so the all-gathered operand [world*per x d]
-is indexed by GLOBAL node id), and holds rows [r0, r1) of L and of L^T as CSR blocks with global column ids.
-One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:102-115):
+Partition (data/scaled.py::ShardLayout): rank k owns a contiguous block of USERS and a contiguous block of ITEMS — `per`
+rows in all — so every rank holds about nnz / world non-zeros (a block partition of the node ids alone would give the
+item-owning ranks several times the non-zeros of the others). The all-gathered operand X [world * per x d] is indexed by
+position = rank * per + local row; users and items map monotonically, so every CSR row keeps the column order it has
+on one GPU and the SpMM results are bit-identical at any world size.
+One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:102-115), local rows cut into P row panels:
 
-    forward, per layer l :  X = all_gather(E_l)            NCCL, N*d*4 bytes
-                            LE_l = L[r0:r1, :] X           yr_spmm_csr on the local row block
-                            E_{l+1} = dense(E_l, LE_l)     yr_ngcf_dense_fwd on local rows
-    tail                 :  owner gather of rows u / U+pos / U+neg of every layer -> all_reduce (exact gather),
+    forward, per layer l :  for panel p:  LE_l[p] = L[p, :] X_l          yr_spmm_csr on the panel's rows
+                                          E_{l+1}[p] = dense(E_l, LE_l)  yr_ngcf_dense_fwd
+                                          exchange(E_{l+1}[p])           grouped NCCL send/recv into every peer's X_{l+1},
+                                                                          issued asynchronously: it runs underneath panel p+1
+    tail                 :  owner gather of rows u / pos / neg of every layer -> all_reduce (exact gather),
                             yr_bpr_rows_grad on the concatenated rows (every rank, all B triples: the loss and the row
-                            gradients are replicated, no collective), yr_shard_accumulate scatters owned rows into G_l
-    backward, per layer  :  yr_ngcf_dense_bwd on local rows -> T, G_l += ..., dW partial
-                            X = all_gather(T);  G_l += L^T[r0:r1, :] X
-                            all_reduce(dW1, dW2)
+                            gradients are replicated, no further collective), yr_shard_accumulate scatters owned rows into G_l
+    backward, per layer  :  for panel p:  yr_ngcf_dense_bwd -> T[p], G_l[p] += ..., dW partial;  exchange(T[p]) (async)
+                            G_l += L^T[block, :] X_T;   all_reduce(dW1, dW2) once per step
     update               :  yr_dense_opt_step on the local rows of E_0 and (identically on every rank) on the weights
 
-The result equals the single-GPU NGCFTrainer up to fp32 summation order of dW (per-CTA partials, then ranks) and of
-duplicate tail rows. No CPU product path: `device`/`kernels` exist so that tests/_dist_shard_worker.py can drive the
-choreography under gloo with a CPU restatement of the kernels.
+The all-gather of a layer is therefore hidden behind the compute of the other panels; only the last panel's exchange
+(1 / P of N * d * 4 bytes) is exposed. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
+cut on the device, any weights) or as a data.scaled.ScaledGraph (config 5: generated and normalised on the device).
+No CPU product path: `device` / `kernels` exist so that tests/_dist_shard_worker.py can drive the choreography under gloo
+with a CPU restatement of the kernels.
 """
 from __future__ import annotations
 
@@ -30,7 +35,8 @@ import torch
 import torch.distributed as dist
 
 from .. import _cabi, ops
-from ..data.graph import CSRMatrix, coo_to_csr
+from ..data.graph import CSRMatrix
+from ..data.scaled import ScaledGraph, ShardLayout, shard_laplacian, shard_laplacian_from_coo
 from .base_trainer import FusedOptimizer
 
 I32, I64, F32, F64 = torch.int32, torch.int64, torch.float32, torch.float64
@@ -50,6 +56,7 @@ class CabiNgcfShardKernels:
         return _cabi.stream_ptr(self.device)
 
     def make_csr(self, rowptr, col, val):
+        """rowptr: absolute offsets into col / val (a row panel shares the block's storage)"""
         return CSRMatrix(rowptr, col, val, self.device)
 
     def spmm(self, A, X, out, accumulate):
@@ -96,132 +103,163 @@ class CabiNgcfShardKernels:
 
 
 class ShardedNGCFTrainer:
-    def __init__(self, cfg, num_items: int, num_users: int, laplacian_matrix: torch.Tensor, init=None, group=None,
-                 device=None, kernels=None):
-        """`laplacian_matrix`: the reference's sparse COO [N x N] (every rank passes the same; each keeps its row block).
-        `init`: optional dict with 'embedding.weight' [N x d], 'W1.l.weight', 'W2.l.weight' (tests); otherwise
-        torch.manual_seed(cfg.seed)-driven N(0,1) / kaiming-uniform like the reference (models/ngcf.py:9-23)."""
+    def __init__(self, cfg, num_items: int, num_users: int, laplacian_matrix, init=None, group=None,
+                 device=None, kernels=None, n_panels: int = None, solo: bool = False):
+        """`laplacian_matrix`: the reference's sparse COO [N x N] (every rank passes the same; each keeps its row block) or
+        a data.scaled.ScaledGraph. `init`: optional dict with 'embedding.weight' [N x d] (reference node order),
+        'W1.l.weight', 'W2.l.weight' (tests); otherwise N(0,1) / kaiming-uniform like the reference (models/ngcf.py:9-23),
+        generated on the device per rank (a function of cfg.seed and the rank)."""
         self.cfg, self.nI, self.nU = cfg, int(num_items), int(num_users)
         self.N = self.nU + self.nI
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        multi = dist.is_initialized() and not solo          # solo: this process trains the whole model alone (parity runs)
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.k = kernels if kernels is not None else CabiNgcfShardKernels(self.device)
         self.d, self.n_layers = int(cfg.embed_size), int(cfg.num_orders)
         self.width = (self.n_layers + 1) * self.d
-        if self.width not in (32, 64, 128, 256):
-            raise NotImplementedError(f"concatenated width {self.width} not in (32, 64, 128, 256)")
+        if self.width not in (32, 64, 128, 256, 512, 1024):
+            raise NotImplementedError(f"concatenated width {self.width} not in (32, 64, 128, 256, 512, 1024)")
         self.optimizer = FusedOptimizer(cfg.optimizer, cfg.lr, cfg.weight_decay)
-        self.per = (self.N + self.world - 1) // self.world
-        self.r0 = min(self.rank * self.per, self.N)
-        self.r1 = min(self.r0 + self.per, self.N)
-        self.n_loc = self.r1 - self.r0
-        if self.n_loc <= 0:
-            raise ValueError("more ranks than node rows")
-        # ---- row blocks of L and of L^T (global column ids)
-        Lc = laplacian_matrix.detach().cpu().coalesce()
-        idx, val = Lc.indices().numpy(), Lc.values().numpy().astype(np.float32)
-        self.A = self._row_block(idx[0], idx[1], val)
-        self.AT = self._row_block(idx[1], idx[0], val)
+        self.layout = ShardLayout(self.nU, self.nI, self.world)
+        self.per = self.layout.per
+        self.lo, self.hi = self.rank * self.per, (self.rank + 1) * self.per          # positions of the local rows
+        self.total = self.world * self.per
+        # ---- row block of L (cut into panels) and of L^T, columns = positions in the gathered operand
+        dev = self.device
+        if isinstance(laplacian_matrix, ScaledGraph):
+            rp, ci, va = shard_laplacian(laplacian_matrix, self.layout, self.rank)
+            rpT, ciT, vaT = rp, ci, va                               # binary ratings: L is bit-wise symmetric
+        else:
+            rp, ci, va = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev)
+            rpT, ciT, vaT = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev, transpose=True)
+        self.nnz_local = int(ci.numel())
+        P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", 4 if self.world > 1 else 1))
+        P = max(1, min(P, self.per))
+        step = ((self.per + P - 1) // P + 127) // 128 * 128          # whole 128-row tiles of the dense kernels
+        rp_h = rp.cpu()
+        self.panels = [(a, min(a + step, self.per), self.k.make_csr(rp_h[a: min(a + step, self.per) + 1], ci, va))
+                       for a in range(0, self.per, step)]
+        self.AT = self.k.make_csr(rpT.cpu(), ciT, vaT) if (rpT is not rp or len(self.panels) > 1) else self.panels[0][2]
         # ---- parameters
-        dev, d, n_loc = self.device, self.d, self.n_loc
+        d, per = self.d, self.per
+        f = lambda t: t.detach().to(dev, F32).contiguous().clone()
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         if init is not None:
-            E0 = init["embedding.weight"][self.r0:self.r1]
+            E0 = self.layout.local_rows(self.rank, init["embedding.weight"].to(F32)).to(dev)
             W1 = [init[f"W1.{l}.weight"] for l in range(self.n_layers)]
             W2 = [init[f"W2.{l}.weight"] for l in range(self.n_layers)]
         else:
-            g = torch.Generator().manual_seed(int(getattr(cfg, "seed", 42)))
-            E0 = torch.randn(self.N, d, generator=g)[self.r0:self.r1]
+            seed = int(getattr(cfg, "seed", 42))
+            g = torch.Generator(device=dev).manual_seed(seed * 1000003 + self.rank)
+            E0 = torch.randn(per, d, generator=g, device=dev, dtype=F32)
+            gw = torch.Generator().manual_seed(seed)                  # the weights are replicated: same stream on every rank
             bound = 1.0 / np.sqrt(d)                                  # nn.Linear default: kaiming_uniform(a=sqrt(5))
-            W1 = [(torch.rand(d, d, generator=g) * 2 - 1) * bound for _ in range(self.n_layers)]
-            W2 = [(torch.rand(d, d, generator=g) * 2 - 1) * bound for _ in range(self.n_layers)]
-        f = lambda t: t.detach().to(dev, F32).contiguous().clone()
-        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
-        self.E: List[torch.Tensor] = [f(E0)] + [z(n_loc, d) for _ in range(self.n_layers)]
-        self.LE = [z(n_loc, d) for _ in range(self.n_layers)]
-        self.G = [z(n_loc, d) for _ in range(self.n_layers + 1)]
-        self.T = z(self.per, d)                                       # padded: it is an all_gather input
-        self.X = z(self.world * self.per, d)                          # all-gathered operand, global row ids
-        self.Epad = z(self.per, d)
+            W1 = [(torch.rand(d, d, generator=gw) * 2 - 1) * bound for _ in range(self.n_layers)]
+            W2 = [(torch.rand(d, d, generator=gw) * 2 - 1) * bound for _ in range(self.n_layers)]
+        self.E: List[torch.Tensor] = [f(E0)] + [z(per, d) for _ in range(self.n_layers)]
+        self.LE = [z(per, d) for _ in range(self.n_layers)]
+        self.G = [z(per, d) for _ in range(self.n_layers + 1)]
+        self.T = z(per, d)
+        # gathered operands: two buffers, so that the exchange of layer l+1 can land while layer l's SpMM still reads
+        self.X = [z(self.total, d) for _ in range(2)] if self.world > 1 else None
+        self._pending = [[], []]
         self.W1, self.W2 = [f(w) for w in W1], [f(w) for w in W2]
         self.dW = z(2 * self.n_layers, d, d)
+        self.dWp = z(len(self.panels), 2, d, d)
         mom = self.optimizer.needs_moments
-        self.mE, self.vE = (z(n_loc, d), z(n_loc, d)) if mom else (None, None)
+        self.mE, self.vE = (z(per, d), z(per, d)) if mom else (None, None)
         self.mW = z(2 * self.n_layers, d, d) if mom else None
         self.vW = z(2 * self.n_layers, d, d) if mom else None
-        self.flags = z(max(n_loc, 1), dt=I32)
+        self.flags = z(max(per, 1), dt=I32)
         self.scratch = z(16, dt=I32)
         self.err = z(1, dt=I32)
         self._cap = 0
         self.last_step_losses = None
-
-    def _row_block(self, rows, cols, vals):
-        sel = (rows >= self.r0) & (rows < self.r1)
-        rp, ci, va = coo_to_csr(rows[sel] - self.r0, cols[sel], vals[sel], self.n_loc)
-        return self.k.make_csr(rp, ci, va)
+        self._peers = [r for r in range(self.world) if r != self.rank]
+        self._grank = (lambda r: dist.get_global_rank(self.group, r)) if (self.group is not None and self.world > 1) else (lambda r: r)
 
     # ------------------------------------------------------------------------------------------
-    def _all_gather(self, local: torch.Tensor) -> torch.Tensor:
-        """local: [n_loc x d] (or the padded [per x d] T) -> self.X [world*per x d] indexed by global node id."""
+    def _post_exchange(self, src: torch.Tensor, a: int, b: int, buf: int) -> None:
+        """rows [a, b) of the local [per x d] matrix -> the same rows of this rank's slot in EVERY rank's X[buf]:
+        one grouped send/recv per panel, asynchronous (waited for by _wait before X[buf] is read)."""
         if self.world == 1:
-            if local.shape[0] == self.per:
-                return local
-            self.Epad[: self.n_loc] = local
-            return self.Epad
-        src = local
-        if local.shape[0] != self.per:
-            self.Epad[: self.n_loc] = local
-            src = self.Epad
-        dist.all_gather_into_tensor(self.X, src, group=self.group)
-        return self.X
+            return
+        X, per = self.X[buf], self.per
+        X[self.lo + a: self.lo + b].copy_(src[a:b])
+        ops_ = []
+        for r in self._peers:
+            ops_.append(dist.P2POp(dist.isend, src[a:b], self._grank(r), self.group))
+            ops_.append(dist.P2POp(dist.irecv, X[r * per + a: r * per + b], self._grank(r), self.group))
+        self._pending[buf].extend(dist.batch_isend_irecv(ops_))
+
+    def _wait(self, buf: int) -> None:
+        for w in self._pending[buf]:
+            w.wait()
+        self._pending[buf] = []
+
+    def _exchange_all(self, src: torch.Tensor, buf: int) -> None:
+        for a, b, _ in self.panels:
+            self._post_exchange(src, a, b, buf)
 
     def propagate(self):
-        k = self.k
-        for l in range(self.n_layers):
-            X = self._all_gather(self.E[l])
-            k.spmm(self.A, X, self.LE[l], False)
-            k.dense_fwd(self.E[l], self.LE[l], self.W1[l], self.W2[l], self.E[l + 1])
+        k, L = self.k, self.n_layers
+        self._exchange_all(self.E[0], 0)
+        for l in range(L):
+            buf = l & 1
+            self._wait(buf)
+            X = self.X[buf] if self.world > 1 else self.E[l]
+            for a, b, Ap in self.panels:
+                k.spmm(Ap, X, self.LE[l][a:b], False)
+                k.dense_fwd(self.E[l][a:b], self.LE[l][a:b], self.W1[l], self.W2[l], self.E[l + 1][a:b])
+                if l + 1 < L:
+                    self._post_exchange(self.E[l + 1], a, b, buf ^ 1)
         return self.E
 
     def train_step(self, uid, pos, neg, loss_acc) -> None:
         """uid/pos/neg int64 on self.device, identical on every rank; loss_acc double[1] += sum of -logsigmoid terms
         (replicated: every rank accumulates the same value)."""
-        k, d, B, W = self.k, self.d, int(uid.numel()), self.width
+        k, d, B, W, L = self.k, self.d, int(uid.numel()), self.width, self.n_layers
         if B > self._cap:
             self._R = torch.empty(3 * B, W, device=self.device, dtype=F32)
             self._Gr = torch.empty(3 * B, W, device=self.device, dtype=F32)
             self._cap = B
         R, Gr = self._R[: 3 * B], self._Gr[: 3 * B]
         self.propagate()
-        # ---- tail: R viewed as [B x 3 x W]; row (b, which) = b*3 + which -> ids interleaved the same way
-        ids = torch.stack((uid, pos + self.nU, neg + self.nU), dim=1).reshape(-1).contiguous()
+        # ---- tail: R viewed as [B x 3 x W]; row (b, which) = b*3 + which -> positions interleaved the same way
         bad = ((uid < 0) | (uid >= self.nU) | (pos < 0) | (pos >= self.nI) | (neg < 0) | (neg >= self.nI)).any()
         self.err |= bad.to(I32)
-        ids = ids.clamp(0, self.N - 1)
-        for l in range(self.n_layers + 1):
-            k.gather_rows(self.E[l], self.r0, self.r1, self.N, ids, R, l * d, self.err)
+        lay = self.layout
+        ids = torch.stack((lay.user_pos(uid.clamp(0, self.nU - 1)), lay.item_pos(pos.clamp(0, self.nI - 1)),
+                           lay.item_pos(neg.clamp(0, self.nI - 1))), dim=1).reshape(-1).contiguous()
+        for l in range(L + 1):
+            k.gather_rows(self.E[l], self.lo, self.hi, self.total, ids, R, l * d, self.err)
         if self.world > 1:
             dist.all_reduce(R, op=dist.ReduceOp.SUM, group=self.group)
         k.rows_grad(R, B, W, Gr, loss_acc)
         for g in self.G:
             g.zero_()
-        for l in range(self.n_layers + 1):
-            k.scatter_rows(self.G[l], self.r0, self.r1, ids, Gr, l * d, self.flags, self.scratch)
+        for l in range(L + 1):
+            k.scatter_rows(self.G[l], self.lo, self.hi, ids, Gr, l * d, self.flags, self.scratch)
         # ---- backward through the layers
-        for l in reversed(range(self.n_layers)):
-            Tl = self.T[: self.n_loc]
-            k.dense_bwd(self.E[l], self.LE[l], self.E[l + 1], self.G[l + 1], self.W1[l], self.W2[l], self.G[l], Tl,
-                        self.dW[l], self.dW[self.n_layers + l])
-            X = self._all_gather(self.T)
-            k.spmm(self.AT, X, self.G[l], True)
+        for l in reversed(range(L)):
+            buf = l & 1
+            for pi, (a, b, _) in enumerate(self.panels):
+                k.dense_bwd(self.E[l][a:b], self.LE[l][a:b], self.E[l + 1][a:b], self.G[l + 1][a:b], self.W1[l], self.W2[l],
+                            self.G[l][a:b], self.T[a:b], self.dWp[pi, 0], self.dWp[pi, 1])
+                self._post_exchange(self.T, a, b, buf)
+            torch.sum(self.dWp[:, 0], dim=0, out=self.dW[l])
+            torch.sum(self.dWp[:, 1], dim=0, out=self.dW[L + l])
+            self._wait(buf)
+            k.spmm(self.AT, self.X[buf] if self.world > 1 else self.T, self.G[l], True)
         if self.world > 1:
             dist.all_reduce(self.dW, op=dist.ReduceOp.SUM, group=self.group)
         # ---- optimizer: parameter order embedding, W1.*, W2.* (nn.Module.parameters()); all tensors share the step count
         opt = self.optimizer.opt_struct(self.optimizer.step_count + 1)
         k.opt_step(self.E[0], self.G[0], self.mE, self.vE, opt)
-        for i in range(2 * self.n_layers):
-            Wt = self.W1[i] if i < self.n_layers else self.W2[i - self.n_layers]
+        for i in range(2 * L):
+            Wt = self.W1[i] if i < L else self.W2[i - L]
             k.opt_step(Wt, self.dW[i], self.mW[i] if self.mW is not None else None,
                        self.vW[i] if self.vW is not None else None, opt)
         self.optimizer.step_count += 1
@@ -243,5 +281,9 @@ class ShardedNGCFTrainer:
         return float(means.to(F64).sum().item())
 
     def gather_embedding(self) -> torch.Tensor:
-        """Full E_0 [N x d] on every rank (tests)."""
-        return self._all_gather(self.E[0])[: self.N].clone()
+        """Full E_0 [N x d] in the reference's node order on every rank (tests)."""
+        if self.world == 1:
+            return self.layout.to_node_order(self.E[0])
+        full = torch.empty(self.total, self.d, device=self.device, dtype=F32)
+        dist.all_gather_into_tensor(full, self.E[0].contiguous(), group=self.group)
+        return self.layout.to_node_order(full)
