@@ -265,6 +265,22 @@ int yr_laplacian_build(const int64_t* user, const int64_t* item, const float* ra
                        int64_t num_users, int64_t num_items, int32_t* rowptr, int32_t* col, float* val,
                        void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
 
+/* ---- Per-user random split ------------------------------------------------------------------------
+ * MFDataPipeline.split (data/datasets/mf_data_pipeline.py:18-52), the pairwise branch: per user
+ * train_test_split(test_size=.2, random_state=seed) then train_test_split(rest, test_size=.25, random_state=seed) —
+ * sklearn ShuffleSplit on np.random.RandomState(seed).permutation(n), i.e. MT19937 + the legacy Fisher-Yates shuffle,
+ * reproduced on the device (the permutation depends on the list length only: one table row per length).
+ * ptr/items: CSR over users of the interactions in DataFrame order (int64 item ids). yr_split_sizes gives the three list
+ * lengths per user (the caller scans them into train_ptr / valid_ptr / test_ptr); yr_split_per_user fills the lists in
+ * the order the reference's frames hold them. ws: yr_split_ws_bytes(max list length). *err = 1: internal stream too
+ * short (does not happen with that sizing). */
+size_t yr_split_ws_bytes(int max_list_len);
+int yr_split_sizes(const int32_t* ptr, int64_t num_users, int32_t* n_train, int32_t* n_valid, int32_t* n_test, yr_stream stream);
+int yr_split_per_user(const int32_t* ptr, const int64_t* items, int64_t num_users, int max_list_len, uint32_t seed,
+                      const int32_t* train_ptr, const int32_t* valid_ptr, const int32_t* test_ptr,
+                      int64_t* train_items, int64_t* valid_items, int64_t* test_items, void* ws, size_t ws_bytes,
+                      int32_t* err, yr_stream stream);
+
 /* ---- Scaled synthetic graph (BASELINE config 5) ------------------------------------------------------
  * The reference has no generator (it reads Yelp's review.json); this is the input producer of the scaled benchmark.
  * yr_synth_user_rows: for every user u the SORTED, DUPLICATE-FREE item list of a synthetic bipartite graph: the number of

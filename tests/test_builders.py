@@ -67,3 +67,28 @@ def test_out_of_range_id_raises():
     i = torch.tensor([0, 1, 1], device=dev)
     with pytest.raises(IndexError):
         build_laplacian_csr_device(u, i, torch.ones(3, device=dev), 3, 2)
+
+
+def test_device_split_matches_host_restatement_and_eval_csr():
+    """MFDataPipeline.split on the device (yr_split_per_user: MT19937 + numpy's legacy shuffle) == data.synthetic.split_per_user
+    (pinned to the reference's sklearn split, tests/test_host_logic.py) list for list, order included; the evaluation CSRs
+    built from it on the device == build_eval_csr(eval_lists(...)); and MFTrainer.evaluate accepts them."""
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    from yelprecommendation_b200.data.split import eval_csr_device, split_per_user_device
+    for seed, (nu, ni, nnz) in ((42, (900, 700, 30_000)), (7, (31_668, 38_048, 1_561_406))):
+        inter = syn.make_interactions(num_users=nu, num_items=ni, nnz=nnz, seed=3 if nu < 1000 else 2018,
+                                      n_clusters=4 if nu < 1000 else 16)
+        host = syn.split_per_user(inter, seed=seed)
+        deg = np.bincount(inter.user, minlength=nu)
+        ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)).cuda()
+        dsp = split_per_user_device(ptr, torch.from_numpy(inter.item.astype(np.int64)).cuda(), seed=seed)
+        for name in ("train", "valid", "test"):
+            assert np.array_equal(getattr(dsp, f"{name}_ptr").cpu().numpy(), getattr(host, f"{name}_ptr")), name
+            assert np.array_equal(getattr(dsp, f"{name}_items").cpu().numpy(), getattr(host, f"{name}_items")), name
+        for mode in ("valid", "test"):
+            uid, pos, mask = syn.eval_lists(host, mode)
+            ref = build_eval_csr(uid, pos, mask, ni)
+            got = eval_csr_device(dsp, mode, ni, 10)
+            for k in ("eval_uid", "mask_ptr", "mask_idx", "act_ptr", "act_idx", "act_nuniq"):
+                assert np.array_equal(getattr(got, k).cpu().numpy()[: getattr(ref, k).size], getattr(ref, k)), (mode, k)

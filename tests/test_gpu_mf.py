@@ -190,7 +190,10 @@ def test_full_size_yelp_shape_vs_oracle(name, wd, det):
     orc = cport.MFTrainerOracle(U0, V0, name, 1e-2, wd)
     ototal, osteps = orc.train([{k: v.numpy() for k, v in x.items()} for x in b])
     assert isclose(total, ototal, rel_tol=1e-6)
-    _same_losses(tr.last_step_losses.cpu().numpy(), osteps)
+    if name != "sgd" or det:
+        _same_losses(tr.last_step_losses.cpu().numpy(), osteps)
+    else:                              # register path: expf / log1pf on the fp32 pipe (<= 1 ulp per term)
+        assert rel_err(tr.last_step_losses.cpu().numpy(), osteps) < 1e-6
     Ug, Vg = (w.detach().cpu().numpy() for w in (tr.model.user_embedding.weight, tr.model.item_embedding.weight))
     if name != "sgd" or det:
         assert np.array_equal(Ug, orc.U) and np.array_equal(Vg, orc.V)
@@ -247,9 +250,12 @@ def test_other_embedding_widths_vs_oracle(d, name, wd):
     orc = cport.MFTrainerOracle(U0, V0, name, 1e-2, wd)
     ototal, osteps = orc.train([{k: v.numpy() for k, v in x.items()} for x in b])
     assert isclose(total, ototal, rel_tol=1e-6)
-    _same_losses(tr.last_step_losses.cpu().numpy(), osteps)
-    Ug, Vg = (w.detach().cpu().numpy() for w in (tr.model.user_embedding.weight, tr.model.item_embedding.weight))
     register_path = name == "sgd" and wd == 0.0 and d <= 256
+    if register_path:
+        assert rel_err(tr.last_step_losses.cpu().numpy(), osteps) < 1e-6
+    else:
+        _same_losses(tr.last_step_losses.cpu().numpy(), osteps)
+    Ug, Vg = (w.detach().cpu().numpy() for w in (tr.model.user_embedding.weight, tr.model.item_embedding.weight))
     if register_path:
         assert rel_err(Ug, orc.U) < RTOL and rel_err(Vg, orc.V) < RTOL
         tu_, tv_ = _touches(b, nU, nI)

@@ -31,6 +31,7 @@ SYMBOLS = (
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
     "yr_sample_negatives", "yr_laplacian_ws_bytes", "yr_laplacian_build",
     "yr_synth_user_rows", "yr_laplacian_binary_values",
+    "yr_split_ws_bytes", "yr_split_sizes", "yr_split_per_user",
 )
 
 YR_OPT_SGD, YR_OPT_ADAM, YR_OPT_ADAMW = 0, 1, 2
@@ -169,6 +170,9 @@ def load() -> C.CDLL:
         "yr_laplacian_build": (C.c_int, [p, p, p, i64, i64, i64, p, p, p, p, sz, p, p]),
         "yr_synth_user_rows": (C.c_int, [C.c_uint64, i64, i64, C.c_double, C.c_double, C.c_double, i32, i32, p, p, p, p]),
         "yr_laplacian_binary_values": (C.c_int, [p, i64, p, p, p, p, p]),
+        "yr_split_ws_bytes": (sz, [i32]),
+        "yr_split_sizes": (C.c_int, [p, i64, p, p, p, p]),
+        "yr_split_per_user": (C.c_int, [p, p, i64, i32, C.c_uint32, p, p, p, p, p, p, p, sz, p, p]),
         "yr_sample_negatives": (C.c_int, [p, i64, p, p, i64, i64, C.c_uint64, C.c_uint64, i32, p, p, p]),
         "yr_shard_gather_rows": (C.c_int, [p, i64, i64, i64, i32, p, i64, p, i64, p, p]),
         "yr_bpr_rows_grad": (C.c_int, [p, i32, i64, i64, i64, p, p, p]),

@@ -312,14 +312,14 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
         const Row<VPL> pr = ld_row<VPL>(st.V + p * D, lane);
         const Row<VPL> nr = ld_row<VPL>(st.V + n * D, lane);
         const float x = __fsub_rn(warp_sum(dot_partial<VPL>(ur, pr)), warp_sum(dot_partial<VPL>(ur, nr)));
-        const float g = __fmul_rn(neg_logsigmoid_grad(x), inv_nb);
+        const float g = __fmul_rn(neg_logsigmoid_grad_fast(x), inv_nb);
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
           const float a = __fsub_rn(__fmul_rn(g, pr.x[j]), __fmul_rn(g, nr.x[j]));   // Q2: two rounded products
           const float c = __fmul_rn(g, ur.x[j]);
           gu.x[j] = __fmul_rn(neg_lr, a); gp.x[j] = __fmul_rn(neg_lr, c); gn.x[j] = -gp.x[j];
         }
-        wl = (double)neg_logsigmoid(x);
+        wl = (double)neg_logsigmoid_fast(x);
       }
       const int64_t uu = u, pp = p, nn = n;
       // ids of the next step (read-only input): requested before the barrier, consumed after the second one

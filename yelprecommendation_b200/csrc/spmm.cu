@@ -213,20 +213,17 @@ static int spmm_variant() {
 template <int D>
 static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s,
                        const int32_t* row_flag = nullptr) {
-  // Default = the measured best of the sweep in profiles/r02_spmm_sweep.txt (B200, Yelp-shape graph): 128-thread CTAs
-  // bounded to 64 registers (8 CTAs = 32 warps per SM), 4 neighbour rows in flight per group, direct index loads:
-  // 55.8 us at d = 64 / 111 us at d = 128 against 85.5 / 216 us for the round-1 shape (variant 0).
+  // Default = the measured best of the sweeps in profiles/r02_spmm_sweep*.txt (B200, Yelp-shape graph, sorted plan): 128-thread
+  // CTAs bounded to 48 registers (10 CTAs = 40 warps per SM), 4 neighbour rows in flight per group, direct index loads:
+  // 53.8 us at d = 64 (14.9 TB/s of gathers) / 98.9 us at d = 128 (16.2 TB/s) against a measured L2 -> SM gather ceiling of
+  // 17.6 TB/s (scripts/l2_gather_bench.cu); the round-1 shape (variant 0, row-order plan) took 85.5 / 216 us.
   switch (spmm_variant()) {
     case 0: return launch_spmm_v<D, 256, (D <= 64 ? 3 : 2), 8, false>(A, X, Y, accumulate, s, row_flag);
     case 1: return launch_spmm_v<D, 128, 8, 4, false>(A, X, Y, accumulate, s, row_flag);
-    case 2: return launch_spmm_v<D, 128, 12, 4, true>(A, X, Y, accumulate, s, row_flag);
-    case 3: return launch_spmm_v<D, 128, 16, 2, true>(A, X, Y, accumulate, s, row_flag);
+    case 2: return launch_spmm_v<D, 128, 8, 4, true>(A, X, Y, accumulate, s, row_flag);
+    case 3: return launch_spmm_v<D, 128, 8, 6, true>(A, X, Y, accumulate, s, row_flag);
     case 4: return launch_spmm_v<D, 64, 16, 4, true>(A, X, Y, accumulate, s, row_flag);
-    case 5: return launch_spmm_v<D, 256, 4, 4, true>(A, X, Y, accumulate, s, row_flag);
-    case 7: return launch_spmm_v<D, 128, 10, 4, true>(A, X, Y, accumulate, s, row_flag);
-    case 8: return launch_spmm_v<D, 128, 8, 6, true>(A, X, Y, accumulate, s, row_flag);
-    case 9: return launch_spmm_v<D, 128, 6, 8, true>(A, X, Y, accumulate, s, row_flag);
-    default: return launch_spmm_v<D, 128, 8, 4, true>(A, X, Y, accumulate, s, row_flag);
+    default: return launch_spmm_v<D, 128, 10, 4, true>(A, X, Y, accumulate, s, row_flag);
   }
 }
 
