@@ -459,6 +459,15 @@ int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const float* Vemb, co
 int yr_topk_masked_row(const float* pred, int64_t nI, const int64_t* mask_idx, int64_t n_mask, int K,
                        int64_t* topk_out, yr_stream stream);
 
+/* The same for a batch of score rows of ANY model — the device half of DCN's chunked evaluator
+ * (trainers/dcn_trainer.py:145-203, :188-203): pred [n_rows x ld] holds one full-catalog score row per evaluated user
+ * (assembled chunk by chunk by the caller's model), mask CSR (int32, ids in [0, nI)) per row, masked positions take
+ * `mask_value` (DCN: 0, its outputs are sigmoids; MF / NGCF: -3.40282e+38), K best by (score desc, item id asc) per row.
+ * ws: n_rows * nI bytes. */
+int yr_topk_masked_rows(const float* pred, int64_t ld, int64_t n_rows, int64_t nI, const int32_t* mask_ptr,
+                        const int32_t* mask_idx, float mask_value, int K, int64_t* topk_out, void* ws, size_t ws_bytes,
+                        yr_stream stream);
+
 /* metric.py:7-109 on device for already-computed recommendations: predicted [n x ldp] int64 (first K columns
  * used), actual as CSR in original order. Same outputs as yr_eval_topk_metrics. */
 int yr_topk_metrics(const int64_t* predicted, int64_t ldp, int64_t n, const int32_t* act_ptr,

@@ -219,3 +219,49 @@ def test_full_catalog_yelp_shape_properties():
     # checksum of checksums: metric sums equal the sum of the per-row terms
     assert np.allclose(sums[:4], um.sum(axis=0), rtol=1e-12)
     assert sums[0] / len(uid) > 0.01                                          # planted structure is recoverable
+
+
+def test_chunked_evaluator_for_non_dot_product_models_like_dcn():
+    """the DCN trainer's chunked evaluator (trainers/dcn_trainer.py:145-203) on the fused kernels — any scoring
+    model, catalog scored in chunks of cfg.batch_size items, train items masked with 0 (sigmoid outputs, :191), top-K by
+    (score desc, id asc), the reference's metrics; 'valid' evaluates the first 1,000 rows of the frame (:152-153)."""
+    import pandas as pd
+    from oracle import torch_port as tp
+    from yelprecommendation_b200.trainers import ChunkedTopKEvaluator
+    rng = np.random.default_rng(5)
+    nU, nI, K, d = 1500, 2311, 10, 16
+    A = torch.from_numpy(rng.standard_normal((nU, d)).astype(np.float32)).cuda()
+    Bm = torch.from_numpy(rng.standard_normal((nI, d)).astype(np.float32)).cuda()
+    cat = torch.from_numpy(rng.integers(0, 7, nI)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(7).astype(np.float32)).cuda()
+
+    def score_fn(uid, items):                               # a cross-feature model: not a dot product of two tables
+        x = A[uid].unsqueeze(1) * Bm[items].unsqueeze(0)    # [R, C, d]
+        out = torch.sigmoid(0.1 * (x.sum(-1) + 0.3 * (x * x).sum(-1)) + bias[cat[items]].unsqueeze(0))
+        seen[(int(uid[0]), int(items[0]))] = (uid.cpu().numpy(), items.cpu().numpy(), out.cpu().numpy())   # what the model returned
+        return out
+
+    seen = {}
+
+    users = rng.permutation(nU)[:1200]
+    pos = [rng.permutation(nI)[: int(rng.integers(1, 9))].tolist() for _ in users]
+    mask = [rng.permutation(nI)[: int(rng.integers(0, 30))].tolist() for _ in users]
+    frame = pd.DataFrame({"pos_items": pos, "mask_items": mask}, index=pd.Index(users, name="user_id"))
+    ev = ChunkedTopKEvaluator(nI, K, "cuda", chunk_size=256, mask_value=0.0, rows_per_block=50)
+    for mode, n_rows in (("valid", 1000), ("test", 1200)):
+        seen.clear()
+        got = ev.evaluate(score_fn, frame, mode=mode)
+        full = np.full((n_rows, nI), np.nan, np.float32)     # the catalog scores exactly as the chunked calls produced them
+        row_of = {int(u): r for r, u in enumerate(users[:n_rows])}
+        for uid_c, items_c, out_c in seen.values():
+            full[np.array([row_of[int(u)] for u in uid_c])[:, None], items_c[None, :]] = out_c
+        assert not np.isnan(full).any()
+        predicted = []
+        for r in range(n_rows):
+            s = full[r].copy()
+            s[np.asarray(mask[r], dtype=np.int64)] = 0.0
+            order = np.lexsort((np.arange(nI), -s))[:K]
+            predicted.append(order)
+        assert np.array_equal(ev.last_topk.cpu().numpy(), np.stack(predicted)), mode
+        want = tp.all_metrics(pos[:n_rows], predicted, K)
+        assert np.allclose(got, want, rtol=1e-12), (mode, got, want)

@@ -24,7 +24,7 @@ SYMBOLS = (
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
-    "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_metrics",
+    "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_masked_rows", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex",
     "yr_nsbce_loss",
@@ -150,6 +150,7 @@ def load() -> C.CDLL:
         "yr_ngcf_train_step_ex": (C.c_int, [C.POINTER(YrNgcfState), C.POINTER(YrOpt), f32, p, p, p, i64, p, i32, p]),
         "yr_ngcf_concat": (C.c_int, [p, i32, i64, i32, p, p]),
         "yr_topk_masked_row": (C.c_int, [p, i64, p, i64, i32, p, p]),
+        "yr_topk_masked_rows": (C.c_int, [p, i64, i64, i64, p, p, f32, i32, p, p, sz, p]),
         "yr_topk_metrics": (C.c_int, [p, i64, i64, p, p, p, p, i32, p, p, p]),
         "yr_transpose_items": (C.c_int, [p, i64, i32, p, i64, p]),
         "yr_eval_ws_bytes": (sz, [i64, i32, i32]),

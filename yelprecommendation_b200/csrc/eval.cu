@@ -568,6 +568,61 @@ topk_masked_row_kernel(const float* __restrict__ pred, int64_t nI, const int64_t
   }
 }
 
+// Batched form for model-agnostic evaluators (DCN's chunked evaluator, trainers/dcn_trainer.py:145-203): one block per score
+// row, the row's mask list comes from a CSR, masked positions take `mask_value` (DCN masks sigmoid outputs with 0, :191).
+__global__ void __launch_bounds__(1024)
+topk_masked_rows_kernel(const float* __restrict__ pred, int64_t ld, int64_t nI, const int32_t* __restrict__ mask_ptr,
+                        const int32_t* __restrict__ mask_idx, float mask_value, int K, int64_t* __restrict__ topk_out,
+                        unsigned char* __restrict__ flags_all) {
+  __shared__ float s_s[32];
+  __shared__ int64_t s_i[32];
+  __shared__ float best_s;
+  __shared__ int64_t best_i;
+  const int64_t row = blockIdx.x;
+  const float* p = pred + row * ld;
+  unsigned char* flags = flags_all + row * nI;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t i = tid; i < nI; i += blockDim.x) flags[i] = 0;
+  __syncthreads();
+  for (int m = mask_ptr[row] + tid; m < mask_ptr[row + 1]; m += blockDim.x) {
+    const int j = mask_idx[m];
+    if (j >= 0 && j < nI) flags[j] = 1;
+  }
+  __syncthreads();
+  float prev_s = INFINITY;
+  int64_t prev_i = -1;
+  for (int r = 0; r < K; ++r) {
+    float bs = -INFINITY;
+    int64_t bi = -1;
+    for (int64_t i = tid; i < nI; i += blockDim.x) {
+      const float s = flags[i] ? mask_value : p[i];
+      const bool after = (s < prev_s) || (s == prev_s && i > prev_i);
+      if (after && (bi < 0 || s > bs || (s == bs && i < bi))) { bs = s; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(kFull, bs, o);
+      const int64_t oi = __shfl_xor_sync(kFull, bi, o);
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+    }
+    if (lane == 0) { s_s[warp] = bs; s_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bs = (lane < (int)(blockDim.x >> 5)) ? s_s[lane] : -INFINITY;
+      bi = (lane < (int)(blockDim.x >> 5)) ? s_i[lane] : -1;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(kFull, bs, o);
+        const int64_t oi = __shfl_xor_sync(kFull, bi, o);
+        if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+      }
+      if (lane == 0) { best_s = bs; best_i = bi; topk_out[row * K + r] = bi; }
+    }
+    __syncthreads();
+    prev_s = best_s;
+    prev_i = best_i;
+    __syncthreads();
+  }
+}
+
 // warp per row; tolerates duplicates inside `predicted` exactly like Python's sets do.
 __global__ void __launch_bounds__(256)
 topk_metrics_kernel(const int64_t* __restrict__ predicted, int64_t ldp, int64_t n,
@@ -627,6 +682,19 @@ extern "C" int yr_topk_masked_row(const float* pred, int64_t nI, const int64_t* 
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(flags, s);
   return (int)e;
+}
+
+extern "C" int yr_topk_masked_rows(const float* pred, int64_t ld, int64_t n_rows, int64_t nI, const int32_t* mask_ptr,
+                                   const int32_t* mask_idx, float mask_value, int K, int64_t* topk_out, void* ws,
+                                   size_t ws_bytes, yr_stream stream) {
+  if (!pred || !topk_out || !mask_ptr || !mask_idx || !ws || nI <= 0 || K <= 0 || K > nI || n_rows < 0 || ld < nI)
+    return YR_ERR_BAD_ARG;
+  if (ws_bytes < (size_t)n_rows * (size_t)nI) return YR_ERR_WORKSPACE;
+  if (n_rows == 0) return YR_OK;
+  topk_masked_rows_kernel<<<(unsigned)n_rows, 1024, 0, (cudaStream_t)stream>>>(pred, ld, nI, mask_ptr, mask_idx, mask_value, K,
+                                                                              topk_out, (unsigned char*)ws);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
 }
 
 extern "C" int yr_topk_metrics(const int64_t* predicted, int64_t ldp, int64_t n, const int32_t* act_ptr,
