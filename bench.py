@@ -216,7 +216,12 @@ def config5_extras(extra, dev, rank, world, barrier, max_over_ranks, pk, args):
             rec = {"value": val, "unit": UNIT, "ms_per_step": ms5, "scaling": "strong", "batch": B5,
                    "tables": f"{nU5:,}u x {nI5:,}i x d{d5} row-sharded over {world} GPU(s)",
                    "efficiency_vs_n1": eff(f"c5_mf_{oname}", val)}
-            rec.update(tr.traffic_model(B5, pk) if hasattr(tr, "traffic_model") else {})
+            tm = tr.traffic_model(B5)
+            rec.update(tm)
+            # every GPU moves alg_bytes_per_triple * B / world through its HBM per step; the exchange moves nvlink_bytes over
+            # NVLink 5 (900 GB/s per direction per GPU): whichever fraction is larger is what bounds the step
+            rec["hbm_frac"] = tm["alg_bytes_per_triple"] * B5 / world / (ms5 * 1e-3) / 1e9 / pk["hbm"]
+            rec["nvlink_frac_of_900GBps"] = tm["nvlink_bytes_per_step_per_gpu"] / 2 / (ms5 * 1e-3) / 900e9 if world > 1 else None
             extra[f"c5_mf_{oname}"] = rec
             del tr
         except Exception as ex:

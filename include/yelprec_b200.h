@@ -347,6 +347,34 @@ int yr_shard_accumulate(const yr_shard_state* st, const yr_opt* opt, const int64
                         int64_t g_ld, yr_stream stream);
 int yr_shard_step(const yr_shard_state* st, const yr_opt* opt, int64_t max_rows, yr_stream stream);
 
+/* Packed gather for the all-to-all form of the exchange: out[j*out_ld ..] = (sel[j] ? T1 : T0)[row[j], :] — an owner collects,
+ * in slot order, the rows of its user-table shard (sel 0) and item-table shard (sel 1) that a requester's slice needs. The
+ * caller guarantees row[j] is inside the selected shard. */
+int yr_shard_gather_local(const float* T0, const float* T1, int d, const int32_t* sel, const int32_t* row, int64_t n,
+                          float* out, int64_t out_ld, yr_stream stream);
+
+/* Ordered (atomics-free) form of yr_shard_accumulate: the caller has grouped the n received gradient rows by local row with
+ * a STABLE sort — rows_sorted[j] = local row (ascending), src[j] = index of that gradient row in G — and one warp per
+ * segment sums it left to right (arrival order: requester rank, then slot) into the row's scratch. Bit-identical run to
+ * run. list_rows != 0 also lists the rows for a sparse step (plain SGD, sparse Adam). */
+int yr_shard_accumulate_sorted(const yr_shard_state* st, const yr_opt* opt, const int32_t* rows_sorted, const int32_t* src,
+                               int64_t n, const float* G, int64_t g_ld, int list_rows, yr_stream stream);
+
+/* Sparse-traffic ("catch-up") Adam / AdamW for a shard: torch's optimizer is dense (a row without a gradient keeps moving
+ * while its moments are non-zero, trainers/base_trainer.py:34-40), but such a row follows a fixed recurrence, so only the
+ * rows of the batch are visited: before they are gathered for the forward pass they replay the steps they missed
+ * (yr_shard_catch_up: last[row] + 1 .. step - 1, g = 0, the same update code and scalars as the dense sweep), and the rows
+ * listed by yr_shard_accumulate_sorted then take step opt->step with their gradient. Bit-identical to
+ * yr_shard_step's sweep. scal: 2 * n_scal_steps floats from yr_adam_scalars; last: int32 per local row, zero on first
+ * use. flush != 0 brings EVERY row up to opt->step (before the tables are read: evaluation, state_dict). */
+int yr_adam_scalars(const yr_opt* opt, int n_steps, float* scal, yr_stream stream);
+/* Rows that are about to be READ for the forward pass of step opt->step (rows_sorted: ascending local rows, duplicates
+ * allowed) are first brought up to step opt->step - 1. */
+int yr_shard_catch_up(const yr_shard_state* st, const yr_opt* opt, const float* scal, int32_t n_scal_steps, int32_t* last,
+                      const int32_t* rows_sorted, int64_t n, yr_stream stream);
+int yr_shard_step_sparse_adam(const yr_shard_state* st, const yr_opt* opt, const float* scal, int32_t n_scal_steps,
+                              int32_t* last, int64_t max_rows, int flush, yr_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * CDAE  (models/cdae.py, loss.py:7-16 NSBCELoss, trainers/cdae_trainer.py) — BASELINE config 4
  * ---------------------------------------------------------------------------------------------- */

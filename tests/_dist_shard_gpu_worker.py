@@ -28,15 +28,20 @@ def main():
         U0, V0 = (torch.from_numpy(np.ascontiguousarray(a)) for a in syn.planted_embeddings(inter, d=d, seed=5))
         batches = syn.to_batches(u, p, n, 2047)[:5]
         cfg = SimpleNamespace(embed_size=d, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
-        tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0))
-        loss = tr.train(batches)
-        U, V = tr.gather_tables()
         port = MFPort(U0, V0, optimizer=optname, lr=lr, weight_decay=wd)
         ref_loss, _ = port.train(batches)
-        for got, ref in ((U.cpu(), port.user.weight.detach()), (V.cpu(), port.item.weight.detach())):
-            rel = float((got - ref).norm() / ref.norm())
-            assert rel < 1e-5, (optname, rel)
-        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+        got_tables = {}
+        for exchange, adam_mode in (("all_to_all", "sparse"), ("all_to_all", "dense"), ("all_reduce", "dense")):
+            tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0), exchange=exchange, adam_mode=adam_mode)
+            loss = tr.train(batches)
+            U, V = tr.gather_tables()
+            got_tables[(exchange, adam_mode)] = (U.clone(), V.clone())
+            for got, ref in ((U.cpu(), port.user.weight.detach()), (V.cpu(), port.item.weight.detach())):
+                rel = float((got - ref).norm() / ref.norm())
+                assert rel < 1e-5, (optname, exchange, adam_mode, rel)
+            assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+        a, b = got_tables[("all_to_all", "sparse")], got_tables[("all_to_all", "dense")]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "catch-up Adam must equal the dense sweep bit for bit"
     # ---- row-sharded NGCF (rectangular SpMM blocks, all-gather per layer, all-reduce of dW)
     inter = syn.make_interactions(num_users=1203, num_items=958, nnz=30000, seed=21, n_clusters=4, star_ratings=True)
     split = syn.split_per_user(inter, seed=42)

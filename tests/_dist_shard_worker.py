@@ -69,6 +69,68 @@ class CpuShardKernels:
         s["flags"].zero_()
 
 
+def _cpu_a2a_methods():
+    """the all-to-all choreography's device pieces on CPU tensors (yr_shard_gather_local / yr_bpr_rows_grad on a slice /
+    yr_shard_accumulate_sorted / yr_shard_step_sparse_adam)"""
+
+    def gather_local(self, su, sv, sel, row, out):
+        r = row.long()
+        out.copy_(torch.where((sel != 0).unsqueeze(1), sv["T"][r.clamp(max=sv["T"].shape[0] - 1)], su["T"][r.clamp(max=su["T"].shape[0] - 1)]))
+
+    def rows_grad_slice(self, R, B, b0, b1, G, loss_acc):
+        n = b1 - b0
+        u, p, q = R[:n, 0], R[:n, 1], R[:n, 2]
+        x = (u * p).sum(1) - (u * q).sum(1)
+        loss_acc += (-F.logsigmoid(x)).double().sum()
+        g = (-torch.sigmoid(-x) / B).unsqueeze(1)
+        G[:n, 0] = g * p - g * q
+        G[:n, 1] = g * u
+        G[:n, 2] = -(g * u)
+
+    def accumulate_sorted(self, s, opt, rows_sorted, src, G, list_rows):
+        s["g"].index_add_(0, rows_sorted.long(), G[src.long()])
+        s["flags"][rows_sorted.long()] = 1
+
+    def adam_scalars(self, opt, n_steps, scal):
+        pass
+
+    def catch_up(self, s, opt, scal, n_scal, rows_sorted, d):
+        rows = torch.unique(rows_sorted.long())
+        last = s["last"][rows].long()
+        for t in range(int(last.min()) + 1, opt.step):
+            sel = rows[last < t]
+            if sel.numel() == 0:
+                continue
+            T, m, v = s["T"][sel], s["m"][sel], s["v"][sel]
+            _opt_step_cpu(T, torch.zeros(sel.numel(), d), m, v, type(opt)(opt.kind, t, opt.lr, opt.weight_decay, opt.beta1, opt.beta2, opt.eps))
+            s["T"][sel], s["m"][sel], s["v"][sel] = T, m, v
+        s["last"][rows] = torch.maximum(s["last"][rows], torch.full_like(s["last"][rows], opt.step - 1))
+
+    def step_sparse_adam(self, s, opt, scal, n_scal, max_rows, d, flush=False):
+        n = s["hi"] - s["lo"]
+        t_now = opt.step
+        rows = torch.arange(n) if flush else torch.nonzero(s["flags"][:n]).flatten()
+        if rows.numel() == 0:
+            return
+        last = s["last"][rows].long()
+        for t in range(int(last.min()) + 1, t_now + 1):
+            sel = rows[last < t]
+            if sel.numel() == 0:
+                continue
+            g = s["g"][sel] if (t == t_now and not flush) else torch.zeros(sel.numel(), d)
+            T, m, v = s["T"][sel], s["m"][sel], s["v"][sel]
+            o = type(opt)(opt.kind, t, opt.lr, opt.weight_decay, opt.beta1, opt.beta2, opt.eps)
+            _opt_step_cpu(T, g, m, v, o)
+            s["T"][sel], s["m"][sel], s["v"][sel] = T, m, v
+        s["last"][rows] = t_now
+        if not flush:
+            s["g"][rows] = 0
+            s["flags"][rows] = 0
+
+    return dict(gather_local=gather_local, rows_grad_slice=rows_grad_slice, accumulate_sorted=accumulate_sorted,
+                adam_scalars=adam_scalars, step_sparse_adam=step_sparse_adam, catch_up=catch_up)
+
+
 def _opt_step_cpu(T, g, m, v, opt):
     kind = {v_: k for k, v_ in _cabi.OPT_KINDS.items()}[opt.kind]
     if kind == "sgd":
@@ -82,6 +144,10 @@ def _opt_step_cpu(T, g, m, v, opt):
     v.mul_(opt.beta2).addcmul_(g, g, value=1 - opt.beta2)
     bc1, bc2 = 1 - opt.beta1 ** opt.step, 1 - opt.beta2 ** opt.step
     T.addcdiv_(m, (v.sqrt() / np.sqrt(bc2)).add_(opt.eps), value=-opt.lr / bc1)
+
+
+for _name, _fn in _cpu_a2a_methods().items():
+    setattr(CpuShardKernels, _name, _fn)
 
 
 class CpuNgcfShardKernels:
@@ -179,17 +245,19 @@ def main():
     batches = syn.to_batches(u, p, n, 509)[:4]          # 509: not a multiple of world -> ragged slices
     for optname, lr, wd in (("sgd", 0.05, 0.0), ("adam", 1e-2, 1e-4), ("adamw", 1e-2, 1e-2)):
         cfg = SimpleNamespace(embed_size=32, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
-        tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0), device="cpu", kernels=CpuShardKernels())
-        assert (tr.u1 - tr.u0) in (150, 151) and (tr.i1 - tr.i0) in (78, 79)
-        loss = tr.train(batches)
-        U, V = tr.gather_tables()
         port = MFPort(U0, V0, optimizer=optname, lr=lr, weight_decay=wd)
         ref_loss, _ = port.train(batches)
-        for got, ref in ((U, port.user.weight.detach()), (V, port.item.weight.detach())):
-            assert got.shape == ref.shape
-            rel = float((got - ref).norm() / ref.norm())
-            assert rel < 2e-6, (optname, rel)
-        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
+        for exchange, adam_mode in (("all_to_all", "sparse"), ("all_to_all", "dense"), ("all_reduce", "dense")):
+            tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0), device="cpu", kernels=CpuShardKernels(),
+                                  exchange=exchange, adam_mode=adam_mode)
+            assert (tr.u1 - tr.u0) in (150, 151) and (tr.i1 - tr.i0) in (78, 79)
+            loss = tr.train(batches)
+            U, V = tr.gather_tables()
+            for got, ref in ((U, port.user.weight.detach()), (V, port.item.weight.detach())):
+                assert got.shape == ref.shape
+                rel = float((got - ref).norm() / ref.norm())
+                assert rel < 2e-6, (optname, exchange, adam_mode, rel)
+            assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss), (loss, ref_loss)
     # out-of-range id -> IndexError on every rank (nn.Embedding behaviour)
     bad = dict(batches[0])
     bad["pos_item"] = bad["pos_item"].clone()

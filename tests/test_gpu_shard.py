@@ -27,15 +27,24 @@ def test_sharded_trainer_world1_matches_oracle(optname, lr, wd, d):
     batches = syn.to_batches(u, p, n, 1023)[:6]
     U0, V0 = (torch.from_numpy(np.ascontiguousarray(a)) for a in syn.planted_embeddings(inter, d=d, seed=5))
     cfg = SimpleNamespace(embed_size=d, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
-    tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0))
-    loss = tr.train(batches)
     port = MFPort(U0, V0, optimizer=optname, lr=lr, weight_decay=wd)
     ref_loss, _ = port.train(batches)
-    assert rel_fro(tr.U.cpu(), port.user.weight.detach()) < 1e-5
-    assert rel_fro(tr.V.cpu(), port.item.weight.detach()) < 1e-5
-    assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss)
-    # scratch is left clean for the next step
-    assert int(tr._sh["V"]["flags"].sum()) == 0 and float(tr._sh["V"]["g"].abs().sum()) == 0.0
+    out = {}
+    for exchange, adam_mode in (("all_to_all", "sparse"), ("all_to_all", "sparse"), ("all_to_all", "dense"), ("all_reduce", "dense")):
+        tr = ShardedMFTrainer(cfg, inter.num_items, inter.num_users, init=(U0, V0), exchange=exchange, adam_mode=adam_mode)
+        loss = tr.train(batches)
+        U, V = tr.gather_tables()
+        assert rel_fro(U.cpu(), port.user.weight.detach()) < 1e-5, (exchange, adam_mode)
+        assert rel_fro(V.cpu(), port.item.weight.detach()) < 1e-5, (exchange, adam_mode)
+        assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss)
+        # scratch is left clean for the next step
+        assert int(tr._sh["V"]["flags"].sum()) == 0 and float(tr._sh["V"]["g"].abs().sum()) == 0.0
+        out.setdefault((exchange, adam_mode), []).append((U.clone(), V.clone(), loss))
+    # ordered accumulate: two runs are bit-identical; the sparse-traffic (catch-up) Adam equals the dense sweep bit for bit
+    (Ua, Va, la), (Ub, Vb, lb) = out[("all_to_all", "sparse")]
+    assert torch.equal(Ua, Ub) and torch.equal(Va, Vb) and la == lb
+    Ud, Vd, _ = out[("all_to_all", "dense")][0]
+    assert torch.equal(Ua, Ud) and torch.equal(Va, Vd)
 
 
 def test_sharded_trainer_oob_id_raises():

@@ -29,6 +29,7 @@ SYMBOLS = (
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex",
     "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
+    "yr_shard_accumulate_sorted", "yr_adam_scalars", "yr_shard_step_sparse_adam", "yr_shard_gather_local", "yr_shard_catch_up",
     "yr_sample_negatives", "yr_laplacian_ws_bytes", "yr_laplacian_build",
     "yr_synth_user_rows", "yr_laplacian_binary_values",
     "yr_split_ws_bytes", "yr_split_sizes", "yr_split_per_user",
@@ -179,6 +180,11 @@ def load() -> C.CDLL:
         "yr_bpr_rows_grad": (C.c_int, [p, i32, i64, i64, i64, p, p, p]),
         "yr_shard_accumulate": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, i64, p, i64, p]),
         "yr_shard_step": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), i64, p]),
+        "yr_shard_accumulate_sorted": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, p, i64, p, i64, i32, p]),
+        "yr_shard_catch_up": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, i32, p, p, i64, p]),
+        "yr_shard_gather_local": (C.c_int, [p, p, i32, p, p, i64, p, i64, p]),
+        "yr_adam_scalars": (C.c_int, [C.POINTER(YrOpt), i32, p, p]),
+        "yr_shard_step_sparse_adam": (C.c_int, [C.POINTER(YrShardState), C.POINTER(YrOpt), p, i32, p, i64, i32, p]),
         "yr_eval_tc_supported": (C.c_int, [i32, i32]),
         "yr_eval_tc_ws_bytes": (sz, [i64]),
         "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
