@@ -21,6 +21,7 @@
 // The user tile (gathered rows of eval_uid) is written to shared memory by all threads in the 128B-swizzled K-major
 // layout the UMMA descriptor expects.
 #include <float.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace yr {
@@ -46,6 +47,7 @@ struct TcParams {
   int32_t* fb_count; int32_t* fb_rows;
   int* cand;                     // global scratch for the candidate buffers: [grid][2 arrays][2][CAP][128]
   int SPS, NST, CAP;             // 32-float slabs per stage, pipeline stages, candidate buffer entries per half-stream
+  int MCAP;                      // mask entries per row staged in shared memory (0 = none)
 };
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ u, const float* __restrict__ v, int d) {
@@ -90,7 +92,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // the swizzled tiles need 1024-byte alignment in the shared window; the launch adds 1 KB of slack for this
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
-  const int d = P.d, K = P.K, SPS = P.SPS, NST = P.NST, CAP = P.CAP;
+  const int d = P.d, K = P.K, SPS = P.SPS, NST = P.NST, CAP = P.CAP, MCAP = P.MCAP;
   constexpr int TN = kTcTN;
   const int n_slabs = d / 32;
   const int n_kc = n_slabs / SPS;                       // stages per item tile
@@ -107,6 +109,10 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(cntB + kTcTM);             // full[4] empty[4] tfull[4] tempty[4]
   uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  // The first MCAP entries of every row's sorted mask list, staged per user tile (row stride MCAP + 1: the 32 lanes of a warp
+  // walk 32 different rows). The candidate path advances a cursor through this list; from global memory every step was a
+  // dependent L2 round trip inside a divergent loop — the dominant cost of the epilogue in round 1's profile.
+  int* msk = reinterpret_cast<int*>(tmem_slot + 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_utiles = (P.n_eval + kTcTM - 1) / kTcTM;
@@ -147,6 +153,16 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
       }
       const int slab = c4 >> 3, c = c4 & 7;
       *reinterpret_cast<float4*>(Us + (size_t)slab * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+    if (MCAP > 0) {
+      for (int idx = tid; idx < kTcTM * MCAP; idx += kTcThreads) {
+        const int r = idx / MCAP, j = idx - r * MCAP;
+        const int64_t e = e0 + r;
+        if (e < P.n_eval) {
+          const int m0 = P.mask_ptr[e];
+          if (j < P.mask_ptr[e + 1] - m0) msk[r * (MCAP + 1) + j] = P.mask_idx[m0 + j];
+        }
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
     __syncthreads();
@@ -226,13 +242,19 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
       asm volatile("bar.sync 1, 256;" ::: "memory");               // both halves initialised before anyone reads
       int cnt = 0;
       bool overflow = false;
-      int mcur = live ? P.mask_ptr[e] : 0;
+      const int mbeg = live ? P.mask_ptr[e] : 0;
+      int mcur = mbeg;
       const int mend = live ? P.mask_ptr[e + 1] : 0;
-      int mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff;
+      const int* mrow = msk + r * (MCAP + 1);
+      auto mask_at = [&](int m) -> int {                     // staged prefix from shared memory, the tail from global
+        if (m >= mend) return 0x7fffffff;
+        return (m - mbeg < MCAP) ? mrow[m - mbeg] : P.mask_idx[m];
+      };
+      int mnext = mask_at(mcur);
 
       auto handle = [&](int item, float s) {          // candidate -> buffer (+ the K best s~ values)
         if (s < theta) return;                                      // theta may have risen since the scan
-        while (mnext < item) { ++mcur; mnext = (mcur < mend) ? P.mask_idx[mcur] : 0x7fffffff; }
+        while (mnext < item) { ++mcur; mnext = mask_at(mcur); }
         if (mnext == item) return;                                  // masked: never a candidate (see fallback rule)
         if (cnt == CAP) {                                           // compact: keep what is still inside the window
           int w = 0;
@@ -410,19 +432,29 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-struct TcConfig { int SPS, NST, CAP; size_t smem; };
+struct TcConfig { int SPS, NST, CAP, MCAP; size_t smem; };
 
 static bool tc_config(int d, int K, TcConfig* c) {
   if (d < 32 || d > 256 || (d % 32) != 0 || K < 1 || K > kTcMaxK) return false;
   c->SPS = (d % 64 == 0 && d <= 128) ? 2 : 1;
   c->CAP = kTcCap;
-  const size_t fixed = (size_t)(d / 32) * 16384 + 4 * kTcTM * 4 + 2 * kTcTM * 4 + 16 * 8 + 16;   // Us, xch, tauB/cntB, barriers
+  const size_t fixed = (size_t)(d / 32) * 16384 + 4 * kTcTM * 4 + 2 * kTcTM * 4 + 16 * 8 + 32;   // Us, xch, tauB/cntB, barriers, tmem slot
   const size_t stage = (size_t)c->SPS * kTcTN * 128;
   int nst = (int)((224 * 1024 - fixed) / stage);
   if (nst > 4) nst = 4;
   if (nst < 2) return false;
   c->NST = nst;
-  c->smem = fixed + (size_t)nst * stage + 1024;     // + slack for the 1024-byte alignment of the swizzled tiles
+  // what is left (after >= 3 pipeline stages where they fit) stages the first entries of the rows' mask lists
+  const char* e = getenv("YR_EVAL_MCAP");
+  int want = (e && *e) ? atoi(e) : 32;      // measured (profiles/README.md): 0 -> 1.46 ms, 32 -> 1.43 ms, 64 -> 1.58 ms on the MF workload
+  if (want < 0) want = 0;
+  if (want > 256) want = 256;
+  auto need = [&](int n_st, int mcap) { return fixed + (size_t)n_st * stage + (size_t)kTcTM * (mcap + 1) * 4 + 1024; };
+  while (want > 0 && need(c->NST, want) > 225 * 1024) {
+    if (c->NST > 3) --c->NST; else want /= 2;
+  }
+  c->MCAP = want;
+  c->smem = need(c->NST, c->MCAP);                  // + slack for the 1024-byte alignment of the swizzled tiles
   return true;
 }
 
@@ -482,7 +514,7 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
     P.mask_ptr = mask_ptr; P.mask_idx = mask_idx; P.act_ptr = act_ptr; P.act_idx = act_idx; P.act_nuniq = act_nuniq;
     P.inv_log2 = inv_log2; P.K = K; P.topk_out = topk_out; P.topk_score = topk_score; P.user_metrics = user_metrics;
     P.err = err; P.vmax = vmax; P.fb_count = fb_count; P.fb_rows = fb_rows; P.cand = cand;
-    P.SPS = cfg.SPS; P.NST = cfg.NST; P.CAP = cfg.CAP;
+    P.SPS = cfg.SPS; P.NST = cfg.NST; P.CAP = cfg.CAP; P.MCAP = cfg.MCAP;
     YR_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     const int64_t n_utiles = (n_eval + kTcTM - 1) / kTcTM;
     int64_t grid = yr_sm_count();
