@@ -32,6 +32,8 @@ constexpr int kTcAcc = 4;          // TMEM accumulator stages (4 x 128 columns)
 constexpr int kTcThreads = 384;    // 4 control warps + 8 epilogue warps
 constexpr int kTcMaxK = 16;
 constexpr int kTcCap = 128;        // candidate buffer entries per half-stream (global scratch): compaction is rare
+constexpr int kTcPend = 4;         // deferred candidates per epilogue thread (shared memory ring)
+constexpr int kTcDrain = 8;        // chunks of 32 columns between two drains of the rings
 constexpr float kTcErrCoef = 0.0025f;   // > 2*2^-10 (TF32 operands) + accumulation + fp32-chain rounding
 
 struct TcParams {
@@ -113,6 +115,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
   // walk 32 different rows). The candidate path advances a cursor through this list; from global memory every step was a
   // dependent L2 round trip inside a divergent loop — the dominant cost of the epilogue in round 1's profile.
   int* msk = reinterpret_cast<int*>(tmem_slot + 4);
+  // Deferred candidate handling: the scan only PUSHES (item, s~) into a small per-thread ring; the expensive part (mask
+  // cursor, candidate buffer, sorted K-best list, threshold exchange) runs for the whole warp at once every kTcDrain chunks.
+  // With 32 rows per warp nearly every 32-column chunk has a candidate in SOME lane, so handling candidates inline made
+  // the whole warp walk the slow path once per chunk; batched, that cost is shared by all the lanes that have work.
+  float* pend_s = reinterpret_cast<float*>(msk + kTcTM * (MCAP + 1));       // [kTcPend][256]
+  int* pend_i = reinterpret_cast<int*>(pend_s + kTcPend * 256);             // [kTcPend][256]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_utiles = (P.n_eval + kTcTM - 1) / kTcTM;
@@ -280,6 +288,17 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         }
       };
 
+      const int et = tid - 128;                          // epilogue thread 0..255
+      int npend = 0, chunk_ctr = 0;
+      auto drain = [&]() {                               // warp-collective
+        int nmax = npend;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
+        for (int q = 0; q < nmax; ++q)
+          if (q < npend) handle(pend_i[q * 256 + et], pend_s[q * 256 + et]);
+        npend = 0;
+      };
+
       for (int it = 0; it < n_itiles; ++it) {
         mbar_wait(tfull + acc_e, aph_e);
         tc_fence_after();
@@ -308,22 +327,27 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
             // columns past the catalog are zero-filled TMA rows (score 0): never candidates
             if ((int64_t)item0 + 32 > P.nI) mask = (item0 < P.nI) ? (mask & ((1u << (int)(P.nI - item0)) - 1u)) : 0u;
             const bool single = __popc(mask) == 1;                  // the usual case: the only candidate is the max
-            while (__any_sync(kFull, mask != 0)) {                    // few lanes, few bits: handled in place
-              if (mask) {
+            while (__any_sync(kFull, mask != 0)) {                    // few lanes, few bits: pushed, handled later
+              if (mask && npend < kTcPend) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
                 float sj;
                 if (single) sj = m; else sj = select32(v, j);
-                handle(item0 + j, sj);
+                pend_i[npend * 256 + et] = item0 + j;
+                pend_s[npend * 256 + et] = sj;
+                ++npend;
               }
+              if (__any_sync(kFull, npend == kTcPend)) drain();       // a full ring: everybody empties theirs
             }
           }
+          if (((++chunk_ctr) & (kTcDrain - 1)) == 0 && __any_sync(kFull, npend > 0)) drain();
         }
         tc_fence_before();
         mbar_arrive(tempty + acc_e);
         if (++acc_e == kTcAcc) { acc_e = 0; aph_e ^= 1; }
       }
 
+      if (__any_sync(kFull, npend > 0)) drain();
       // ---- hand the second half-stream's state to the first; first half finishes the row ----
       if (half == 1) { tauB[r] = tau; cntB[r] = overflow ? -1 : cnt; }
       xch_own[0] = tau; xch_own[kTcTM] = mid;
@@ -449,7 +473,9 @@ static bool tc_config(int d, int K, TcConfig* c) {
   int want = (e && *e) ? atoi(e) : 32;      // measured (profiles/README.md): 0 -> 1.46 ms, 32 -> 1.43 ms, 64 -> 1.58 ms on the MF workload
   if (want < 0) want = 0;
   if (want > 256) want = 256;
-  auto need = [&](int n_st, int mcap) { return fixed + (size_t)n_st * stage + (size_t)kTcTM * (mcap + 1) * 4 + 1024; };
+  auto need = [&](int n_st, int mcap) {
+    return fixed + (size_t)n_st * stage + (size_t)kTcTM * (mcap + 1) * 4 + (size_t)2 * kTcPend * 256 * 4 + 1024;
+  };
   while (want > 0 && need(c->NST, want) > 225 * 1024) {
     if (c->NST > 3) --c->NST; else want /= 2;
   }
