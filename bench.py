@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the scaled config-5 runs (10 M x 2 M, 500 M interactions)")
     ap.add_argument("--c5-scale", type=float, default=1.0, help="shrink config 5 (users, items, interactions) by this factor")
+    ap.add_argument("--only-c5", action="store_true", help="profiling aid: only the config-5 runs, no JSON contract")
     ap.add_argument("--only", default="", help="profiling aid: run only 'ngcf' | 'mf' | 'eval' steps, no JSON contract")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if not args.only else args.warmup
@@ -314,6 +315,25 @@ def main():
     from yelprecommendation_b200.trainers import MFTrainer, NGCFTrainer
 
     pk = peaks()
+    if args.only_c5:
+        def _barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def _max(ms):
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            return ms
+        extra = {}
+        config5_extras(extra, dev, rank, world, _barrier, _max, pk, args)
+        if rank == 0:
+            print(json.dumps({"n_gpus": world, "extra": extra}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     w = build_workload()
     K, W = args.steps, args.warmup
     tu, tp_, tn = w.tri

@@ -128,14 +128,19 @@ typedef struct yr_csr {
   const int32_t *rowptr, *col;
   const float* val;
   int32_t n_chunks;               /* work items: one per short row, ceil(len/CHUNK) per long row */
-  const int32_t *chunk_desc;      /* [n_chunks x 4], 16-byte aligned: {row, first non-zero, length | split_row_index << 8,
-                                     slot} — slot -1 = whole row (direct store), else index into `partials` */
+  const int32_t *chunk_desc;      /* [n_chunks x 4], 16-byte aligned: {row, first non-zero, length | split_row_index << 8
+                                     (| 1 << 31 for a big row), slot} — slot -1 = whole row (direct store), else index into
+                                     `partials` */
   int32_t n_split_rows;           /* rows that were cut */
   const int32_t *split_row;       /* [n_split_rows] */
   const int32_t *split_ptr;       /* [n_split_rows+1] range of partial slots of each split row */
   float* partials;                /* [split_ptr[n_split_rows] x d] scratch */
   int32_t* split_count;           /* [n_split_rows] arrival counters, zero on first use; every call leaves them zero.
                                      The chunk that arrives last at a split row sums that row's partials (in order). */
+  int32_t n_big_rows;             /* split rows with more than YR_SPMM_BIG_CHUNKS chunks (hub rows of a scaled graph): their */
+  const int32_t* big_split_idx;   /* partials are summed — same left-to-right order — by a follow-up kernel that stages them
+                                     through shared memory instead of one warp walking thousands of partials; [n_big_rows]
+                                     indices into split_row / split_ptr, from yr_spmm_plan_big_h. 0 / NULL if there are none. */
 } yr_csr;
 
 /* Host-side plan builder (host pointers). Call _size_h first, allocate, then _fill_h. */
@@ -143,6 +148,10 @@ int yr_spmm_plan_size_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_chun
                         int32_t* n_partials_h);
 int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* chunk_desc_h, int32_t* split_row_h,
                         int32_t* split_ptr_h);
+/* Split rows with more than YR_SPMM_BIG_CHUNKS chunks: *n_big_h = how many; big_split_idx_h (may be NULL to only count)
+ * receives their indices into the split-row list. Their chunk descriptors carry bit 31 of word 2 (set by _fill_h). */
+#define YR_SPMM_BIG_CHUNKS 256
+int yr_spmm_plan_big_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_big_h, int32_t* big_split_idx_h);
 
 /* Y = A X (accumulate == 0) or Y += A X (accumulate != 0), X/Y row-major [n_rows x d].
  * Replaces torch.sparse.mm(laplacian_matrix, last_embed) (models/ngcf.py:64,67). */

@@ -460,3 +460,27 @@ def test_other_embedding_widths_trainer_vs_port(d, layers, name, lr):
                                                  ec.act_idx, 10)
     assert np.array_equal(tr.last_topk.cpu().numpy(), otopk)
     assert np.allclose(got, cport.metrics_from_sums(osums, ec.n_eval), rtol=1e-12)
+
+
+def test_spmm_hub_rows_bit_exact_vs_oracle():
+    """Rows with more than YR_SPMM_BIG_CHUNKS = 256 chunks (hub rows of the scaled config-5 graph) take the follow-up kernel
+    that stages the chunk partials through shared memory: same left-to-right order, still bit-exact against the oracle."""
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data.graph import CSRMatrix
+    rng = np.random.default_rng(7)
+    n = 90_000
+    lens = rng.integers(0, 60, n)
+    lens[5], lens[77], lens[4000], lens[n - 1] = 70_001, 33_000, 20_000, 40_321      # 547 / 258 / 157 / 316 chunks
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    col = rng.integers(0, n, int(rowptr[-1])).astype(np.int32)
+    val = (rng.standard_normal(int(rowptr[-1])) * 0.05).astype(np.float32)
+    A = CSRMatrix(rowptr, col, val, "cuda")
+    assert A.n_big_rows == 3 and A.n_split_rows >= 4
+    for d in (64, 128):
+        X = rng.standard_normal((n, d)).astype(np.float32)
+        Y0 = rng.standard_normal((n, d)).astype(np.float32)
+        y = ops.spmm_csr(A, torch.from_numpy(X).cuda())
+        assert np.array_equal(y.cpu().numpy(), cport.spmm_csr(rowptr, col, val, X))
+        ya = torch.from_numpy(Y0).cuda()
+        ops.spmm_csr(A, torch.from_numpy(X).cuda(), out=ya, accumulate=True)
+        assert np.array_equal(ya.cpu().numpy(), cport.spmm_csr(rowptr, col, val, X, Y0))

@@ -20,7 +20,7 @@ SYMBOLS = (
     "yr_version", "yr_device_sm_count",
     "yr_mf_score", "yr_mf_score_bwd", "yr_bpr_loss_fwd", "yr_bpr_loss_bwd",
     "yr_bpr_mf_train_ws_bytes", "yr_bpr_mf_train", "yr_bpr_mf_validate",
-    "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
+    "yr_spmm_plan_size_h", "yr_spmm_plan_fill_h", "yr_spmm_plan_big_h", "yr_spmm_csr", "yr_ngcf_layer_fwd", "yr_ngcf_layer_bwd_ws_bytes", "yr_ngcf_layer_bwd",
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
@@ -70,7 +70,8 @@ class YrCsr(C.Structure):
                 ("chunk_desc", C.c_void_p),
                 ("n_split_rows", C.c_int32),
                 ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p),
-                ("split_count", C.c_void_p)]
+                ("split_count", C.c_void_p),
+                ("n_big_rows", C.c_int32), ("big_split_idx", C.c_void_p)]
 
 
 class YrShardState(C.Structure):
@@ -136,6 +137,7 @@ def load() -> C.CDLL:
         "yr_bpr_mf_validate": (C.c_int, [p, p, i64, i64, i32, p, p, p, i64, i32, p, p, p, p]),
         "yr_spmm_plan_size_h": (C.c_int, [p, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "yr_spmm_plan_fill_h": (C.c_int, [p, i64, p, p, p]),
+        "yr_spmm_plan_big_h": (C.c_int, [p, i64, C.POINTER(i32), p]),
         "yr_spmm_csr": (C.c_int, [C.POINTER(YrCsr), i32, p, p, i32, p]),
         "yr_ngcf_layer_fwd": (C.c_int, [C.POINTER(YrCsr), i32, p, p, p, f32, p, p, i32, p]),
         "yr_ngcf_layer_bwd_ws_bytes": (sz, [i32]),

@@ -94,7 +94,8 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, 
     // the flag, so the split-row arrival count stays consistent
     if (row_flag && c < A.n_chunks && !__ldg(row_flag + dsc.x)) { dsc = make_int4(0, 0, 0, -1); c_valid = false; }
     const int row = dsc.x, s = dsc.y, len = dsc.z & 0xff, slot = dsc.w;
-    const int split_idx = dsc.z >> 8;            // index into split_row / split_ptr / split_count (split chunks only)
+    const int split_idx = (dsc.z & 0x7fffffff) >> 8;   // index into split_row / split_ptr / split_count (split chunks only)
+    const bool big = dsc.z < 0;                  // hub row: its partials are summed by spmm_finish_big_kernel afterwards
     float4 acc[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -172,7 +173,7 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, 
     }
     // ---- split rows: the chunk that arrives LAST sums the row's partials left to right (deterministic order).
     // Long rows' chunks are scheduled first (plan order), so this tail work overlaps the bulk of the kernel.
-    const bool is_split = (c_valid) && slot >= 0;
+    const bool is_split = (c_valid) && slot >= 0 && !big;
     if (__any_sync(kFull, is_split)) {
       if (is_split) __threadfence();                       // my part of the partial is visible device-wide
       __syncwarp();
@@ -191,6 +192,47 @@ spmm_chunk_kernel(yr_csr A, const float* __restrict__ X, float* __restrict__ Y, 
   }
 }
 
+// Hub rows (more than YR_SPMM_BIG_CHUNKS chunks — a config-5 item row has up to ~28,000): one CTA per row sums the chunk
+// partials in the SAME left-to-right order as spmm_finish_split, but the loads are decoupled from the dependent adds: all
+// threads stage a 32 KB tile of partials in shared memory, the first D/4 threads add them. One warp walking the partials eight
+// at a time took 3.5 ms for the largest row — a serial tail longer than a rank's whole row-panel SpMM on 8 GPUs.
+constexpr int kBigBytes = 32 * 1024;     // static shared memory of the staging tile
+template <int D, bool ACC>
+__global__ void __launch_bounds__(256)
+spmm_finish_big_kernel(yr_csr A, float* __restrict__ Y, const int32_t* __restrict__ row_flag) {
+  constexpr int kVec = D / 4;
+  constexpr int kBigTile = kBigBytes / (D * 4);                 // partials per tile: 128 at d = 64, 64 at d = 128
+  __shared__ float4 tile[kBigTile * kVec];
+  const int sidx = A.big_split_idx[blockIdx.x];
+  const int row = A.split_row[sidx];
+  if (row_flag && !row_flag[row]) return;
+  const int p0 = A.split_ptr[sidx], p1 = A.split_ptr[sidx + 1];
+  const float4* P4 = reinterpret_cast<const float4*>(A.partials);
+  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool first = true;
+  for (int t0 = p0; t0 < p1; t0 += kBigTile) {
+    const int nt = min(kBigTile, p1 - t0);
+    for (int i = threadIdx.x; i < nt * kVec; i += blockDim.x) tile[i] = __ldcg(P4 + (int64_t)t0 * kVec + i);
+    __syncthreads();
+    if (threadIdx.x < kVec) {
+      for (int q = 0; q < nt; ++q) {
+        const float4 x = tile[q * kVec + threadIdx.x];
+        if (first) { tot = x; first = false; }
+        else { tot.x += x.x; tot.y += x.y; tot.z += x.z; tot.w += x.w; }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < kVec) {
+    float4* y4 = reinterpret_cast<float4*>(Y + (int64_t)row * D) + threadIdx.x;
+    if (ACC) {
+      const float4 y = *y4;
+      tot.x = y.x + tot.x; tot.y = y.y + tot.y; tot.z = y.z + tot.z; tot.w = y.w + tot.w;
+    }
+    *y4 = tot;
+  }
+}
+
 template <int D, int THREADS, int MINB, int U, bool DIRECT>
 static int launch_spmm_v(const yr_csr* A, const float* X, float* Y, int accumulate, cudaStream_t s, const int32_t* row_flag) {
   using C = SpmmCfg<D>;
@@ -201,6 +243,12 @@ static int launch_spmm_v(const yr_csr* A, const float* X, float* Y, int accumula
   if (accumulate) spmm_chunk_kernel<D, true, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
   else spmm_chunk_kernel<D, false, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
   YR_CHECK_LAUNCH();
+  if (A->n_big_rows > 0) {
+    if (!A->big_split_idx) return YR_ERR_BAD_ARG;
+    if (accumulate) spmm_finish_big_kernel<D, true><<<(unsigned)A->n_big_rows, 256, 0, s>>>(*A, Y, row_flag);
+    else spmm_finish_big_kernel<D, false><<<(unsigned)A->n_big_rows, 256, 0, s>>>(*A, Y, row_flag);
+    YR_CHECK_LAUNCH();
+  }
   return YR_OK;
 }
 
@@ -259,7 +307,9 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     for (int64_t s = rowptr_h[r]; s < rowptr_h[r + 1]; s += YR_SPMM_CHUNK) {
       const int64_t e = s + YR_SPMM_CHUNK < rowptr_h[r + 1] ? s + YR_SPMM_CHUNK : rowptr_h[r + 1];
       int32_t* d = chunk_desc_h + 4 * c;
-      d[0] = (int32_t)r; d[1] = (int32_t)s; d[2] = (int32_t)(e - s) | (int32_t)(sr << 8); d[3] = (int32_t)slot;
+      const int64_t n_ch = (len + YR_SPMM_CHUNK - 1) / YR_SPMM_CHUNK;
+      d[0] = (int32_t)r; d[1] = (int32_t)s; d[3] = (int32_t)slot;
+      d[2] = (int32_t)((uint32_t)(e - s) | ((uint32_t)sr << 8) | (n_ch > YR_SPMM_BIG_CHUNKS ? 0x80000000u : 0u));
       ++c; ++slot;
     }
     split_row_h[sr] = (int32_t)r;
@@ -291,6 +341,23 @@ extern "C" int yr_spmm_plan_fill_h(const int32_t* rowptr_h, int64_t n_rows, int3
     d[0] = (int32_t)r; d[1] = rowptr_h[r]; d[2] = (int32_t)len; d[3] = -1;
     ++c;
   }
+  return YR_OK;
+}
+
+extern "C" int yr_spmm_plan_big_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_big_h, int32_t* big_split_idx_h) {
+  if (!rowptr_h || n_rows < 0 || !n_big_h) return YR_ERR_BAD_ARG;
+  int64_t sr = 0, nb = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = rowptr_h[r + 1] - rowptr_h[r];
+    if (len <= YR_SPMM_CHUNK) continue;
+    if ((len + YR_SPMM_CHUNK - 1) / YR_SPMM_CHUNK > YR_SPMM_BIG_CHUNKS) {
+      if (big_split_idx_h) big_split_idx_h[nb] = (int32_t)sr;
+      ++nb;
+    }
+    ++sr;
+  }
+  if (sr >= (1LL << 23)) return YR_ERR_BAD_DIM;        // split-row index shares a descriptor word with the length and the flag
+  *n_big_h = (int32_t)nb;
   return YR_OK;
 }
 

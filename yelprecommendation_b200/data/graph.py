@@ -78,6 +78,12 @@ class CSRMatrix:
         srow, sptr = np.empty(max(ns.value, 1), np.int32), np.zeros(ns.value + 1, np.int32)
         _cabi.check(lib.yr_spmm_plan_fill_h(rowptr.ctypes.data, self.n_rows, cdesc.ctypes.data, srow.ctypes.data,
                                             sptr.ctypes.data), "yr_spmm_plan_fill_h")
+        nbig = C.c_int32(0)
+        _cabi.check(lib.yr_spmm_plan_big_h(rowptr.ctypes.data, self.n_rows, C.byref(nbig), None), "yr_spmm_plan_big_h")
+        big = np.zeros(max(nbig.value, 1), np.int32)
+        if nbig.value:
+            _cabi.check(lib.yr_spmm_plan_big_h(rowptr.ctypes.data, self.n_rows, C.byref(nbig), big.ctypes.data), "yr_spmm_plan_big_h")
+        self.n_big_rows = nbig.value
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.device = torch.device(device)
         tt = lambda a, dt_np, dt_t: (a.to(device=device, dtype=dt_t).contiguous() if isinstance(a, torch.Tensor)
@@ -85,6 +91,7 @@ class CSRMatrix:
         self.rowptr, self.col, self.val = t(rowptr), tt(col, np.int32, torch.int32), tt(val, np.float32, torch.float32)
         self.chunk_desc = t(cdesc)
         self.split_row, self.split_ptr = t(srow), t(sptr)
+        self.big_split_idx = t(big)
         self.split_count = torch.zeros(max(ns.value, 1), dtype=torch.int32, device=device)
         self._partials = {}
 
@@ -102,7 +109,8 @@ class CSRMatrix:
         p = _cabi.dptr
         return _cabi.YrCsr(self.n_rows, self.nnz, p(self.rowptr), p(self.col), p(self.val), self.n_chunks,
                            p(self.chunk_desc), self.n_split_rows,
-                           p(self.split_row), p(self.split_ptr), p(part), p(self.split_count))
+                           p(self.split_row), p(self.split_ptr), p(part), p(self.split_count),
+                           self.n_big_rows, p(self.big_split_idx) if self.n_big_rows else None)
 
 
 @dataclass

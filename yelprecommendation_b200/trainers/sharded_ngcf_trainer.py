@@ -135,7 +135,8 @@ class ShardedNGCFTrainer:
             rp, ci, va = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev)
             rpT, ciT, vaT = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev, transpose=True)
         self.nnz_local = int(ci.numel())
-        P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", 4 if self.world > 1 else 1))
+        import os
+        P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", int(os.environ.get("YR_SHARD_PANELS", "8")) if self.world > 1 else 1))
         P = max(1, min(P, self.per))
         step = ((self.per + P - 1) // P + 127) // 128 * 128          # whole 128-row tiles of the dense kernels
         rp_h = rp.cpu()
