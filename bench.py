@@ -651,11 +651,23 @@ def main():
             ctr.train(hb)                                   # host tensors: H2D of the dense masks every step
             torch.cuda.synchronize()
             e2e_c = time.perf_counter() - t0
+            # the same batches as index lists (data/cdae_sparse.py, what a list-holding dataset yields): host -> device per step
+            from yelprecommendation_b200.data.cdae_sparse import sparse_cdae_batch
+            sbatches = [sparse_cdae_batch(b_) for b_ in hb]
+            ctr.train(sbatches[:4])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctr.train(sbatches)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            h2d_s = sum(sum(v.numel() * v.element_size() for v in b_.values()) for b_ in sbatches) / len(sbatches)
             extra["cdae_train"] = {"value": world * Bc * n_b / (ms_c * 1e-3), "unit": "users/s", "ms_per_step": ms_c / n_b,
                                    "batch": Bc, "e2e_value": world * Bc * n_b / e2e_c,
                                    "h2d_bytes_per_step": 2 * Bc * nI * 4,
+                                   "e2e_value_index_lists": world * Bc * n_b / e2e_s, "h2d_bytes_per_step_index_lists": h2d_s,
                                    "note": "masks resident in HBM for `value`; e2e ships the dense [32 x 38,048] input/negative "
-                                           "masks the reference's CDAEDataset yields"}
+                                           "masks the reference's CDAEDataset yields; e2e_value_index_lists ships the same batches "
+                                           "as item lists (yr_cdae_step_idx)"}
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 from oracle.torch_port import CDAEPort
                 port = CDAEPort({k: v.detach().cpu() for k, v in ctr.model.state_dict().items()}, "adam", 1e-4)

@@ -438,6 +438,17 @@ int yr_cdae_step_ex(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, cons
                     const float* negative_mask, int64_t B, double* loss, float* step_loss,
                     void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
 
+/* The same step from INDEX LISTS instead of dense [B x nI] masks (the dense rows the reference's CDAEDataset yields are 152 KB
+ * per user; the lists are a few hundred bytes): in_ptr [B + 1] / in_idx = the active inputs of every row (ascending item ids),
+ * in_val = their values after dropout (NULL = 1: evaluation), tgt_ptr / tgt_idx / tgt_val = the loss positions of every row
+ * (ascending item ids: the union of the target items, value 1, and the sampled negatives, value 0). Same arithmetic and
+ * order as yr_cdae_step_ex on the equivalent dense tensors. opt == NULL: loss only. */
+int yr_cdae_step_idx(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                     const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                     const int64_t* uid, const int32_t* in_ptr, const int32_t* in_idx, const float* in_val,
+                     const int32_t* tgt_ptr, const int32_t* tgt_idx, const float* tgt_val, int64_t B,
+                     double* loss, float* step_loss, void* ws, size_t ws_bytes, int32_t* err, yr_stream stream);
+
 /* NSBCELoss.forward on dense tensors (loss.py:12-16): mean BCE over positions where target + negative_mask != 0. */
 int yr_nsbce_loss(const float* pred, const float* target, const float* negative_mask, int64_t n, float* loss,
                   void* ws, size_t ws_bytes, yr_stream stream);

@@ -203,3 +203,33 @@ def test_widest_hidden_sizes_vs_port(h, act):
     (pm, ppred) = tp.CDAEPort({k: v.detach().cpu() for k, v in tr.model.state_dict().items()}, hidden_activation=act)._rank(eb, "test_mask")
     same = sum(np.array_equal(tr.last_topk[r].cpu().numpy(), ppred[r]) for r in range(nU))
     assert same >= nU - max(2, nU // 20)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,lr", [("sgd", 0.05), ("adam", 1e-3)])
+def test_index_list_batches_equal_dense_batches(name, lr):
+    """yr_cdae_step_idx: the same batches shipped as index lists (data/cdae_sparse.py: a few hundred bytes per user instead of
+    two dense [B x num_items] masks) give the same losses and parameters as the dense form, with the same dropout values."""
+    from yelprecommendation_b200.data.cdae_sparse import sparse_cdae_batch
+    g, nU, nI, B, tb, vb, eb, keeps, init = _fixture()
+    dense = _trainer(g, nU, nI, init, name, lr)
+    ld = dense.train(tb, keeps)
+    sparse = _trainer(g, nU, nI, init, name, lr)
+    sb = [sparse_cdae_batch(b) for b in tb]
+    kv = [k[b["input_mask"] != 0] for k, b in zip(keeps, tb)]           # the dropout multiplier of every listed input
+    assert all(s["input_idx"].numel() == v.numel() for s, v in zip(sb, kv))
+    ls = sparse.train(sb, kv)
+    assert np.isclose(ls, ld, rtol=1e-6)
+    assert rel_err(sparse.last_step_losses.cpu().numpy(), dense.last_step_losses.cpu().numpy()) < 1e-6
+    for (k, a), (_, b_) in zip(sparse.model.state_dict().items(), dense.model.state_dict().items()):
+        if name == "sgd":
+            assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) < 1e-6, k
+        else:
+            assert_adam_close(a.cpu().numpy(), b_.cpu().numpy(), k, touched=a.numel() * 3)
+    # device-drawn dropout on the lists runs, and a bad item id raises like nn.Embedding would
+    assert np.isfinite(sparse.train(sb)) 
+    bad = dict(sb[0])
+    bad["input_idx"] = bad["input_idx"].clone()
+    bad["input_idx"][0] = nI
+    with pytest.raises(IndexError):
+        sparse.train([bad])

@@ -210,12 +210,25 @@ def test_full_catalog_yelp_shape_properties():
     assert topk.shape == (len(uid), 10) and topk.min() >= 0 and topk.max() < inter.num_items
     assert np.all(np.diff(tsc, axis=1) <= 0)                                  # best first
     assert np.all(np.sort(topk, axis=1)[:, 1:] != np.sort(topk, axis=1)[:, :-1])   # distinct ids
-    rows = np.random.default_rng(0).choice(len(uid), 96, replace=False)
+    rows = np.sort(np.random.default_rng(0).choice(len(uid), 2000, replace=False))     # 2,000 oracle rows (round 1: 96)
     for e in rows:                                                             # never a masked item
         assert not (set(topk[e].tolist()) & set(mask[e]))
     sub = build_eval_csr(uid[rows], [pos[e] for e in rows], [mask[e] for e in rows], inter.num_items)
     otopk, otsc, oum, _ = cport.eval_topk_metrics(U, V, sub.eval_uid, sub.mask_ptr, sub.mask_idx, sub.act_ptr, sub.act_idx, 10)
     assert np.array_equal(topk[rows], otopk) and np.array_equal(tsc[rows], otsc) and np.array_equal(um[rows], oum)
+    # the NGCF form of the same evaluation: concatenated width d_eff = 256 (d = 64 x 4 layer outputs), all rows tensor-core vs
+    # exact kernel, 400 rows against the oracle
+    rng = np.random.default_rng(1)
+    U4 = np.concatenate([U] + [(U * s_ + 0.05 * rng.standard_normal(U.shape)).astype(np.float32) for s_ in (0.7, 0.4, 0.2)], axis=1)
+    V4 = np.concatenate([V] + [(V * s_ + 0.05 * rng.standard_normal(V.shape)).astype(np.float32) for s_ in (0.7, 0.4, 0.2)], axis=1)
+    assert U4.shape[1] == 256
+    t4, s4, m4, sums4 = run_gpu(U4, V4, csr, 10, "tc")
+    t4x, s4x, m4x, sums4x = run_gpu(U4, V4, csr, 10, "exact")
+    assert np.array_equal(t4, t4x) and np.array_equal(s4, s4x) and np.array_equal(m4, m4x) and np.array_equal(sums4, sums4x)
+    r4 = rows[:400]
+    sub4 = build_eval_csr(uid[r4], [pos[e] for e in r4], [mask[e] for e in r4], inter.num_items)
+    o4, os4, om4, _ = cport.eval_topk_metrics(U4, V4, sub4.eval_uid, sub4.mask_ptr, sub4.mask_idx, sub4.act_ptr, sub4.act_idx, 10)
+    assert np.array_equal(t4[r4], o4) and np.array_equal(s4[r4], os4) and np.array_equal(m4[r4], om4)
     # checksum of checksums: metric sums equal the sum of the per-row terms
     assert np.allclose(sums[:4], um.sum(axis=0), rtol=1e-12)
     assert sums[0] / len(uid) > 0.01                                          # planted structure is recoverable

@@ -26,7 +26,7 @@ SYMBOLS = (
     "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
     "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_masked_rows", "yr_topk_metrics",
     "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
-    "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex",
+    "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex", "yr_cdae_step_idx",
     "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
     "yr_shard_accumulate_sorted", "yr_adam_scalars", "yr_shard_step_sparse_adam", "yr_shard_gather_local", "yr_shard_catch_up",
@@ -169,6 +169,9 @@ def load() -> C.CDLL:
         "yr_cdae_step_ex": (C.c_int, [C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors),
                                       C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, i32, p, p, p, p, p, i64, p,
                                       p, p, sz, p, p]),
+        "yr_cdae_step_idx": (C.c_int, [C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors), C.POINTER(YrCdaeTensors),
+                                       C.POINTER(YrCdaeTensors), C.POINTER(YrOpt), i64, i64, i32, i32, p, p, p, p, p, p, p, i64,
+                                       p, p, p, sz, p, p]),
         "yr_nsbce_loss": (C.c_int, [p, p, p, i64, p, p, sz, p]),
         "yr_laplacian_ws_bytes": (sz, [i64, i64, i64]),
         "yr_laplacian_build": (C.c_int, [p, p, p, i64, i64, i64, p, p, p, p, sz, p, p]),

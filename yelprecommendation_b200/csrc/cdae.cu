@@ -124,6 +124,46 @@ cdae_compact_kernel(const float* __restrict__ x, const float* __restrict__ keep,
   }
 }
 
+// Index-list form of a batch (no dense [B x nI] tensors anywhere): block per row copies its lists into the layout the row
+// kernel reads. in_val == NULL: every listed input is 1 (evaluation / no dropout); otherwise the value after dropout
+// (0 or 1/(1-p); zeros are harmless). Loss positions: tgt_idx ascending per row with tgt_val = the target (1 / 0).
+__global__ void __launch_bounds__(256)
+cdae_lists_kernel(const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_idx, const float* __restrict__ in_val,
+                  const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ tgt_idx, const float* __restrict__ tgt_val,
+                  int64_t nI, CdaeWs w, int32_t* err) {
+  const int b = blockIdx.x;
+  const int i0 = in_ptr[b], ni = in_ptr[b + 1] - i0;
+  int32_t* xi = w.xin_idx + (int64_t)b * nI;
+  float* xv = w.xin_val + (int64_t)b * nI;
+  bool bad = ni < 0 || ni > nI;
+  for (int j = threadIdx.x; j < ni && !bad; j += blockDim.x) {
+    const int it = in_idx[i0 + j];
+    if (it < 0 || it >= nI) { if (err) atomicExch(err, 1); xi[j] = 0; xv[j] = 0.f; continue; }
+    xi[j] = it;
+    xv[j] = in_val ? in_val[i0 + j] : 1.f;
+  }
+  int nt = 0;
+  if (tgt_ptr) {
+    const int t0 = tgt_ptr[b];
+    nt = tgt_ptr[b + 1] - t0;
+    bad = bad || nt < 0 || nt > nI;
+    int32_t* ti = w.tgt_idx + (int64_t)b * nI;
+    float* tv = w.tgt_val + (int64_t)b * nI;
+    for (int j = threadIdx.x; j < nt && !bad; j += blockDim.x) {
+      const int it = tgt_idx[t0 + j];
+      if (it < 0 || it >= nI) { if (err) atomicExch(err, 1); ti[j] = 0; tv[j] = 0.f; continue; }
+      ti[j] = it;
+      tv[j] = tgt_val[t0 + j];
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (bad && err) atomicExch(err, 1);
+    w.xin_cnt[b] = bad ? 0 : ni;
+    w.tgt_cnt[b] = bad ? 0 : nt;
+    if (!bad && nt) atomicAdd(w.total, nt);
+  }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Block per batch row. H = 32 * VPL = hidden size (32 ... 1,024: the values of the reference's cdae_sweep_config.yaml).
@@ -354,6 +394,42 @@ extern "C" int yr_cdae_output(const yr_cdae_tensors* P, int64_t nI, int h, const
   return YR_OK;
 }
 
+static int cdae_step_tail(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                          const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                          const int64_t* uid, int64_t B, double* loss, float* step_loss, const CdaeWs& w, int32_t* err,
+                          yr_stream stream);
+
+static int cdae_step_args_ok(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                             const yr_cdae_tensors* v, const yr_opt* opt, int h, int hidden_act) {
+  if (cdae_tensors_ok(P)) return YR_ERR_BAD_ARG;
+  if (hidden_act != YR_ACT_SIGMOID && hidden_act != YR_ACT_IDENTITY) return YR_ERR_BAD_ARG;
+  if (!dim_vpl(h)) return YR_ERR_BAD_DIM;
+  if (opt) {
+    if (cdae_tensors_ok(grads)) return YR_ERR_BAD_ARG;
+    if (opt->kind < YR_OPT_SGD || opt->kind > YR_OPT_ADAMW) return YR_ERR_BAD_OPT;
+    if (opt->kind != YR_OPT_SGD && (cdae_tensors_ok(m) || cdae_tensors_ok(v))) return YR_ERR_BAD_ARG;
+  }
+  return YR_OK;
+}
+
+extern "C" int yr_cdae_step_idx(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                                const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                                const int64_t* uid, const int32_t* in_ptr, const int32_t* in_idx, const float* in_val,
+                                const int32_t* tgt_ptr, const int32_t* tgt_idx, const float* tgt_val, int64_t B,
+                                double* loss, float* step_loss, void* ws, size_t ws_bytes, int32_t* err, yr_stream stream) {
+  if (!uid || !in_ptr || !in_idx || !tgt_ptr || !tgt_idx || !tgt_val || !loss || !ws || B <= 0 || nI <= 0) return YR_ERR_BAD_ARG;
+  int rc = cdae_step_args_ok(P, grads, m, v, opt, h, hidden_act);
+  if (rc) return rc;
+  if (ws_bytes < yr_cdae_ws_bytes(B, nI)) return YR_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  CdaeWs w;
+  cdae_ws_layout(B, nI, ws, &w);
+  YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
+  cdae_lists_kernel<<<(unsigned)B, 256, 0, s>>>(in_ptr, in_idx, in_val, tgt_ptr, tgt_idx, tgt_val, nI, w, err);
+  YR_CHECK_LAUNCH();
+  return cdae_step_tail(P, grads, m, v, opt, nU, nI, h, hidden_act, uid, B, loss, step_loss, w, err, stream);
+}
+
 extern "C" int yr_cdae_step(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
                             const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h,
                             const int64_t* uid, const float* x, const float* keep, const float* target,
@@ -384,6 +460,16 @@ extern "C" int yr_cdae_step_ex(const yr_cdae_tensors* P, const yr_cdae_tensors* 
   YR_CUDA(cudaMemsetAsync(w.total, 0, 16, s));
   cdae_compact_kernel<<<(unsigned)B, kCompactThreads, 0, s>>>(x, keep, target, negative_mask, nI, w);
   YR_CHECK_LAUNCH();
+  return cdae_step_tail(P, grads, m, v, opt, nU, nI, h, hidden_act, uid, B, loss, step_loss, w, err, stream);
+}
+
+// everything of a step behind the compaction / list staging: row kernel (forward, loss, backward), loss finish, optimizer
+static int cdae_step_tail(const yr_cdae_tensors* P, const yr_cdae_tensors* grads, const yr_cdae_tensors* m,
+                          const yr_cdae_tensors* v, const yr_opt* opt, int64_t nU, int64_t nI, int h, int hidden_act,
+                          const int64_t* uid, int64_t B, double* loss, float* step_loss, const CdaeWs& w, int32_t* err,
+                          yr_stream stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool train = opt != nullptr;
   yr_cdae_tensors none = {};
   int rrc = train ? launch_cdae_row<true>(h, B, s, *P, *grads, nU, nI, uid, w, true, nullptr, 0, loss + 1, err, hidden_act)
                   : launch_cdae_row<false>(h, B, s, *P, none, nU, nI, uid, w, true, nullptr, 0, loss + 1, err, hidden_act);

@@ -1,7 +1,8 @@
 """Drop-in for the reference's trainers/cdae_trainer.py:22-144 on the sm_100a kernels (BASELINE config 4).
 
 `train` runs one yr_cdae_step per DataLoader batch: the dense `input_mask` / `negative_mask` rows the reference's
-CDAEDataset yields are compacted on the device, the loss and its gradient are evaluated only at the loss positions, and
+CDAEDataset yields are compacted on the device (or, for index-list batches — data/cdae_sparse.py — shipped as a few hundred
+bytes per user through yr_cdae_step_idx), the loss and its gradient are evaluated only at the loss positions, and
 every parameter gets torch's dense optimizer step. `validate` returns the reference's 5-tuple (loss, P, R, MAP, NDCG),
 `evaluate` the 4 metrics; both rank with the fused full-catalog kernels on the output LOGITS: sigmoid is monotone, so
 top-K by logit equals top-K by prediction except where the float sigmoid saturates into ties — which the reference
@@ -85,6 +86,38 @@ class CDAETrainer(BaseTrainer):
         if train:
             self.optimizer.step_count += 1
 
+    def _step_idx(self, data, train: bool, step_loss=None, keep_vals=None):
+        """One step from an index-list batch (data/cdae_sparse.py): nothing of size B x num_items crosses PCIe or exists in HBM."""
+        lib = _cabi.load()
+        m = self.model
+        b, g, mo, vo = self._state()
+        dev = self.device
+        mv = lambda k, dt: data[k].to(device=dev, dtype=dt, non_blocking=True).contiguous()
+        uid, in_ptr, in_idx = mv("user_id", I64), mv("input_ptr", I32), mv("input_idx", I32)
+        ls_ptr, ls_idx, ls_val = mv("loss_ptr", I32), mv("loss_idx", I32), mv("loss_val", F32)
+        B = int(uid.numel())
+        in_val = None
+        if train:
+            if keep_vals is not None:
+                in_val = keep_vals.to(device=dev, dtype=F32).contiguous()
+            else:
+                p_drop = float(m.corruption_level)
+                in_val = ((torch.rand(in_idx.numel(), device=dev) >= p_drop).to(F32) / (1.0 - p_drop)) if p_drop > 0 else None
+        ws = m.workspace(B)
+        P = m.tensors()
+        opt = self.optimizer.opt_struct(self.optimizer.step_count + 1) if train else None
+        _cabi.check(lib.yr_cdae_step_idx(C.byref(P), C.byref(g) if train else None,
+                                         C.byref(mo) if (train and mo is not None) else None,
+                                         C.byref(vo) if (train and vo is not None) else None,
+                                         C.byref(opt) if train else None, self.num_users, self.num_items, m.hidden_size,
+                                         m.hidden_act, _cabi.dptr(uid), _cabi.dptr(in_ptr), _cabi.dptr(in_idx),
+                                         _cabi.dptr(in_val) if in_val is not None else None, _cabi.dptr(ls_ptr),
+                                         _cabi.dptr(ls_idx), _cabi.dptr(ls_val), B, _cabi.dptr(b["loss"]),
+                                         _cabi.dptr(step_loss) if step_loss is not None else None, _cabi.dptr(ws), ws.numel(),
+                                         _cabi.dptr(b["err"]), _cabi.stream_ptr(dev)), "yr_cdae_step_idx")
+        if train:
+            self.optimizer.step_count += 1
+
     def _loss_sum(self) -> float:
         b = self._bufs
         v = float(b["loss"][0].item())
@@ -101,9 +134,13 @@ class CDAETrainer(BaseTrainer):
         keeps = iter(keeps) if keeps is not None else None
         losses = []
         for data in train_dataloader:
+            sl = torch.empty(1, device=self.device, dtype=F32)
+            if "input_idx" in data:                         # index-list batch (data/cdae_sparse.py): `keeps` = values per listed input
+                self._step_idx(data, True, sl, next(keeps) if keeps is not None else None)
+                losses.append(sl)
+                continue
             x = data["input_mask"].to(self.device, dtype=F32)
             keep = next(keeps).to(self.device, dtype=F32).contiguous() if keeps is not None else self.model.draw_keep(x)
-            sl = torch.empty(1, device=self.device, dtype=F32)
             self._step(data["user_id"], x, keep, x, data["negative_mask"], True, sl)
             losses.append(sl)
         if not losses:
