@@ -161,6 +161,7 @@ class ShardedMFTrainer:
         self.err = z(1, dt=I32)
         self._cap = 0
         self._a2a, self._a2a_cap = None, 0
+        self._slot_cache = None
         self.last_step_losses = None
 
     # ------------------------------------------------------------------------------------------
@@ -224,22 +225,31 @@ class ShardedMFTrainer:
         bad = ((uid < 0) | (uid >= self.num_users) | (pos < 0) | (pos >= self.num_items) | (neg < 0) | (neg >= self.num_items)).any()
         self.err |= bad.to(I32)
         uid, pos, neg = uid.clamp(0, self.num_users - 1), pos.clamp(0, self.num_items - 1), neg.clamp(0, self.num_items - 1)
-        # ---- 1. plan: slot = 3 * triple + role; owner and owner-local row of every slot
+        # ---- 1. plan: slot = 3 * triple + role; owner and owner-local row of every slot. One host round trip per step: the
+        # world x world count matrix (who sends how many rows to whom) plus this rank's per-table counts.
         ou = torch.bucketize(uid, self._ustart[1:], right=True)
         op = torch.bucketize(pos, self._istart[1:], right=True)
         on = torch.bucketize(neg, self._istart[1:], right=True)
         owner = torch.stack((ou, op, on), 1).view(-1)
-        lrow = torch.stack((uid - self._ustart[ou], pos - self._istart[op], neg - self._istart[on]), 1).view(-1).to(I32)
-        slot = torch.arange(3 * B, device=dev)
-        requester = (slot // 3) // S
-        mine = (owner == me).nonzero(as_tuple=False).view(-1)              # slots I own, in slot (= requester, slot) order
-        my_sel = ((mine % 3) != 0).to(I32)                                   # 0 = user table, 1 = item table
-        my_row = lrow[mine]
-        own_slice = owner[3 * b0: 3 * b1]
-        order = torch.argsort(own_slice, stable=True)                        # my slice's slots grouped by owner
-        counts = torch.stack((torch.bincount(requester[mine], minlength=N), torch.bincount(own_slice, minlength=N))).cpu()
-        send_counts, recv_counts = counts[0].tolist(), counts[1].tolist()
-        n_send, n_slice = int(mine.numel()), 3 * (b1 - b0)
+        lrow = torch.stack((uid - self._ustart[ou], pos - self._istart[op], neg - self._istart[on]), 1).view(-1)
+        if self._slot_cache is None or self._slot_cache[0] != (B, S):
+            slot = torch.arange(3 * B, device=dev)
+            self._slot_cache = ((B, S), (slot // 3) // S, (slot % 3 != 0).to(I64))      # requester and table (0 user, 1 item) of a slot
+        requester, table = self._slot_cache[1], self._slot_cache[2]
+        is_mine = owner == me
+        cm = torch.bincount(requester * N + owner, minlength=N * N)                     # [requester, owner] counts
+        n_item_mine = (is_mine & (table == 1)).sum()
+        host = torch.cat((cm, n_item_mine.view(1))).cpu()
+        cm_h = host[: N * N].view(N, N)
+        send_counts, recv_counts = cm_h[:, me].tolist(), cm_h[me, :].tolist()
+        n_send, n_slice = int(sum(send_counts)), 3 * (b1 - b0)
+        n_v = int(host[-1])
+        n_u = n_send - n_v
+        # slots I own, in slot (= requester, slot) order: a stable sort that moves them to the front
+        mine = torch.argsort(~is_mine, stable=True)[:n_send]
+        my_sel = table[mine].to(I32)
+        my_row = lrow[mine].to(I32)
+        order = torch.argsort(owner[3 * b0: 3 * b1], stable=True)                        # my slice's slots grouped by owner
         if self._a2a_cap < max(n_send, n_slice, 1):
             cap = max(n_send, n_slice, 1) * 5 // 4
             self._a2a = [torch.empty(cap, d, device=dev, dtype=F32) for _ in range(4)]
@@ -250,14 +260,15 @@ class ShardedMFTrainer:
         dense = (opt.kind != _cabi.YR_OPT_SGD) or (opt.weight_decay != 0.0)
         sparse_adam = self._sparse_adam()
         listed = (not dense) or sparse_adam
-        # the slots I own, grouped by table row (stable: equal rows keep slot order) — used twice: sparse Adam brings the rows
-        # up to date before they are read, and the ordered accumulate sums every segment left to right
+        # the slots I own, grouped by (table, table row) with ONE stable sort (equal rows keep slot order) — used twice: sparse
+        # Adam brings the rows up to date before they are read, and the ordered accumulate sums every segment left to right
+        key_sorted, perm = torch.sort(my_sel.to(I64) * (1 << 32) + my_row.to(I64), stable=True)
+        rows_all = (key_sorted & 0xFFFFFFFF).to(I32)
+        src_all = perm.to(I32)
         groups = []
-        for s_, table in ((su, 0), (sv, 1)):
-            idx = (my_sel == table).nonzero(as_tuple=False).view(-1)
-            rows_sorted, perm = torch.sort(my_row[idx], stable=True)
-            groups.append((s_, idx, rows_sorted.contiguous(), idx[perm].to(I32).contiguous()))
-            if sparse_adam and idx.numel():
+        for s_, lo_, n_ in ((su, 0, n_u), (sv, n_u, n_v)):
+            groups.append((s_, n_, rows_all[lo_: lo_ + n_].contiguous(), src_all[lo_: lo_ + n_].contiguous()))
+            if sparse_adam and n_:
                 scal, n_scal = self._scalars(opt.step)
                 k.catch_up(s_, opt, scal, n_scal, groups[-1][2], d)
         # ---- 2./3. owners pack the rows, requesters receive them grouped by owner, then put them in slot order
@@ -278,11 +289,11 @@ class ShardedMFTrainer:
         else:
             grecv = gsend
         # ---- 6./7. ordered accumulate per table, one optimizer step per table
-        for s_, idx, rows_sorted, src in groups:
-            n_t = int(idx.numel()) if listed else 0
-            if idx.numel():
-                if s_["rows_list"] is None or s_["rows_list"].numel() < idx.numel():
-                    s_["rows_list"] = torch.zeros(int(idx.numel()) * 5 // 4 + 16, device=dev, dtype=I32)
+        for s_, n_, rows_sorted, src in groups:
+            n_t = n_ if listed else 0
+            if n_:
+                if s_["rows_list"] is None or s_["rows_list"].numel() < n_:
+                    s_["rows_list"] = torch.zeros(n_ * 5 // 4 + 16, device=dev, dtype=I32)
                 k.accumulate_sorted(s_, opt, rows_sorted, src, grecv, listed)
             if s_["rows_list"] is None:
                 s_["rows_list"] = torch.zeros(16, device=dev, dtype=I32)
