@@ -119,3 +119,49 @@ def test_unsupported_widths_fail_loudly():
     with pytest.raises(YelprecError):
         CDAE(SimpleNamespace(hidden_size=64, **{**base, "output_activation": "identity"}), 12, 10)
     CDAE(SimpleNamespace(hidden_size=1024, **{**base, "hidden_activation": "identity"}), 12, 10)
+
+
+def test_shard_layout_positions_are_a_monotone_bijection():
+    """data/scaled.py::ShardLayout — rank k owns a block of users AND a block of items; positions in the gathered operand are
+    rank-major, every node has exactly one position, users / items map monotonically (so CSR rows keep their column order at
+    any world size), and local_rows / to_node_order are inverse to each other."""
+    import torch
+    from yelprecommendation_b200.data.scaled import ShardLayout
+    for nU, nI, world in ((10, 4, 1), (103, 57, 3), (1000, 333, 8), (7, 5, 8)):
+        lay = ShardLayout(nU, nI, world)
+        pos = lay.node_pos(torch.arange(nU + nI)).numpy()
+        assert len(set(pos.tolist())) == nU + nI and pos.min() >= 0 and pos.max() < world * lay.per
+        assert np.all(np.diff(pos[:nU]) > 0) and np.all(np.diff(pos[nU:]) > 0)
+        owners = pos // lay.per
+        for k in range(world):
+            (u0, u1), (i0, i1) = lay.user_block(k), lay.item_block(k)
+            assert np.all(owners[u0:u1] == k) and np.all(owners[nU + i0: nU + i1] == k)
+        table = torch.arange((nU + nI) * 3, dtype=torch.float32).view(nU + nI, 3)
+        gathered = torch.cat([lay.local_rows(k, table) for k in range(world)])
+        assert torch.equal(lay.to_node_order(gathered), table)
+        if world == 1:
+            assert np.array_equal(pos, np.arange(nU + nI))
+
+
+def test_sparse_cdae_batch_equals_the_dense_masks():
+    """data/cdae_sparse.py: index lists carry exactly the information of the reference's dense CDAE batch
+    (data/datasets/cdae_dataset.py:38-62): active inputs, and the loss positions target + negative_mask != 0 with their targets."""
+    import torch
+    from yelprecommendation_b200.data.cdae_sparse import sparse_cdae_batch
+    rng = np.random.default_rng(0)
+    B, nI = 9, 101
+    x = (rng.random((B, nI)) < 0.1).astype(np.float32)
+    valid = ((rng.random((B, nI)) < 0.05) & (x == 0)).astype(np.float32)
+    neg = ((rng.random((B, nI)) < 0.2) & (x == 0) & (valid == 0)).astype(np.float32)
+    x[3] = 0                                                               # a user without inputs
+    data = {"user_id": torch.arange(B), "input_mask": torch.from_numpy(x), "valid_mask": torch.from_numpy(valid),
+            "negative_mask": torch.from_numpy(neg)}
+    for extra in (None, "valid_mask"):
+        s = sparse_cdae_batch(data, target_extra=extra)
+        tgt = x if extra is None else x + valid
+        ip, ii, lp, li, lv = (s[k].numpy() for k in ("input_ptr", "input_idx", "loss_ptr", "loss_idx", "loss_val"))
+        for b in range(B):
+            assert np.array_equal(ii[ip[b]:ip[b + 1]], np.nonzero(x[b])[0])
+            want = np.nonzero((tgt[b] + neg[b]) != 0)[0]
+            assert np.array_equal(li[lp[b]:lp[b + 1]], want)
+            assert np.array_equal(lv[lp[b]:lp[b + 1]], tgt[b][want])
