@@ -19,8 +19,10 @@ One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:10
                             G_l += L^T[block, :] X_T;   all_reduce(dW1, dW2) once per step
     update               :  yr_dense_opt_step on the local rows of E_0 and (identically on every rank) on the weights
 
-The all-gather of a layer is therefore hidden behind the compute of the other panels; only the last panel's exchange
-(1 / P of N * d * 4 bytes) is exposed. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
+Where the whole operand is exchanged right before it is consumed — layer 0 (it follows the optimizer step) and every
+backward layer (T) — the SpMM is cut by COLUMN panel instead: the entries whose column is a row of panel p on some rank; the
+SpMM over column panel p needs only exchange round p and runs underneath round p+1. Only one round (1 / P of N * d * 4
+bytes) per layer stays exposed. YR_SHARD_COLPANELS=0 keeps the row-panel-only schedule of the first version. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
 cut on the device, any weights) or as a data.scaled.ScaledGraph (config 5: generated and normalised on the device).
 No CPU product path: `device` / `kernels` exist so that tests/_dist_shard_worker.py can drive the choreography under gloo
 with a CPU restatement of the kernels.
@@ -28,6 +30,7 @@ with a CPU restatement of the kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List
 
 import numpy as np
@@ -135,7 +138,6 @@ class ShardedNGCFTrainer:
             rp, ci, va = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev)
             rpT, ciT, vaT = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev, transpose=True)
         self.nnz_local = int(ci.numel())
-        import os
         P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", int(os.environ.get("YR_SHARD_PANELS", "8")) if self.world > 1 else 1))
         P = max(1, min(P, self.per))
         step = ((self.per + P - 1) // P + 127) // 128 * 128          # whole 128-row tiles of the dense kernels
@@ -143,6 +145,14 @@ class ShardedNGCFTrainer:
         self.panels = [(a, min(a + step, self.per), self.k.make_csr(rp_h[a: min(a + step, self.per) + 1], ci, va))
                        for a in range(0, self.per, step)]
         self.AT = self.k.make_csr(rpT.cpu(), ciT, vaT) if (rpT is not rp or len(self.panels) > 1) else self.panels[0][2]
+        # COLUMN panels (one per row panel of the gathered operand): the SpMM over column panel p only needs the rows
+        # every rank sent in exchange round p, so it can run underneath round p+1 — used where the whole operand is
+        # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
+        self.use_col_panels = self.world > 1 and len(self.panels) > 1 and int(os.environ.get("YR_SHARD_COLPANELS", "1")) != 0
+        self.colA = self.colAT = None
+        if self.use_col_panels:
+            self.colAT = self._column_panels(rpT, ciT, vaT, step)
+            self.colA = self.colAT if rpT is rp else self._column_panels(rp, ci, va, step)
         # ---- parameters
         d, per = self.d, self.per
         f = lambda t: t.detach().to(dev, F32).contiguous().clone()
@@ -181,6 +191,25 @@ class ShardedNGCFTrainer:
         self._peers = [r for r in range(self.world) if r != self.rank]
         self._grank = (lambda r: dist.get_global_rank(self.group, r)) if (self.group is not None and self.world > 1) else (lambda r: r)
 
+    def _column_panels(self, rp, ci, va, step):
+        """The row block cut by COLUMN panel: panel p holds the entries whose column is a row of panel p on some rank
+        ((col mod per) in [a_p, b_p)), all local rows, columns ascending inside a row. A stable sort by panel keeps the
+        (row, column) order inside every panel; the flat cumulative count is every panel's rowptr (absolute offsets into the
+        re-ordered col / val, which the panels share)."""
+        per, P = self.per, len(self.panels)
+        pan = (ci.to(I64) % per) // step
+        order = torch.argsort(pan, stable=True)
+        rows = torch.repeat_interleave(torch.arange(per, device=ci.device), (rp[1:] - rp[:-1]).to(I64))
+        key = pan[order] * per + rows[order]
+        del pan, rows
+        ci_p, va_p = ci[order].contiguous(), va[order].contiguous()
+        del order
+        ptr = torch.zeros(P * per + 1, dtype=I64, device=ci.device)
+        ptr[1:] = torch.cumsum(torch.bincount(key, minlength=P * per), 0)
+        del key
+        ptr_h = ptr.to(I32).cpu()
+        return [self.k.make_csr(ptr_h[p * per: (p + 1) * per + 1], ci_p, va_p) for p in range(P)]
+
     # ------------------------------------------------------------------------------------------
     def _post_exchange(self, src: torch.Tensor, a: int, b: int, buf: int) -> None:
         """rows [a, b) of the local [per x d] matrix -> the same rows of this rank's slot in EVERY rank's X[buf]:
@@ -193,12 +222,19 @@ class ShardedNGCFTrainer:
         for r in self._peers:
             ops_.append(dist.P2POp(dist.isend, src[a:b], self._grank(r), self.group))
             ops_.append(dist.P2POp(dist.irecv, X[r * per + a: r * per + b], self._grank(r), self.group))
-        self._pending[buf].extend(dist.batch_isend_irecv(ops_))
+        self._pending[buf].append(dist.batch_isend_irecv(ops_))      # one entry per posted round, in posting order
 
     def _wait(self, buf: int) -> None:
-        for w in self._pending[buf]:
-            w.wait()
+        for works in self._pending[buf]:
+            for w in works:
+                w.wait()
         self._pending[buf] = []
+
+    def _wait_round(self, buf: int) -> None:
+        """wait for the OLDEST posted exchange round of this buffer"""
+        if self._pending[buf]:
+            for w in self._pending[buf].pop(0):
+                w.wait()
 
     def _exchange_all(self, src: torch.Tensor, buf: int) -> None:
         for a, b, _ in self.panels:
@@ -209,8 +245,19 @@ class ShardedNGCFTrainer:
         self._exchange_all(self.E[0], 0)
         for l in range(L):
             buf = l & 1
-            self._wait(buf)
             X = self.X[buf] if self.world > 1 else self.E[l]
+            if l == 0 and self.use_col_panels:
+                # the operand of layer 0 has only just been posted (it follows the optimizer step): consume it column panel
+                # by column panel as the rounds arrive, then transform and send the next layer's panels
+                for p in range(len(self.panels)):
+                    self._wait_round(buf)
+                    k.spmm(self.colA[p], X, self.LE[l], p > 0)
+                for a, b, _ in self.panels:
+                    k.dense_fwd(self.E[l][a:b], self.LE[l][a:b], self.W1[l], self.W2[l], self.E[l + 1][a:b])
+                    if l + 1 < L:
+                        self._post_exchange(self.E[l + 1], a, b, buf ^ 1)
+                continue
+            self._wait(buf)
             for a, b, Ap in self.panels:
                 k.spmm(Ap, X, self.LE[l][a:b], False)
                 k.dense_fwd(self.E[l][a:b], self.LE[l][a:b], self.W1[l], self.W2[l], self.E[l + 1][a:b])
@@ -250,10 +297,17 @@ class ShardedNGCFTrainer:
                 k.dense_bwd(self.E[l][a:b], self.LE[l][a:b], self.E[l + 1][a:b], self.G[l + 1][a:b], self.W1[l], self.W2[l],
                             self.G[l][a:b], self.T[a:b], self.dWp[pi, 0], self.dWp[pi, 1])
                 self._post_exchange(self.T, a, b, buf)
+                if self.use_col_panels and pi >= 1:              # round pi-1 has had a panel's worth of compute to arrive
+                    self._wait_round(buf)
+                    k.spmm(self.colAT[pi - 1], self.X[buf], self.G[l], True)
             torch.sum(self.dWp[:, 0], dim=0, out=self.dW[l])
             torch.sum(self.dWp[:, 1], dim=0, out=self.dW[L + l])
-            self._wait(buf)
-            k.spmm(self.AT, self.X[buf] if self.world > 1 else self.T, self.G[l], True)
+            if self.use_col_panels:
+                self._wait_round(buf)
+                k.spmm(self.colAT[len(self.panels) - 1], self.X[buf], self.G[l], True)
+            else:
+                self._wait(buf)
+                k.spmm(self.AT, self.X[buf] if self.world > 1 else self.T, self.G[l], True)
         if self.world > 1:
             dist.all_reduce(self.dW, op=dist.ReduceOp.SUM, group=self.group)
         # ---- optimizer: parameter order embedding, W1.*, W2.* (nn.Module.parameters()); all tensors share the step count
