@@ -236,20 +236,26 @@ class ShardedMFTrainer:
             slot = torch.arange(3 * B, device=dev)
             self._slot_cache = ((B, S), (slot // 3) // S, (slot % 3 != 0).to(I64))      # requester and table (0 user, 1 item) of a slot
         requester, table = self._slot_cache[1], self._slot_cache[2]
-        is_mine = owner == me
-        cm = torch.bincount(requester * N + owner, minlength=N * N)                     # [requester, owner] counts
-        n_item_mine = (is_mine & (table == 1)).sum()
-        host = torch.cat((cm, n_item_mine.view(1))).cpu()
-        cm_h = host[: N * N].view(N, N)
-        send_counts, recv_counts = cm_h[:, me].tolist(), cm_h[me, :].tolist()
-        n_send, n_slice = int(sum(send_counts)), 3 * (b1 - b0)
-        n_v = int(host[-1])
-        n_u = n_send - n_v
-        # slots I own, in slot (= requester, slot) order: a stable sort that moves them to the front
-        mine = torch.argsort(~is_mine, stable=True)[:n_send]
-        my_sel = table[mine].to(I32)
-        my_row = lrow[mine].to(I32)
-        order = torch.argsort(owner[3 * b0: 3 * b1], stable=True)                        # my slice's slots grouped by owner
+        if N == 1:                                   # one rank owns and computes everything: no plan, no host round trip
+            send_counts = recv_counts = [3 * B]
+            n_send = n_slice = 3 * B
+            n_u, n_v = B, 2 * B
+            my_sel, my_row, order = table.to(I32), lrow.to(I32), None
+        else:
+            is_mine = owner == me
+            cm = torch.bincount(requester * N + owner, minlength=N * N)                 # [requester, owner] counts
+            n_item_mine = (is_mine & (table == 1)).sum()
+            host = torch.cat((cm, n_item_mine.view(1))).cpu()
+            cm_h = host[: N * N].view(N, N)
+            send_counts, recv_counts = cm_h[:, me].tolist(), cm_h[me, :].tolist()
+            n_send, n_slice = int(sum(send_counts)), 3 * (b1 - b0)
+            n_v = int(host[-1])
+            n_u = n_send - n_v
+            # slots I own, in slot (= requester, slot) order: a stable sort that moves them to the front
+            mine = torch.argsort(~is_mine, stable=True)[:n_send]
+            my_sel = table[mine].to(I32)
+            my_row = lrow[mine].to(I32)
+            order = torch.argsort(owner[3 * b0: 3 * b1], stable=True)                    # my slice's slots grouped by owner
         if self._a2a_cap < max(n_send, n_slice, 1):
             cap = max(n_send, n_slice, 1) * 5 // 4
             self._a2a = [torch.empty(cap, d, device=dev, dtype=F32) for _ in range(4)]
@@ -275,19 +281,19 @@ class ShardedMFTrainer:
         k.gather_local(su, sv, my_sel, my_row, packed)
         if N > 1:
             self._p2p(packed, send_counts, rbuf, recv_counts)
+            R.index_copy_(0, order, rbuf)
         else:
-            rbuf = packed
-        R.index_copy_(0, order, rbuf)
+            R = packed                                               # already in slot order
         # ---- 4. loss + gradient rows of my slice
         if b1 > b0:
             k.rows_grad_slice(R.view(-1, 3, d), B, b0, b1, G.view(-1, 3, d), loss_acc)
         # ---- 5. gradient rows back to the owners (received in requester, slot order = the order of `mine`)
-        gsend = G.index_select(0, order)
-        grecv = self._a2a[0][:n_send]                                        # the packed rows are no longer needed
         if N > 1:
+            gsend = G.index_select(0, order)
+            grecv = self._a2a[0][:n_send]                                    # the packed rows are no longer needed
             self._p2p(gsend, recv_counts, grecv, send_counts)
         else:
-            grecv = gsend
+            grecv = G
         # ---- 6./7. ordered accumulate per table, one optimizer step per table
         for s_, n_, rows_sorted, src in groups:
             n_t = n_ if listed else 0
