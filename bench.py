@@ -200,11 +200,12 @@ def config5_extras(extra, dev, rank, world, barrier, max_over_ranks, pk, args):
     torch.cuda.empty_cache()
     g5 = torch.Generator(device=dev).manual_seed(5)              # same triples on every rank
     n_mf = 12
+    skip_mf = os.environ.get("YR_C5_SKIP_MF", "0") == "1"          # experiments on the NGCF exchange only
     su5 = torch.randint(0, nU5, (n_mf + 3, B5), device=dev, generator=g5)
     sp5 = torch.randint(0, nI5, (n_mf + 3, B5), device=dev, generator=g5)
     sn5 = torch.randint(0, nI5, (n_mf + 3, B5), device=dev, generator=g5)
     # ---- row-sharded BPR-MF
-    for oname in ("sgd", "adam"):
+    for oname in (() if skip_mf else ("sgd", "adam")):
         try:
             tr = ShardedMFTrainer(cfg(embed_size=d5, optimizer=oname), nI5, nU5)
             acc = torch.zeros(1, device=dev, dtype=torch.float64)

@@ -22,7 +22,8 @@ One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:10
 Where the whole operand is exchanged right before it is consumed — layer 0 (it follows the optimizer step) and every
 backward layer (T) — the SpMM is cut by COLUMN panel instead: the entries whose column is a row of panel p on some rank; the
 SpMM over column panel p needs only exchange round p and runs underneath round p+1. Only one round (1 / P of N * d * 4
-bytes) per layer stays exposed. YR_SHARD_COLPANELS=0 keeps the row-panel-only schedule of the first version. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
+bytes) per layer stays exposed. Measured on 8 x B200 (profiles/README.md): no gain (133.5 vs 131.0 ms per step — eight SpMMs
+over short row fragments cost what the overlap saves), so it is off by default: YR_SHARD_COLPANELS=1 enables it. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
 cut on the device, any weights) or as a data.scaled.ScaledGraph (config 5: generated and normalised on the device).
 No CPU product path: `device` / `kernels` exist so that tests/_dist_shard_worker.py can drive the choreography under gloo
 with a CPU restatement of the kernels.
@@ -148,7 +149,9 @@ class ShardedNGCFTrainer:
         # COLUMN panels (one per row panel of the gathered operand): the SpMM over column panel p only needs the rows
         # every rank sent in exchange round p, so it can run underneath round p+1 — used where the whole operand is
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
-        self.use_col_panels = self.world > 1 and len(self.panels) > 1 and int(os.environ.get("YR_SHARD_COLPANELS", "1")) != 0
+        self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "p2p")
+        self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode != "allgather"
+                               and int(os.environ.get("YR_SHARD_COLPANELS", "0")) != 0)
         self.colA = self.colAT = None
         if self.use_col_panels:
             self.colAT = self._column_panels(rpT, ciT, vaT, step)
@@ -217,7 +220,16 @@ class ShardedNGCFTrainer:
         if self.world == 1:
             return
         X, per = self.X[buf], self.per
+        if self._xmode == "allgather":
+            # experiment (YR_SHARD_EXCHANGE=allgather): ONE NCCL all-gather of the whole matrix, posted with the last panel
+            # (the rank-major layout of X is exactly all_gather_into_tensor's output) — no panel pipelining
+            if b >= self.per:
+                self._pending[buf].append([dist.all_gather_into_tensor(X, src, group=self.group, async_op=True)])
+            return
         X[self.lo + a: self.lo + b].copy_(src[a:b])
+        if self._xmode == "none":              # experiment (YR_SHARD_EXCHANGE=none): compute only, results are garbage
+            self._pending[buf].append([])
+            return
         ops_ = []
         for r in self._peers:
             ops_.append(dist.P2POp(dist.isend, src[a:b], self._grank(r), self.group))
