@@ -134,8 +134,8 @@ def test_scaled_graph_generator_properties():
     assert torch.equal(g.user_ptr, g2.user_ptr) and torch.equal(g.user_items, g2.user_items)
 
 
-@pytest.mark.parametrize("world", [1, 3, 8])
-def test_shard_laplacian_blocks_equal_the_reference_laplacian(world):
+@pytest.mark.parametrize("world,panels", [(1, 1), (3, 1), (8, 1), (1, 4), (4, 8)])
+def test_shard_laplacian_blocks_equal_the_reference_laplacian(world, panels):
     """Row blocks cut on the device (shard_laplacian: binary ratings, yr_laplacian_binary_values) re-assembled in the
     reference's node order == data.graph.build_laplacian of the same interactions (pinned to the reference,
     tests/test_oracle_golden.py) bit for bit; the COO entry point gives the same blocks."""
@@ -148,7 +148,7 @@ def test_shard_laplacian_blocks_equal_the_reference_laplacian(world):
     L = build_laplacian(users, items, np.ones(items.size), nU, nI)
     idx, val = L.indices().numpy(), L.values().numpy()
     rp_ref, ci_ref, va_ref = coo_to_csr(idx[0], idx[1], val, nU + nI)
-    lay = ShardLayout(nU, nI, world)
+    lay = ShardLayout(nU, nI, world, panels)
     pos_of_node = lay.node_pos(torch.arange(nU + nI)).numpy()
     node_of_pos = np.full(world * lay.per, -1, np.int64)
     node_of_pos[pos_of_node] = np.arange(nU + nI)

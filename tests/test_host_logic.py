@@ -127,8 +127,10 @@ def test_shard_layout_positions_are_a_monotone_bijection():
     any world size), and local_rows / to_node_order are inverse to each other."""
     import torch
     from yelprecommendation_b200.data.scaled import ShardLayout
-    for nU, nI, world in ((10, 4, 1), (103, 57, 3), (1000, 333, 8), (7, 5, 8)):
-        lay = ShardLayout(nU, nI, world)
+    for nU, nI, world, panels in ((10, 4, 1, 1), (103, 57, 3, 1), (1000, 333, 8, 1), (7, 5, 8, 1), (10, 4, 1, 3), (1000, 333, 8, 4),
+                                  (5003, 1201, 2, 8)):
+        lay = ShardLayout(nU, nI, world, panels)
+        assert lay.per == lay.panels * lay.pp and (panels == 1 or lay.pp % 128 == 0)
         pos = lay.node_pos(torch.arange(nU + nI)).numpy()
         assert len(set(pos.tolist())) == nU + nI and pos.min() >= 0 and pos.max() < world * lay.per
         assert np.all(np.diff(pos[:nU]) > 0) and np.all(np.diff(pos[nU:]) > 0)
@@ -139,8 +141,15 @@ def test_shard_layout_positions_are_a_monotone_bijection():
         table = torch.arange((nU + nI) * 3, dtype=torch.float32).view(nU + nI, 3)
         gathered = torch.cat([lay.local_rows(k, table) for k in range(world)])
         assert torch.equal(lay.to_node_order(gathered), table)
-        if world == 1:
+        if world == 1 and panels == 1:
             assert np.array_equal(pos, np.arange(nU + nI))
+        if panels > 1:                              # every panel holds a slice of the users AND a slice of the items
+            local = pos % lay.per
+            for p_ in range(lay.panels):
+                a, b = lay.panel_rows(p_)
+                in_p = (local >= a) & (local < b)
+                if nU >= 4 * world * panels and nI >= 4 * world * panels:
+                    assert in_p[:nU].any() and in_p[nU:].any()
 
 
 def test_sparse_cdae_batch_equals_the_dense_masks():

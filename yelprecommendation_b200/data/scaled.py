@@ -73,14 +73,27 @@ def make_scaled_graph(num_users: int, num_items: int, target_nnz: int, seed: int
 
 @dataclass
 class ShardLayout:
+    """Who owns which node and where its row sits. Rank k owns users [k * perU, (k+1) * perU) and items [k * perI, (k+1) * perI).
+    Inside a rank the rows are cut into `panels` row panels of `pp = perUp + perIp` rows, each holding a slice of the rank's
+    users FOLLOWED BY a slice of its items: every panel then carries about 1 / panels of the rank's non-zeros and of BOTH kinds
+    of columns (a [all users ; all items] order would put every item — half of the non-zeros, and all the columns the user
+    rows reference — into the last panel, and the panel pipeline would degenerate). panels = 1 is [users ; items]."""
     num_users: int
     num_items: int
     world: int
+    panels: int = 1
 
     def __post_init__(self):
-        self.perU = (self.num_users + self.world - 1) // self.world
+        P = max(1, int(self.panels))
+        self.perU = (self.num_users + self.world - 1) // self.world      # users / items a rank owns (ids are blocked by these)
         self.perI = (self.num_items + self.world - 1) // self.world
-        self.per = self.perU + self.perI                 # rows of every rank's block (the last ranks' tails are padding)
+        self.perUp = (self.perU + P - 1) // P                           # of them per panel
+        self.perIp = (self.perI + P - 1) // P
+        self.panels = P
+        self.pp = self.perUp + self.perIp                                # rows of a panel ...
+        if P > 1:
+            self.pp += (-self.pp) % 128                                  # ... padded to whole 128-row tiles of the dense kernels
+        self.per = P * self.pp                                           # rows of every rank's block (the rest is padding)
 
     def user_block(self, rank: int) -> Tuple[int, int]:
         a = min(rank * self.perU, self.num_users)
@@ -90,16 +103,27 @@ class ShardLayout:
         a = min(rank * self.perI, self.num_items)
         return a, min(a + self.perI, self.num_items)
 
+    def panel_rows(self, p: int) -> Tuple[int, int]:
+        return p * self.pp, (p + 1) * self.pp
+
+    def user_local(self, lu: torch.Tensor) -> torch.Tensor:
+        """index inside the rank's user block -> local row"""
+        return (lu // self.perUp) * self.pp + (lu % self.perUp)
+
+    def item_local(self, li: torch.Tensor) -> torch.Tensor:
+        return (li // self.perIp) * self.pp + self.perUp + (li % self.perIp)
+
     def user_pos(self, u: torch.Tensor) -> torch.Tensor:
         """position of user ids in the gathered operand [world * per rows] (monotonic in u)"""
-        if self.world == 1:
+        if self.world == 1 and self.panels == 1:
             return u
-        return (u // self.perU) * self.per + (u % self.perU)
+        return (u // self.perU) * self.per + self.user_local(u % self.perU)
 
     def item_pos(self, i: torch.Tensor) -> torch.Tensor:
-        if self.world == 1:
+        """position of item ids (monotonic in i)"""
+        if self.world == 1 and self.panels == 1:
             return i + self.num_users
-        return (i // self.perI) * self.per + self.perU + (i % self.perI)
+        return (i // self.perI) * self.per + self.item_local(i % self.perI)
 
     def node_pos(self, n: torch.Tensor) -> torch.Tensor:
         """reference node ids ([users ; items], models/ngcf.py:33-35) -> positions"""
@@ -111,16 +135,16 @@ class ShardLayout:
         """rows of a [num_users + num_items, d] table (reference node order) owned by `rank`, padded to `per` rows"""
         (u0, u1), (i0, i1) = self.user_block(rank), self.item_block(rank)
         out = torch.zeros(self.per, table.shape[1], dtype=table.dtype, device=table.device)
-        out[: u1 - u0] = table[u0:u1]
-        out[self.perU: self.perU + (i1 - i0)] = table[self.num_users + i0: self.num_users + i1]
+        dev = table.device
+        out[self.user_local(torch.arange(u1 - u0, device=dev))] = table[u0:u1]
+        out[self.item_local(torch.arange(i1 - i0, device=dev))] = table[self.num_users + i0: self.num_users + i1]
         return out
 
     def to_node_order(self, gathered: torch.Tensor) -> torch.Tensor:
         """[world * per, d] gathered blocks -> [num_users + num_items, d] in the reference's node order"""
-        g = gathered.view(self.world, self.per, -1)
-        users = g[:, : self.perU].reshape(self.world * self.perU, -1)[: self.num_users]
-        items = g[:, self.perU:].reshape(self.world * self.perI, -1)[: self.num_items]
-        return torch.cat([users, items])
+        dev = gathered.device
+        return torch.cat([gathered[self.user_pos(torch.arange(self.num_users, device=dev))],
+                          gathered[self.item_pos(torch.arange(self.num_items, device=dev))]])
 
 
 def _values(lib, rowptr, row_node, col, deg_pos, dev) -> torch.Tensor:
@@ -159,16 +183,27 @@ def shard_laplacian(g: ScaledGraph, layout: ShardLayout, rank: int):
     del owner_user, perm, it_local
     icnt = torch.bincount(it_sorted, minlength=i1 - i0).to(I64)
     del it_sorted
-    # ---- rowptr of [users ; padding ; items ; padding]
+    # ---- rowptr in LOCAL row order (panel by panel: a slice of the users, then a slice of the items, then padding)
+    lrow_u = layout.user_local(torch.arange(u1 - u0, device=dev))
+    lrow_i = layout.item_local(torch.arange(i1 - i0, device=dev))
     cnt = torch.zeros(layout.per, dtype=I64, device=dev)
-    cnt[: u1 - u0] = ucnt
-    cnt[layout.perU: layout.perU + (i1 - i0)] = icnt
+    cnt[lrow_u] = ucnt
+    cnt[lrow_i] = icnt
     rowptr = torch.zeros(layout.per + 1, dtype=I64, device=dev)
     rowptr[1:] = torch.cumsum(cnt, 0)
     if int(rowptr[-1].item()) >= 2 ** 31:
         raise ValueError("row block with more than 2^31 non-zeros")
+    if layout.panels == 1:
+        col = torch.cat([ucol, icol])                    # [users ; items] is already the local order
+    else:
+        # every entry moves to (start of its row in the local order) + (its rank inside the row)
+        col = torch.empty(int(rowptr[-1].item()), dtype=I32, device=dev)
+        for cols_, cnts_, lrow_ in ((ucol, ucnt, lrow_u), (icol, icnt, lrow_i)):
+            start_src = torch.cumsum(cnts_, 0) - cnts_                                   # first entry of every source row
+            shift = rowptr[lrow_] - start_src                                            # dest - src, constant inside a row
+            col[torch.arange(cols_.numel(), device=dev) + torch.repeat_interleave(shift, cnts_)] = cols_
+        del ucol, icol
     rowptr = rowptr.to(I32)
-    col = torch.cat([ucol, icol])
     row_node = torch.arange(rank * layout.per, (rank + 1) * layout.per, dtype=I32, device=dev)
     val = _values(lib, rowptr, row_node, col, deg_pos, dev)
     return rowptr, col, val

@@ -126,7 +126,8 @@ class ShardedNGCFTrainer:
         if self.width not in (32, 64, 128, 256, 512, 1024):
             raise NotImplementedError(f"concatenated width {self.width} not in (32, 64, 128, 256, 512, 1024)")
         self.optimizer = FusedOptimizer(cfg.optimizer, cfg.lr, cfg.weight_decay)
-        self.layout = ShardLayout(self.nU, self.nI, self.world)
+        P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", int(os.environ.get("YR_SHARD_PANELS", "8")) if self.world > 1 else 1))
+        self.layout = ShardLayout(self.nU, self.nI, self.world, max(1, P))
         self.per = self.layout.per
         self.lo, self.hi = self.rank * self.per, (self.rank + 1) * self.per          # positions of the local rows
         self.total = self.world * self.per
@@ -139,9 +140,7 @@ class ShardedNGCFTrainer:
             rp, ci, va = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev)
             rpT, ciT, vaT = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev, transpose=True)
         self.nnz_local = int(ci.numel())
-        P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", int(os.environ.get("YR_SHARD_PANELS", "8")) if self.world > 1 else 1))
-        P = max(1, min(P, self.per))
-        step = ((self.per + P - 1) // P + 127) // 128 * 128          # whole 128-row tiles of the dense kernels
+        step = self.layout.pp                                        # a panel = a slice of the users + a slice of the items
         rp_h = rp.cpu()
         self.panels = [(a, min(a + step, self.per), self.k.make_csr(rp_h[a: min(a + step, self.per) + 1], ci, va))
                        for a in range(0, self.per, step)]
@@ -151,7 +150,7 @@ class ShardedNGCFTrainer:
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
         self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "p2p")
         self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode != "allgather"
-                               and int(os.environ.get("YR_SHARD_COLPANELS", "0")) != 0)
+                               and int(os.environ.get("YR_SHARD_COLPANELS", "1")) != 0)
         self.colA = self.colAT = None
         if self.use_col_panels:
             self.colAT = self._column_panels(rpT, ciT, vaT, step)
