@@ -3,7 +3,7 @@
 set -u
 O=gpurun_out
 mkdir -p $O
-for CP in 1 0; do
+for CP in 1 0; do export YR_C5_SKIP_MF=1
 YR_SHARD_COLPANELS=$CP timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2964$CP bench.py --gpus 8 --only-c5 > $O/r02_c5_n8_cp$CP.json 2> $O/r02_c5_n8_cp$CP.err; echo "bench rc=$?"
 python - <<P2
 import json

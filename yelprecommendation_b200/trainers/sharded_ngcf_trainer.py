@@ -22,8 +22,8 @@ One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:10
 Where the whole operand is exchanged right before it is consumed — layer 0 (it follows the optimizer step) and every
 backward layer (T) — the SpMM is cut by COLUMN panel instead: the entries whose column is a row of panel p on some rank; the
 SpMM over column panel p needs only exchange round p and runs underneath round p+1. Only one round (1 / P of N * d * 4
-bytes) per layer stays exposed. Measured on 8 x B200 (profiles/README.md): no gain (133.5 vs 131.0 ms per step — eight SpMMs
-over short row fragments cost what the overlap saves), so it is off by default: YR_SHARD_COLPANELS=1 enables it. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
+bytes) per layer stays exposed. It needs panels that each hold users AND items (YR_SHARD_INTERLEAVE=1, data/scaled.py); measured
+on 8 x B200 the pair gains nothing over row panels alone (133.7 vs 131.0 ms per step), so both are off by default. The graph arrives either as the reference's torch sparse COO Laplacian (row blocks
 cut on the device, any weights) or as a data.scaled.ScaledGraph (config 5: generated and normalised on the device).
 No CPU product path: `device` / `kernels` exist so that tests/_dist_shard_worker.py can drive the choreography under gloo
 with a CPU restatement of the kernels.
@@ -127,7 +127,12 @@ class ShardedNGCFTrainer:
             raise NotImplementedError(f"concatenated width {self.width} not in (32, 64, 128, 256, 512, 1024)")
         self.optimizer = FusedOptimizer(cfg.optimizer, cfg.lr, cfg.weight_decay)
         P = int(n_panels if n_panels is not None else getattr(cfg, "shard_panels", int(os.environ.get("YR_SHARD_PANELS", "8")) if self.world > 1 else 1))
-        self.layout = ShardLayout(self.nU, self.nI, self.world, max(1, P))
+        # YR_SHARD_INTERLEAVE=1: every row panel holds a slice of the users and a slice of the items (what the column-panel
+        # schedule needs to be balanced). Measured on 8 x B200 (profiles/README.md): the mixed panels cost the SpMM 15 % (the
+        # user-vector gathers evict the hot item vectors from L2) and the column panels win back about as much — 133.7 ms per
+        # step against 131.0 ms for the plain [users ; items] order with row panels only, which therefore stays the default.
+        interleave = int(os.environ.get("YR_SHARD_INTERLEAVE", "0")) != 0 and P > 1
+        self.layout = ShardLayout(self.nU, self.nI, self.world, max(1, P) if interleave else 1)
         self.per = self.layout.per
         self.lo, self.hi = self.rank * self.per, (self.rank + 1) * self.per          # positions of the local rows
         self.total = self.world * self.per
@@ -140,7 +145,11 @@ class ShardedNGCFTrainer:
             rp, ci, va = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev)
             rpT, ciT, vaT = shard_laplacian_from_coo(laplacian_matrix, self.layout, self.rank, dev, transpose=True)
         self.nnz_local = int(ci.numel())
-        step = self.layout.pp                                        # a panel = a slice of the users + a slice of the items
+        if interleave:
+            step = self.layout.pp                                    # a panel = a slice of the users + a slice of the items
+        else:
+            P = max(1, min(P, self.per))
+            step = ((self.per + P - 1) // P + 127) // 128 * 128      # whole 128-row tiles of the dense kernels
         rp_h = rp.cpu()
         self.panels = [(a, min(a + step, self.per), self.k.make_csr(rp_h[a: min(a + step, self.per) + 1], ci, va))
                        for a in range(0, self.per, step)]
@@ -150,7 +159,7 @@ class ShardedNGCFTrainer:
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
         self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "p2p")
         self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode != "allgather"
-                               and int(os.environ.get("YR_SHARD_COLPANELS", "1")) != 0)
+                               and int(os.environ.get("YR_SHARD_COLPANELS", "1" if interleave else "0")) != 0)
         self.colA = self.colAT = None
         if self.use_col_panels:
             self.colAT = self._column_panels(rpT, ciT, vaT, step)
