@@ -390,8 +390,9 @@ def test_other_layer_counts_vs_port(layers):
 
 @pytest.mark.parametrize("d", [32, 128])
 def test_other_embedding_widths_layer_fwd_bwd_vs_oracle(d):
-    """embed_size 32 / 128: FP32-pipe dense transforms (the tensor-core kernels are d = 64 only). Forward bit-exact
-    against the C oracle (same fma chain), backward at 1e-5."""
+    """embed_size 32 / 128. FP32-pipe dense transforms (dense_mode 0; the only mode at d = 32): forward bit-exact against
+    the C oracle (same fma chain), backward at 1e-5. d = 128 also runs the tcgen05 kernels (default mode: forward < 2e-6;
+    dense_mode 2: backward on tensor cores at 1e-5)."""
     from yelprecommendation_b200 import ops
     from yelprecommendation_b200.data import synthetic as syn
     from yelprecommendation_b200.data.graph import build_laplacian, coo_to_csr, laplacian_to_csr
@@ -409,15 +410,20 @@ def test_other_embedding_widths_layer_fwd_bwd_vs_oracle(d):
     Gn = rng.standard_normal((n, d)).astype(np.float32)
     G0 = rng.standard_normal((n, d)).astype(np.float32)
     cu = lambda a: torch.from_numpy(a).cuda()
-    En, LE = ops.ngcf_layer_fwd(dcsr, cu(E0), cu(W1), cu(W2))
+    En, LE = ops.ngcf_layer_fwd(dcsr, cu(E0), cu(W1), cu(W2), dense_mode=0)
     Eo, LEo = cport.ngcf_layer_fwd(csr, E0, W1, W2)
     assert np.array_equal(LE.cpu().numpy(), LEo)
     assert np.array_equal(En.cpu().numpy(), Eo)
-    G = cu(G0.copy())
-    dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(E0), LE, En, cu(Gn), cu(W1), cu(W2), G)
     Go, dW1o, dW2o = cport.ngcf_layer_bwd(csrT, E0, LEo, Eo, Gn, W1, W2, G0)
-    assert rel_fro(G.cpu().numpy(), Go) < RTOL
-    assert rel_fro(dW1.cpu().numpy(), dW1o) < RTOL and rel_fro(dW2.cpu().numpy(), dW2o) < RTOL
+    for mode in ((0, 1, 2) if d == 128 else (0,)):
+        if mode:
+            En_tc, LE_tc = ops.ngcf_layer_fwd(dcsr, cu(E0), cu(W1), cu(W2), dense_mode=mode)
+            assert np.array_equal(LE_tc.cpu().numpy(), LEo)
+            assert rel_err(En_tc.cpu().numpy(), Eo) < 2e-6
+        G = cu(G0.copy())
+        dW1, dW2 = ops.ngcf_layer_bwd(dcsr, cu(E0), LE, En, cu(Gn), cu(W1), cu(W2), G, dense_mode=mode)
+        assert rel_fro(G.cpu().numpy(), Go) < RTOL, mode
+        assert rel_fro(dW1.cpu().numpy(), dW1o) < RTOL and rel_fro(dW2.cpu().numpy(), dW2o) < RTOL, mode
 
 
 @pytest.mark.parametrize("d,layers,name,lr", [(32, 3, "sgd", 0.05), (32, 2, "adam", 1e-3), (128, 1, "sgd", 0.05),

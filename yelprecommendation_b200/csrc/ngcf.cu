@@ -500,8 +500,8 @@ extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* 
   if (!E || !LE || !W1 || !W2 || !E_next || n < 0 || !mode_ok(dense_mode)) return YR_ERR_BAD_ARG;
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (n == 0) return YR_OK;
-  if (fwd_tc(dense_mode) && d == 64)      // tcgen05 3xTF32 (ngcf_tc.cu); other widths run on the FP32 pipe
-    return yr_ngcf_dense_fwd_tc_launch(E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
+  if (fwd_tc(dense_mode) && (d == 64 || d == 128))      // tcgen05 3xTF32 (ngcf_tc.cu); d = 32 runs on the FP32 pipe
+    return yr_ngcf_dense_fwd_tc_launch_d(d, E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
   switch (d) {
     case 32: return dense_fwd_fp32_launch<32>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
     case 64: return dense_fwd_fp32_launch<64>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
@@ -529,8 +529,8 @@ static int dense_bwd_launch(int d, int64_t n, const float* E, const float* LE, c
   if (!E || !LE || !E_next || !G_next || !W1 || !W2 || !G || !T || !ws || n <= 0 || !mode_ok(dense_mode)) return YR_ERR_BAD_ARG;
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
-  if (bwd_tc(dense_mode) && d == 64)                       // tcgen05 3xTF32 (ngcf_tc_bwd.cu)
-    return yr_ngcf_dense_bwd_tc_launch(E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
+  if (bwd_tc(dense_mode) && (d == 64 || d == 128))          // tcgen05 3xTF32 (ngcf_tc_bwd.cu); d = 32 runs on the FP32 pipe
+    return yr_ngcf_dense_bwd_tc_launch(d, E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
   switch (d) {
     case 32: return dense_bwd_fp32_launch<32>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
     case 64: return dense_bwd_fp32_launch<64>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
@@ -652,7 +652,7 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
   if (d != 64) return YR_ERR_BAD_DIM;
   if (bwd_tc(st->dense_mode)) {
     int parts = 0;
-    int rc = yr_ngcf_dense_bwd_tc_launch(st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope,
+    int rc = yr_ngcf_dense_bwd_tc_launch(d, st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope,
                                          st->nU + st->nI, st->G[l], st->T, (float*)st->ws, &parts, s, st->row_list,
                                          st->row_count, st->row_list_cap);
     if (rc) return rc;
@@ -887,8 +887,8 @@ static int train_step_body(const yr_ngcf_state* st, const yr_opt* opt, float slo
     if (side) YR_CUDA(cudaStreamWaitEvent(s, side->join, 0));       // row list (and the cleared gradients) ready
     rc = yr_spmm_csr_rows(&st->L, d, st->E[L - 1], st->LE[L - 1], st->row_flag, s);
     if (rc) return rc;
-    rc = yr_ngcf_dense_fwd_tc_launch(st->E[L - 1], st->LE[L - 1], st->W1[L - 1], st->W2[L - 1], slope, n, st->E[L], s,
-                                     st->row_list, st->row_count, 3 * B);
+    rc = yr_ngcf_dense_fwd_tc_launch_d(d, st->E[L - 1], st->LE[L - 1], st->W1[L - 1], st->W2[L - 1], slope, n, st->E[L], s,
+                                       st->row_list, st->row_count, 3 * B);
     if (rc) return rc;
   } else {
     for (int l = prefix_done; l < L; ++l) {

@@ -1,37 +1,37 @@
 // NGCF dense transforms on the 5th-gen tensor cores (sm_100a), backward of one layer on its rows
-// (autograd of reference models/ngcf.py:64-72):
+// (autograd of reference models/ngcf.py:64-72), d = 64 and d = 128:
 //     dZ = G_next * leaky'(E_next)
-//     [dS | dP] = dZ . [W1 | W2]                       GEMM1  (M = 128 rows, N = 128, K = 64)
+//     [dS | dP] = dZ . [W1 | W2]                       GEMM1  (M = 128 rows, K = d)
 //     T = dS + dP * E ;  G += dS + dP * LE             epilogue
-//     [dW1 | dW2]^T = [S | P]^T . dZ                   GEMM2  (M = 128 features, N = 64, K = rows) accumulated in TMEM
+//     [dW1 | dW2]^T = [S | P]^T . dZ                   GEMM2  (M = features, N = d, K = rows), accumulated in TMEM over the
+//                                                              CTA's tiles, one partial per CTA (fixed-order reduce afterwards)
 // Both GEMMs are tcgen05.mma.kind::tf32 with the 3xTF32 split (lo.hi + hi.lo + hi.hi, fp32 accumulation in TMEM).
 //
-// Operand layouts (notes/README.md, verified by notes/mn_test): GEMM1 reads dZ K-major (128B swizzle, as the forward
-// does) and the weights AS STORED ([out][in] row-major = N contiguous) through an MN-major descriptor; GEMM2 reduces
-// over ROWS, so both its operands are the row-major tiles themselves read MN-major (SWIZZLE_128B_BASE32B atoms of
-// 32 columns x 4 rows). dZ is therefore staged twice. Shared memory: W 64 KB + dZ(K) 64 KB + 64-row halves of dZ(MN)
-// 32 KB and [S|P](MN) 64 KB = 224 KB, single-buffered; the halves alternate under the MMAs of the other operands.
+// Operand layouts (notes/README.md, verified by notes/mn_test): GEMM1 reads dZ K-major (128B swizzle) and the weights AS
+// STORED ([out][in] row-major = N contiguous) through an MN-major descriptor; GEMM2 reduces over ROWS, so both its operands
+// are row-major tiles read MN-major (SWIZZLE_128B_BASE32B atoms of 32 columns x 4 rows).
 //
-// Per CTA (persistent over 128-row tiles, one CTA per SM), 416 threads:
-//   warps 0-7 : loaders  — coalesced float4 reads (next tile's G_next / E_next prefetched in registers), dZ, S, P,
-//                          hi/lo split, stores in the two layouts
-//   warps 8-11: epilogue — thread = row = TMEM lane: tcgen05.ld of dS / dP, T and G rows; at the end the dW partial
-//   warp  12  : TMEM allocator + MMA issuer (one elected lane): 24 + 2 x 24 MMAs per tile
-// dW partials: one [2 x 64 x 64] block per CTA, reduced in CTA order by reduce_partials_kernel (deterministic).
+// Round 2: a ring of operand STAGES instead of whole-tile hand-overs. A stage is 1 + XG pairs (hi, lo) of 16 KB blocks,
+// XG = 1 at d = 64 (S and P side by side in one M = N = 128 block), 2 at d = 128:
+//     GEMM1 stage j (K-slab of 32 output features o):  pair 0 = dZ[:, 32 j ..] K-major [128 x 32]
+//                                                      pair 1 + x = W_x[32 j .., :] MN-major [32 x 128], cp.async.bulk from a
+//                                                      pre-split, pre-swizzled workspace (ngcf_split_weights_bwd_kernel)
+//     GEMM2 stage q (32 rows of the tile):             pair 0 = dZ[32 q .., :] MN-major [32 x d]
+//                                                      pair 1 + x = S / P rows MN-major [32 x 128]
+// 12 MMAs per pair 1 + x. d = 64: 3 stages of 64 KB; d = 128: 2 stages of 96 KB. Per tile 2 + 4 (d = 64) or 4 + 4 stages.
+// The epilogue (4 warps, TMEM lane = row) parks 32 columns of dS and dP per warp in shared memory and re-reads them
+// row-contiguous, so that E / LE / G are read and T / G written as whole 128-byte row segments (v1 read them one row per
+// thread: 25 of its 85 us); it runs underneath the tile's GEMM2 MMAs.
 //
-// STATUS (round 1): correct (same parity tests as the FP32-pipe kernel) but NOT the default: 85 us per layer against
-// 75 us for ngcf_dense_bwd_kernel. Measured by disabling parts: with no global traffic the kernel runs in ~35 us; the
-// epilogue's row-per-thread reads of E / LE / G (TMEM lane = row forces that pattern, 128 threads, 12 loads in flight)
-// cost ~25 us, the loaders' exposed latencies ~7 us, the 72 MMAs per tile ~9 us. 13 warps cap the kernel at 128
-// registers per thread (4 warps share one 16 K-register scheduler partition), which is what forbids deeper
-// software pipelining. Selected with yr_ngcf_set_dense_mode(2).
+// Per CTA (persistent over 128-row tiles, one CTA per SM), 416 threads: warps 0-7 loaders (rows asked for in L2 two tiles ahead,
+// one item of global loads in flight per thread), warps 8-11 epilogue, warp 12 TMEM allocator + MMA issuer (one elected lane).
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace yr {
 
 constexpr int kBwdThreads = 416;      // 8 loader warps + 4 epilogue warps + 1 MMA / TMEM warp
 constexpr int kBwdTM = 128;
-constexpr int kBwdD = 64;
 
 // byte offset of element (mn, k) in an MN-major SWIZZLE_128B_BASE32B tile: atoms of 32 mn x 4 k (512 B), atoms
 // lbo apart along MN and sbo apart along K, the four 32-byte chunks of a k-row XOR-ed with k & 3
@@ -48,280 +48,400 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t lbo, ui
   d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
   return d;
 }
+__device__ __forceinline__ void mbar_expect_tx_b(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_b(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(dst)),
+               "l"(src), "r"(bytes), "r"(s2u(bar))
+               : "memory");
+}
 
+template <int D>
+struct BwdTc {
+  static_assert(D == 64 || D == 128, "tensor-core backward: d in {64, 128}");
+  static constexpr int kSlabs = D / 32;                      // K-slabs of GEMM1
+  static constexpr int kXG = D == 128 ? 2 : 1;               // S / P as separate M = N = 128 groups, or one combined group
+  static constexpr int kHalves = D / 64;                     // a 32-row GEMM2 chunk is loaded as this many items
+  static constexpr uint32_t kBlk = 16384;                    // one [128 x 32] / [32 x 128] fp32 block
+  static constexpr uint32_t kPair = 2 * kBlk;                // hi, lo
+  static constexpr uint32_t kStage = (1 + kXG) * kPair;
+  static constexpr int kNst = D == 128 ? 2 : 3;
+  static constexpr uint32_t kRing = kNst * kStage;           // 192 KB
+  static constexpr uint32_t kEpiOff = kRing;                 // 4 epilogue warps x [32 rows x (32 dS + 32 dP)] = 32 KB
+  static constexpr uint32_t kEpiBytes = 4 * 32 * 256;
+  static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
+  static constexpr size_t kSmem = (size_t)kBarOff + 256 + 1024;
+  static constexpr uint32_t kTmemCols = D == 128 ? 512 : 256;
+  static constexpr uint32_t kColG2 = D == 128 ? 256 : 128;   // first TMEM column of the GEMM2 accumulators
+  static constexpr uint32_t kSboW = 2048, kSboSP = 2048, kSboZ = (D / 32) * 512, kLbo = 512;
+  static constexpr int kItems = kSlabs + 4 * kHalves;        // loader items per tile
+  static constexpr size_t kWsplitBytes = (size_t)kSlabs * kXG * kPair;
+};
+
+// [W1 | W2] -> hi / lo MN-major blocks in the order the ring consumes them: block j = rows 32 j .. 32 j + 31 of the weights
+// (K index o), pair x = W_x (d = 128) or one pair with W1 in columns 0..63 and W2 in 64..127 (d = 64)
+template <int D>
+__global__ void __launch_bounds__(256)
+ngcf_split_weights_bwd_kernel(const float* __restrict__ W1, const float* __restrict__ W2, unsigned char* __restrict__ ws) {
+  using C = BwdTc<D>;
+  const int total = 2 * D * (D / 4);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int X = idx / (D * (D / 4)), rem = idx % (D * (D / 4));
+    const int o = rem / (D / 4), c4 = rem % (D / 4), j = o >> 5, k = o & 31;
+    float4 hi, lo;
+    split4(__ldg(reinterpret_cast<const float4*>((X ? W2 : W1) + o * D) + c4), hi, lo);
+    const int pair = C::kXG == 2 ? X : 0;
+    const int mn = C::kXG == 2 ? 4 * c4 : X * D + 4 * c4;
+    unsigned char* blk = ws + (size_t)(j * C::kXG + pair) * C::kPair;
+    const uint32_t off = mn_off(mn, k, C::kLbo, C::kSboW);
+    *reinterpret_cast<float4*>(blk + off) = hi;
+    *reinterpret_cast<float4*>(blk + C::kBlk + off) = lo;
+  }
+}
+
+template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ Enext,
-                         const float* __restrict__ Gnext, const float* __restrict__ W1, const float* __restrict__ W2,
-                         float slope, int64_t n, float* __restrict__ G, float* __restrict__ T, float* __restrict__ ws,
+                         const float* __restrict__ Gnext, const unsigned char* __restrict__ wsplit, float slope, int64_t n,
+                         float* __restrict__ G, float* __restrict__ T, float* __restrict__ ws,
                          const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
-  constexpr int D = kBwdD, TM = kBwdTM;
+  using C = BwdTc<D>;
+  constexpr int TM = kBwdTM, kNst = C::kNst, kXG = C::kXG, kSlabs = C::kSlabs, kHalves = C::kHalves, kItems = C::kItems;
+  constexpr uint32_t kBlk = C::kBlk, kPair = C::kPair, kStage = C::kStage;
   if (row_list) n = *row_count;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
-  unsigned char* Bw[2]  = {smem, smem + 32768};                       // [W1|W2] hi, lo   MN-major (K = o 64, N = i' 128)
-  unsigned char* dZk[2] = {smem + 65536, smem + 98304};               // dZ hi, lo        K-major  (M = r 128, K = o 64)
-  unsigned char* dZm[2] = {smem + 131072, smem + 147456};             // dZ hi, lo        MN-major (K = r 64,  N = o 64)
-  unsigned char* SPm[2] = {smem + 163840, smem + 196608};             // [S|P] hi, lo     MN-major (K = r 64,  M = i' 128)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 229376);
-  uint64_t* g1_full = bars; uint64_t* g1_empty = bars + 1; uint64_t* g2_full = bars + 2; uint64_t* g2_empty = bars + 3;
-  uint64_t* d1_full = bars + 4; uint64_t* d1_empty = bars + 6; uint64_t* d2_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  constexpr uint32_t kLbo = 512, kSboW = 2048, kSboZ = 1024, kSboSP = 2048;
+  unsigned char* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* full = bars; uint64_t* empty = bars + kNst; uint64_t* d1_full = bars + 2 * kNst; uint64_t* d1_empty = d1_full + 1;
+  uint64_t* d2_done = d1_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d1_full + 3);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_tiles = (n + TM - 1) / TM;
+  const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    mbar_init(g1_full, 1); mbar_init(g1_empty, 1); mbar_init(g2_full, 1); mbar_init(g2_empty, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(d1_full + a, 1); mbar_init(d1_empty + a, 128); }
-    mbar_init(d2_done, 1);
+    for (int s = 0; s < kNst; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(d1_full, 1); mbar_init(d1_empty, 128); mbar_init(d2_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);          // D1: 2 stages x 128 columns, D2: 64 columns at 256
-  // weights as stored ([o][i]): row o = K index, column i (W1) / 64 + i (W2) = N index
-  for (int idx = tid; idx < D * (D / 4); idx += kBwdThreads) {
-    const int o = idx / (D / 4), c4 = idx % (D / 4);
-    float4 hi, lo;
-    split4(__ldg(reinterpret_cast<const float4*>(W1 + o * D) + c4), hi, lo);
-    *reinterpret_cast<float4*>(Bw[0] + mn_off(c4 * 4, o, kLbo, kSboW)) = hi;
-    *reinterpret_cast<float4*>(Bw[1] + mn_off(c4 * 4, o, kLbo, kSboW)) = lo;
-    split4(__ldg(reinterpret_cast<const float4*>(W2 + o * D) + c4), hi, lo);
-    *reinterpret_cast<float4*>(Bw[0] + mn_off(D + c4 * 4, o, kLbo, kSboW)) = hi;
-    *reinterpret_cast<float4*>(Bw[1] + mn_off(D + c4 * 4, o, kLbo, kSboW)) = lo;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 12) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // D = f32, A = B = tf32; GEMM1: A K-major, B MN-major, N = 128; GEMM2: both MN-major, N = 64; M = 128
+  // D = f32, A = B = tf32, M = 128; GEMM1: A K-major, B MN-major, N = 128; GEMM2: both MN-major, N = d
   const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+  const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(D >> 3) << 17) |
                           ((uint32_t)(128 >> 4) << 24);
 
   if (warp < 8) {
     // ================= loaders (256 threads) =================
-    // thread t owns float4 #(t + 256 i), i = 0..7, of every 128 x 64 tile: row (t >> 4) + 16 i, columns 4 (t & 15)..+3;
-    // i < 4 is the first 64-row half, i >= 4 the second.
-    const int c4 = tid & 15, rb = tid >> 4;
-    uint32_t ph1 = 0, ph2 = 0;                  // parities of g1_empty / g2_empty waits
-    float4 gn[8], en[8];
-    auto row_of = [&](int64_t tile, int i) -> int64_t {
-      const int64_t q = tile * TM + rb + 16 * i;
-      if (q >= n) return -1;
-      return row_list ? (int64_t)row_list[q] : q;
+    // item i of a tile: i < kSlabs: GEMM1 slab j = i — thread t owns rows (t >> 3) + 32 r, r = 0..3, 16-byte chunk t & 7 of
+    // G_next / E_next; otherwise GEMM2 chunk q (32 rows), half h (d = 128: 16 rows each) — thread t owns two rows and one
+    // 16-byte chunk of the whole row of G_next / E_next / E / LE. Eight float4 per item either way.
+    const int64_t n_items = my_tiles * kItems;
+    uint32_t s = 0, ph = 0;
+    // the five row blocks a tile touches are contiguous (no row list): one thread asks for them in L2 kPfTiles tiles ahead,
+    // so the register loads below and the epilogue's loads see L2 latency instead of HBM latency
+    constexpr int kPfTiles = 2;
+    auto prefetch_tile = [&](int64_t ti) {
+      if (row_list || ti >= my_tiles) return;
+      const int64_t r0 = (blockIdx.x + ti * gridDim.x) * TM;
+      const int64_t rows = (n - r0) < TM ? (n - r0) : TM;
+      const uint32_t bytes = (uint32_t)(rows * D * 4);
+      l2_prefetch_bulk(Gnext + r0 * D, bytes); l2_prefetch_bulk(Enext + r0 * D, bytes);
+      l2_prefetch_bulk(E + r0 * D, bytes); l2_prefetch_bulk(LE + r0 * D, bytes); l2_prefetch_bulk(G + r0 * D, bytes);
     };
-    auto fetch = [&](int64_t tile) {
+    auto issue = [&](int64_t item, float4 (&x)[8]) {
+      const int64_t tile = blockIdx.x + (item / kItems) * gridDim.x;
+      const int it = (int)(item % kItems);
+      if (it < kSlabs) {
+        const int c = tid & 7, rb = tid >> 3;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t r = row_of(tile, i);
-        gn[i] = make_float4(0.f, 0.f, 0.f, 0.f); en[i] = gn[i];
-        if (r >= 0) {
-          gn[i] = __ldg(reinterpret_cast<const float4*>(Gnext + r * D) + c4);
-          en[i] = __ldg(reinterpret_cast<const float4*>(Enext + r * D) + c4);
+        for (int r = 0; r < 4; ++r) {
+          const int64_t q = tile * TM + rb + 32 * r;
+          x[r] = make_float4(0.f, 0.f, 0.f, 0.f); x[4 + r] = x[r];
+          if (q < n) {
+            const int64_t g = (row_list ? (int64_t)__ldg(row_list + q) : q) * (D / 4) + 8 * it + c;
+            x[r] = __ldg(reinterpret_cast<const float4*>(Gnext) + g);
+            x[4 + r] = __ldg(reinterpret_cast<const float4*>(Enext) + g);
+          }
         }
-      }
-    };
-    if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      float4 dz[8];
+      } else {
+        const int u = it - kSlabs, qc = u / kHalves, h = u % kHalves;
+        const int c4 = tid & (D / 4 - 1), r0 = tid / (D / 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dz[i].x = en[i].x > 0.f ? gn[i].x : gn[i].x * slope; dz[i].y = en[i].y > 0.f ? gn[i].y : gn[i].y * slope;
-        dz[i].z = en[i].z > 0.f ? gn[i].z : gn[i].z * slope; dz[i].w = en[i].w > 0.f ? gn[i].w : gn[i].w * slope;
-      }
-      // E / LE of the whole tile: requested now, consumed after the dZ stores and the barrier waits
-      float4 e[8], le[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t r = row_of(tile, i);
-        e[i] = make_float4(0.f, 0.f, 0.f, 0.f); le[i] = e[i];
-        if (r >= 0) {
-          e[i] = __ldg(reinterpret_cast<const float4*>(E + r * D) + c4);
-          le[i] = __ldg(reinterpret_cast<const float4*>(LE + r * D) + c4);
-        }
-      }
-      auto store_half = [&](int h) {               // dZ (MN) and [S|P] (MN) of rows 64 h .. 64 h + 63
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = rb + 16 * i;                // row inside the half
-          float4 hi, lo;
-          split4(dz[4 * h + i], hi, lo);
-          const uint32_t oz = mn_off(c4 * 4, k, kLbo, kSboZ);
-          *reinterpret_cast<float4*>(dZm[0] + oz) = hi;
-          *reinterpret_cast<float4*>(dZm[1] + oz) = lo;
-          const float4 ee = e[4 * h + i], ll = le[4 * h + i];
-          const float4 s = make_float4(ll.x + ee.x, ll.y + ee.y, ll.z + ee.z, ll.w + ee.w);
-          const float4 p = make_float4(ee.x * ll.x, ee.y * ll.y, ee.z * ll.z, ee.w * ll.w);
-          split4(s, hi, lo);
-          const uint32_t os = mn_off(c4 * 4, k, kLbo, kSboSP);
-          *reinterpret_cast<float4*>(SPm[0] + os) = hi;
-          *reinterpret_cast<float4*>(SPm[1] + os) = lo;
-          split4(p, hi, lo);
-          const uint32_t op = mn_off(D + c4 * 4, k, kLbo, kSboSP);
-          *reinterpret_cast<float4*>(SPm[0] + op) = hi;
-          *reinterpret_cast<float4*>(SPm[1] + op) = lo;
-        }
-      };
-      // ---- dZ, K-major, whole tile -> GEMM1
-      mbar_wait(g1_empty, ph1 ^ 1);
-      ph1 ^= 1;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 hi, lo;
-        split4(dz[i], hi, lo);
-        const uint32_t off = sw_off(TM, rb + 16 * i, c4);
-        *reinterpret_cast<float4*>(dZk[0] + off) = hi;
-        *reinterpret_cast<float4*>(dZk[1] + off) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) mbar_arrive(g1_full);
-      // ---- first half of the MN-major operands -> GEMM2
-      mbar_wait(g2_empty, ph2 ^ 1);
-      ph2 ^= 1;
-      store_half(0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) mbar_arrive(g2_full);
-      // ---- second half
-      mbar_wait(g2_empty, ph2 ^ 1);
-      ph2 ^= 1;
-      store_half(1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) mbar_arrive(g2_full);
-      if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
-    }
-  } else if (warp < 12) {
-    // ================= epilogue: thread = row = TMEM lane, 16 columns of dS and of dP per step =================
-    uint32_t acc = 0, aph = 0;
-    const int r = (warp & 3) * 32 + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t q = tile * TM + r;
-      const int64_t row = (q < n) ? (row_list ? (int64_t)row_list[q] : q) : -1;
-      mbar_wait(d1_full + acc, aph);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + lane_base + acc * 128;
-#pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        float ds[16], dp[16];
-        tmem_ld16(trow + c0, ds);
-        tmem_ld16(trow + D + c0, dp);
-        if (row >= 0) {
-          const float4* e4 = reinterpret_cast<const float4*>(E + row * D + c0);
-          const float4* le4 = reinterpret_cast<const float4*>(LE + row * D + c0);
-          float4* g4 = reinterpret_cast<float4*>(G + row * D + c0);
-          float4* t4 = reinterpret_cast<float4*>(T + row * D + c0);
-          float4 ev[4], lv[4], gv[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { ev[c] = __ldg(e4 + c); lv[c] = __ldg(le4 + c); gv[c] = g4[c]; }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float4 t, g = gv[c];
-            t.x = fmaf(dp[4 * c + 0], ev[c].x, ds[4 * c + 0]); t.y = fmaf(dp[4 * c + 1], ev[c].y, ds[4 * c + 1]);
-            t.z = fmaf(dp[4 * c + 2], ev[c].z, ds[4 * c + 2]); t.w = fmaf(dp[4 * c + 3], ev[c].w, ds[4 * c + 3]);
-            g.x += fmaf(dp[4 * c + 0], lv[c].x, ds[4 * c + 0]); g.y += fmaf(dp[4 * c + 1], lv[c].y, ds[4 * c + 1]);
-            g.z += fmaf(dp[4 * c + 2], lv[c].z, ds[4 * c + 2]); g.w += fmaf(dp[4 * c + 3], lv[c].w, ds[4 * c + 3]);
-            t4[c] = t;
-            g4[c] = g;
+        for (int r = 0; r < 2; ++r) {
+          const int64_t q = tile * TM + 32 * qc + 16 * h + r0 + (256 / (D / 4)) * r;
+          x[r] = make_float4(0.f, 0.f, 0.f, 0.f); x[2 + r] = x[r]; x[4 + r] = x[r]; x[6 + r] = x[r];
+          if (q < n) {
+            const int64_t g = (row_list ? (int64_t)__ldg(row_list + q) : q) * (D / 4) + c4;
+            x[r] = __ldg(reinterpret_cast<const float4*>(Gnext) + g);
+            x[2 + r] = __ldg(reinterpret_cast<const float4*>(Enext) + g);
+            x[4 + r] = __ldg(reinterpret_cast<const float4*>(E) + g);
+            x[6 + r] = __ldg(reinterpret_cast<const float4*>(LE) + g);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(d1_empty + acc);
-      if (++acc == 2) { acc = 0; aph ^= 1; }
+    };
+    auto dz_of = [&](const float4& g, const float4& en) {
+      float4 z;
+      z.x = en.x > 0.f ? g.x : g.x * slope; z.y = en.y > 0.f ? g.y : g.y * slope;
+      z.z = en.z > 0.f ? g.z : g.z * slope; z.w = en.w > 0.f ? g.w : g.w * slope;
+      return z;
+    };
+    auto hand_over = [&]() {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // every loader's part of the stage is written
+      if (tid == 0) mbar_arrive(full + s);
+      if (++s == (uint32_t)kNst) { s = 0; ph ^= 1; }
+    };
+    auto process = [&](int64_t item, const float4 (&x)[8]) {
+      const int it = (int)(item % kItems);
+      if (it == 0 && tid == 32) prefetch_tile(item / kItems + kPfTiles);
+      unsigned char* st = ring + (size_t)s * kStage;
+      if (it < kSlabs) {
+        mbar_wait(empty + s, ph ^ 1);                    // the MMAs that read this stage have completed
+        if (tid == 0) {
+          mbar_expect_tx_b(full + s, kXG * kPair);
+          bulk_g2s_b(st + kPair, wsplit + (size_t)it * kXG * kPair, kXG * kPair, full + s);
+        }
+        const int c = tid & 7, rb = tid >> 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float4 hi, lo;
+          split4(dz_of(x[r], x[4 + r]), hi, lo);
+          const uint32_t off = sw_off(TM, rb + 32 * r, c);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + kBlk + off) = lo;
+        }
+        hand_over();
+      } else {
+        const int u = it - kSlabs, h = u % kHalves;
+        if (h == 0) mbar_wait(empty + s, ph ^ 1);
+        const int c4 = tid & (D / 4 - 1), r0 = tid / (D / 4);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int k = 16 * h + r0 + (256 / (D / 4)) * r;          // row inside the 32-row chunk = K index
+          const float4 e = x[4 + r], le = x[6 + r];
+          float4 hi, lo;
+          split4(dz_of(x[r], x[2 + r]), hi, lo);
+          const uint32_t oz = mn_off(4 * c4, k, C::kLbo, C::kSboZ);
+          *reinterpret_cast<float4*>(st + oz) = hi;
+          *reinterpret_cast<float4*>(st + kBlk + oz) = lo;
+          split4(make_float4(le.x + e.x, le.y + e.y, le.z + e.z, le.w + e.w), hi, lo);
+          const uint32_t os = mn_off(4 * c4, k, C::kLbo, C::kSboSP);
+          *reinterpret_cast<float4*>(st + kPair + os) = hi;
+          *reinterpret_cast<float4*>(st + kPair + kBlk + os) = lo;
+          split4(make_float4(e.x * le.x, e.y * le.y, e.z * le.z, e.w * le.w), hi, lo);
+          // P: its own pair (d = 128) or columns 64..127 of the combined block (d = 64)
+          unsigned char* pp = st + (kXG == 2 ? 2 * kPair : kPair);
+          const uint32_t op = kXG == 2 ? os : mn_off(D + 4 * c4, k, C::kLbo, C::kSboSP);
+          *reinterpret_cast<float4*>(pp + op) = hi;
+          *reinterpret_cast<float4*>(pp + kBlk + op) = lo;
+        }
+        if (h == kHalves - 1) hand_over();
+      }
+    };
+    if (tid == 32)
+      for (int ti = 0; ti < kPfTiles; ++ti) prefetch_tile(ti);
+    // one item ahead in registers (the bulk prefetch above has the rows in L2 by then); a third register set spills at the
+    // 128 registers per thread that 13 warps leave (four warps share one 16 K-register scheduler partition)
+    float4 xa[8], xb[8];
+    if (n_items > 0) issue(0, xa);
+    for (int64_t it = 0; it < n_items; it += 2) {
+      if (it + 1 < n_items) issue(it + 1, xb);
+      process(it, xa);
+      if (it + 1 < n_items) {
+        if (it + 2 < n_items) issue(it + 2, xa);
+        process(it + 1, xb);
+      }
     }
-    // ---- dW partial of this CTA: TMEM lane = feature i' (S columns 0..63 -> dW1, P columns -> dW2), column = o
-    float* my = ws + (size_t)blockIdx.x * 2 * D * D + (size_t)(r >> 6) * D * D + (r & 63);
-    if ((int64_t)blockIdx.x < n_tiles) {
+  } else if (warp < 12) {
+    // ================= epilogue: TMEM lane = row; 32 columns of dS and dP at a time through a per-warp transpose =================
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    unsigned char* stg = smem + C::kEpiOff + (size_t)wq * 8192;
+    uint32_t eph = 0;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t q0 = (blockIdx.x + t * gridDim.x) * TM + wq * 32;          // first row of this warp
+      mbar_wait(d1_full, eph);
+      eph ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        {
+          float ds[32], dp[32];
+          tmem_ld32(tmem_base + lane_base + c0, ds);
+          tmem_ld32(tmem_base + lane_base + D + c0, dp);
+          if (c0 == D - 32) {
+            tc_fence_before();
+            mbar_arrive(d1_empty);                          // dS / dP accumulators free for the next tile
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            *reinterpret_cast<float4*>(stg + lane * 256 + ((k ^ (lane & 15)) << 4)) =
+                make_float4(ds[4 * k], ds[4 * k + 1], ds[4 * k + 2], ds[4 * k + 3]);
+            *reinterpret_cast<float4*>(stg + lane * 256 + (((8 + k) ^ (lane & 15)) << 4)) =
+                make_float4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
+          }
+        }
+        __syncwarp();
+        // row-contiguous pass: lane -> row 4 i + (lane >> 3), 16-byte chunk lane & 7; four rows' loads in flight at a time
+        const int k = lane & 7;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 8; i0 += 4) {
+          float4 ev[4], lv[4], gv[4];
+          int64_t g4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 4 * (i0 + i) + (lane >> 3);
+            const int64_t q = q0 + rr;
+            g4[i] = -1;
+            if (q < n) {
+              g4[i] = ((row_list ? (int64_t)__ldg(row_list + q) : q) * D + c0) / 4 + k;
+              ev[i] = __ldg(reinterpret_cast<const float4*>(E) + g4[i]);
+              lv[i] = __ldg(reinterpret_cast<const float4*>(LE) + g4[i]);
+              gv[i] = *(reinterpret_cast<const float4*>(G) + g4[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (g4[i] < 0) continue;
+            const int rr = 4 * (i0 + i) + (lane >> 3);
+            const float4 ds = *reinterpret_cast<const float4*>(stg + rr * 256 + ((k ^ (rr & 15)) << 4));
+            const float4 dp = *reinterpret_cast<const float4*>(stg + rr * 256 + (((8 + k) ^ (rr & 15)) << 4));
+            float4 tt, gg = gv[i];
+            tt.x = fmaf(dp.x, ev[i].x, ds.x); tt.y = fmaf(dp.y, ev[i].y, ds.y);
+            tt.z = fmaf(dp.z, ev[i].z, ds.z); tt.w = fmaf(dp.w, ev[i].w, ds.w);
+            gg.x += fmaf(dp.x, lv[i].x, ds.x); gg.y += fmaf(dp.y, lv[i].y, ds.y);
+            gg.z += fmaf(dp.z, lv[i].z, ds.z); gg.w += fmaf(dp.w, lv[i].w, ds.w);
+            reinterpret_cast<float4*>(T)[g4[i]] = tt;
+            reinterpret_cast<float4*>(G)[g4[i]] = gg;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ---- dW partial of this CTA: TMEM lane = feature (d = 64: S features in lanes 0..63 -> dW1, P features -> dW2;
+    //      d = 128: lanes = features, dW1^T in the first 128 columns, dW2^T in the next), column = o
+    const int r = wq * 32 + lane;
+    if (my_tiles > 0) {
       mbar_wait(d2_done, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + lane_base + 256 + c0, v);
+      for (int x = 0; x < kXG; ++x) {
+        float* my = ws + (size_t)blockIdx.x * 2 * D * D + (kXG == 2 ? (size_t)x * D * D + r : (size_t)(r >> 6) * D * D + (r & 63));
+#pragma unroll 1
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + C::kColG2 + x * 128 + c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) my[(size_t)(c0 + j) * D] = v[j];    // ws[..][o][i]: lanes write consecutive i
+          for (int j = 0; j < 16; ++j) my[(size_t)(c0 + j) * D] = v[j];      // ws[x][o][i]: lanes write consecutive i
+        }
       }
     } else {                                     // a CTA without a tile (short row list) contributes zeros
-      for (int o = 0; o < D; ++o) my[(size_t)o * D] = 0.f;
+      for (int idx = r; idx < 2 * D * D; idx += 128) ws[(size_t)blockIdx.x * 2 * D * D + idx] = 0.f;
     }
   } else if (lane == 0) {
     // ================= MMA issuer =================
-    uint32_t p1 = 0, p2 = 0, acc = 0, aph = 0, first2 = 1;
-    // (A, B) hi/lo index per pass, small terms first
-    const int pa[3] = {1, 0, 0};
-    const int pb[3] = {0, 1, 0};
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t s = 0, ph = 0, first2 = 1;
+    for (int64_t t = 0; t < my_tiles; ++t) {
       // ---- GEMM1: [dS | dP] = dZ . [W1 | W2]
-      mbar_wait(d1_empty + acc, aph ^ 1);
-      mbar_wait(g1_full, p1);
-      p1 ^= 1;
+      mbar_wait(d1_empty, (uint32_t)(t & 1) ^ 1u);
       tc_fence_after();
-      const uint32_t t1 = tmem_base + acc * 128;
-      uint32_t first = 1;
 #pragma unroll 1
-      for (int p = 0; p < 3; ++p) {
-        const uint32_t abase = s2u(dZk[pa[p]]), bbase = s2u(Bw[pb[p]]);
-        for (int sl = 0; sl < 2; ++sl) {
-          const uint64_t ad = sw128_desc(abase + sl * TM * 128);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bd = mn_desc(bbase + (uint32_t)(sl * 8 + ks * 2) * kSboW, kLbo, kSboW);
-            umma_tf32(t1, ad + 2 * ks, bd, idesc1, first ? 0u : 1u);
-            first = 0;
-          }
-        }
-      }
-      umma_commit(g1_empty);
-      umma_commit(d1_full + acc);
-      if (++acc == 2) { acc = 0; aph ^= 1; }
-      // ---- GEMM2: [dW1 | dW2]^T += [S | P]^T . dZ, two 64-row halves
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(g2_full, p2);
-        p2 ^= 1;
+      for (int j = 0; j < kSlabs; ++j) {
+        mbar_wait(full + s, ph);
         tc_fence_after();
-#pragma unroll 1
-        for (int p = 0; p < 3; ++p) {
-          const uint32_t abase = s2u(SPm[pa[p]]), bbase = s2u(dZm[pb[p]]);
+        const uint32_t st = s2u(ring + (size_t)s * kStage);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ad = mn_desc(abase + (uint32_t)(ks * 2) * kSboSP, kLbo, kSboSP);
-            const uint64_t bd = mn_desc(bbase + (uint32_t)(ks * 2) * kSboZ, kLbo, kSboZ);
-            umma_tf32(tmem_base + 256, ad, bd, idesc2, first2 ? 0u : 1u);
-            first2 = 0;
+        for (int x = 0; x < kXG; ++x) {
+          const uint32_t a[2] = {st, st + kBlk}, b[2] = {st + (1 + x) * kPair, st + (1 + x) * kPair + kBlk};
+          const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};           // lo.hi, hi.lo, hi.hi
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            const uint64_t ad = sw128_desc(a[pa[p]]);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bd = mn_desc(b[pb[p]] + (uint32_t)(ks * 2) * C::kSboW, C::kLbo, C::kSboW);
+              umma_tf32(tmem_base + x * 128, ad + 2 * ks, bd, idesc1, (j == 0 && p == 0 && ks == 0) ? 0u : 1u);
+            }
           }
         }
-        umma_commit(g2_empty);
+        umma_commit(empty + s);
+        if (++s == (uint32_t)kNst) { s = 0; ph ^= 1; }
+      }
+      umma_commit(d1_full);
+      // ---- GEMM2: [dW1 | dW2]^T += [S | P]^T . dZ, four 32-row chunks
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t st = s2u(ring + (size_t)s * kStage);
+#pragma unroll
+        for (int x = 0; x < kXG; ++x) {
+          const uint32_t a[2] = {st + (1 + x) * kPair, st + (1 + x) * kPair + kBlk}, b[2] = {st, st + kBlk};
+          const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = mn_desc(a[pa[p]] + (uint32_t)(ks * 2) * C::kSboSP, C::kLbo, C::kSboSP);
+              const uint64_t bd = mn_desc(b[pb[p]] + (uint32_t)(ks * 2) * C::kSboZ, C::kLbo, C::kSboZ);
+              umma_tf32(tmem_base + C::kColG2 + x * 128, ad, bd, idesc2, (first2 && p == 0 && ks == 0) ? 0u : 1u);
+            }
+          }
+        }
+        first2 = 0;
+        umma_commit(empty + s);
+        if (++s == (uint32_t)kNst) { s = 0; ph ^= 1; }
       }
     }
     umma_commit(d2_done);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 512);
+  if (warp == 12) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 }  // namespace yr
 
 using namespace yr;
 
-// internal launcher used by yr_ngcf_dense_bwd (ngcf.cu); returns the number of CTAs (= dW partials) in *n_parts
-int yr_ngcf_dense_bwd_tc_launch(const float* E, const float* LE, const float* En, const float* Gn, const float* W1,
-                                const float* W2, float slope, int64_t n, float* G, float* T, float* ws, int* n_parts,
-                                cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
-  const size_t smem = 229376 + 128 + 1024;
+template <int D>
+static int bwd_tc_launch(const float* E, const float* LE, const float* En, const float* Gn, const float* W1, const float* W2,
+                         float slope, int64_t n, float* G, float* T, float* ws, int* n_parts, cudaStream_t s,
+                         const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
+  using C = BwdTc<D>;
   static yr::AttrOnce attr;
-  { int rc_ = attr.set(ngcf_dense_bwd_tc_kernel, (int)smem); if (rc_) return rc_; }
+  { int rc_ = attr.set(ngcf_dense_bwd_tc_kernel<D>, (int)C::kSmem); if (rc_) return rc_; }
   const int64_t n_tiles = ((row_list ? row_cap : n) + kBwdTM - 1) / kBwdTM;
-  int64_t grid = yr_sm_count();
+  const int64_t sms = yr_sm_count();
+  int64_t grid = sms;
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) grid = 1;
-  ngcf_dense_bwd_tc_kernel<<<(unsigned)grid, kBwdThreads, smem, s>>>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, row_list,
-                                                                     row_count);
+  // the split weights live behind the per-CTA dW partials: yr_ngcf_layer_bwd_ws_bytes() sizes the workspace for two CTAs
+  // per SM (the FP32-pipe kernel), this kernel runs one
+  unsigned char* wsplit = reinterpret_cast<unsigned char*>(ws) + (size_t)sms * 2 * D * D * sizeof(float);
+  ngcf_split_weights_bwd_kernel<D><<<16, 256, 0, s>>>(W1, W2, wsplit);
+  YR_CHECK_LAUNCH();
+  ngcf_dense_bwd_tc_kernel<D><<<(unsigned)grid, kBwdThreads, C::kSmem, s>>>(E, LE, En, Gn, wsplit, slope, n, G, T, ws, row_list,
+                                                                            row_count);
   YR_CHECK_LAUNCH();
   *n_parts = (int)grid;
   return YR_OK;
+}
+
+// internal launcher used by yr_ngcf_dense_bwd / yr_ngcf_train_step (ngcf.cu); returns the number of CTAs (= dW partials) in
+// *n_parts. ws: yr_ngcf_layer_bwd_ws_bytes(d) bytes.
+int yr_ngcf_dense_bwd_tc_launch(int d, const float* E, const float* LE, const float* En, const float* Gn, const float* W1,
+                                const float* W2, float slope, int64_t n, float* G, float* T, float* ws, int* n_parts,
+                                cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
+  if (d == 64) return bwd_tc_launch<64>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap);
+  if (d == 128) return bwd_tc_launch<128>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap);
+  return YR_ERR_BAD_DIM;
 }
