@@ -158,11 +158,12 @@ int yr_spmm_plan_big_h(const int32_t* rowptr_h, int64_t n_rows, int32_t* n_big_h
 int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate, yr_stream stream);
 
 /* Where the per-layer d x d transforms run (`dense_mode` argument / yr_ngcf_state.dense_mode — per call and per
- * trainer state, nothing process-wide): YR_DENSE_TC_FWD (default of the Python mirrors) = forward on tensor cores,
- * tcgen05.mma.kind::tf32 with the 3xTF32 split (within the 1e-5 parity bar), backward on the FP32 pipe;
- * YR_DENSE_FP32 = FP32 pipe for both, one fma chain per output (forward bit-comparable with the oracle);
- * YR_DENSE_TC = tensor cores for the backward too (csrc/ngcf_tc_bwd.cu). The tensor-core kernels are d = 64 only; the
- * transforms accept d in {32, 64, 128} (YR_ERR_BAD_DIM otherwise) and run on the FP32 pipe off d = 64 in every mode. */
+ * trainer state, nothing process-wide): YR_DENSE_TC (default of the Python trainers) = forward and backward on tensor
+ * cores, tcgen05.mma.kind::tf32 with the 3xTF32 split (within the 1e-5 parity bar; csrc/ngcf_tc.cu, csrc/ngcf_tc_bwd.cu);
+ * YR_DENSE_TC_FWD = forward on tensor cores, backward on the FP32 pipe;
+ * YR_DENSE_FP32 = FP32 pipe for both, one fma chain per output (forward bit-comparable with the oracle).
+ * The tensor-core kernels take d = 64 and d = 128; the transforms accept d in {32, 64, 128} (YR_ERR_BAD_DIM otherwise)
+ * and run on the FP32 pipe at d = 32 in every mode. */
 enum yr_dense_mode { YR_DENSE_FP32 = 0, YR_DENSE_TC_FWD = 1, YR_DENSE_TC = 2 };
 
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:

@@ -40,7 +40,7 @@ def main():
         LE = torch.randn(n, d, device=dev, generator=g) * 0.1
         W1 = torch.randn(d, d, device=dev, generator=g) * (1.0 / d ** 0.5)
         W2 = torch.randn(d, d, device=dev, generator=g) * (1.0 / d ** 0.5)
-        check = n <= 200_000
+        check = n <= 2_000_000
         if what in ("fwd", "both"):
             if check:
                 z = ((LE + E).double() @ W1.double().T + (E * LE).double() @ W2.double().T)

@@ -77,7 +77,7 @@ def test_layer_forward_tensor_core_3xtf32():
     from yelprecommendation_b200 import _cabi, ops
     from yelprecommendation_b200.data import synthetic as syn
     from yelprecommendation_b200.data.graph import build_laplacian, laplacian_to_csr
-    assert _cabi.YR_DENSE_TC_FWD == 1            # the default of ops.ngcf_layer_fwd / cfg.ngcf_dense_mode
+    assert _cabi.YR_DENSE_TC_FWD == 1            # the default of ops.ngcf_layer_fwd (cfg.ngcf_dense_mode defaults to 2)
     g, nU, nI, L, csr, csrT, E0, W1, W2 = _golden()
     dcsr = laplacian_to_csr(L, "cuda")
     E, Ec = torch.from_numpy(E0).cuda(), E0
@@ -109,11 +109,13 @@ def test_layer_backward_vs_oracle_and_autograd_golden(dense_mode):
 
 
 def test_train_steps_with_tensor_core_backward():
-    """Whole train steps (row-sparse last layer included) with the tcgen05 backward (cfg.ngcf_dense_mode = 2) vs the
-    reference golden; a second trainer built afterwards with the default config is unaffected (the mode is per trainer)."""
-    test_train_steps_vs_reference_golden(1, ngcf_dense_mode=2)
+    """Whole train steps (row-sparse last layer included) with the FP32-pipe backward (cfg.ngcf_dense_mode = 1) and with
+    FP32-pipe transforms throughout (0) vs the reference golden — the default is 2, tensor cores for both; a second trainer
+    built afterwards with the default config is unaffected (the mode is per trainer)."""
+    test_train_steps_vs_reference_golden(1, ngcf_dense_mode=1)
+    test_train_steps_vs_reference_golden(1, ngcf_dense_mode=0)
     g, nU, nI, L, *_ = _golden()
-    assert _trainer(g, nU, nI, L)._state()[0].dense_mode == 1
+    assert _trainer(g, nU, nI, L)._state()[0].dense_mode == 2
 
 
 def _layer_backward_case(ops, laplacian_to_csr, dense_mode=1):

@@ -301,7 +301,7 @@ ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     // the tile's 128 rows of E and of LE are contiguous: one thread asks for them in L2 kPfTiles tiles ahead (bulk prefetch),
     // so the register loads below see L2 latency instead of HBM latency (two slabs in flight per thread is all the
     // register file allows: measured 2.7 TB/s of reads without the prefetch against 4.3 TB/s for the bare load stream)
-    constexpr int kPfTiles = 3;
+    const int kPfTiles = (dbg >> 8) & 7;
     auto prefetch_tile = [&](int64_t ti) {
       if (row_list || ti >= my_tiles) return;
       const int64_t r0 = (blockIdx.x + ti * gridDim.x) * kFwdTM;
@@ -352,7 +352,7 @@ ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     };
     auto process = [&](int64_t item, const float4 (&e)[4], const float4 (&le)[4]) {
       const int j = (int)(item % kSlabs);
-      if (j == 0 && tid == 32) prefetch_tile(item / kSlabs + kPfTiles);
+      if (j == 0 && tid == 32 && kPfTiles) prefetch_tile(item / kSlabs + kPfTiles);
       produce(j, 0, e, le);
       produce(j, 1, e, le);
     };
@@ -512,7 +512,7 @@ static int fwd_tc_launch(const float* E, const float* LE, const float* W1, const
     YR_CUDA(cudaMallocAsync((void**)&ws, C::kWsBytes, s));
     ngcf_split_weights_kernel<D><<<16, 256, 0, s>>>(W1, W2, ws);
   }
-  const int dbg = getenv("YR_FWD_DBG") ? atoi(getenv("YR_FWD_DBG")) : 0;
+  const int dbg = getenv("YR_FWD_DBG") ? atoi(getenv("YR_FWD_DBG")) : (1 << 8);
   ngcf_dense_fwd_tc_kernel<D><<<(unsigned)grid, kFwdThreads, C::kSmem, s>>>(E, LE, W1, W2, ws, slope, n, Eout, row_list,
                                                                             row_count, dbg);
   cudaError_t e = cudaGetLastError();

@@ -32,6 +32,7 @@ namespace yr {
 
 constexpr int kBwdThreads = 416;      // 8 loader warps + 4 epilogue warps + 1 MMA / TMEM warp
 constexpr int kBwdTM = 128;
+constexpr int kFlushTiles = 4;        // dW leaves TMEM every this many tiles (192 accumulation steps)
 
 // byte offset of element (mn, k) in an MN-major SWIZZLE_128B_BASE32B tile: atoms of 32 mn x 4 k (512 B), atoms
 // lbo apart along MN and sbo apart along K, the four 32-byte chunks of a k-row XOR-ed with k & 3
@@ -72,8 +73,12 @@ struct BwdTc {
   static constexpr uint32_t kEpiBytes = 4 * 32 * 256;
   static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
   static constexpr size_t kSmem = (size_t)kBarOff + 256 + 1024;
-  static constexpr uint32_t kTmemCols = D == 128 ? 512 : 256;
-  static constexpr uint32_t kColG2 = D == 128 ? 256 : 128;   // first TMEM column of the GEMM2 accumulators
+  // TMEM: GEMM1 accumulators [dS | dP] (2 x 128 columns at d = 128, 128 columns at d = 64, where there is room for a
+  // second stage so that the epilogue of tile t overlaps GEMM1 of tile t + 1), then the GEMM2 accumulators
+  static constexpr int kAcc = D == 128 ? 1 : 2;
+  static constexpr uint32_t kAccCols = D == 128 ? 256 : 128;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColG2 = 256;                    // first TMEM column of the GEMM2 accumulators
   static constexpr uint32_t kSboW = 2048, kSboSP = 2048, kSboZ = (D / 32) * 512, kLbo = 512;
   static constexpr int kItems = kSlabs + 4 * kHalves;        // loader items per tile
   static constexpr size_t kWsplitBytes = (size_t)kSlabs * kXG * kPair;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ Enext,
                          const float* __restrict__ Gnext, const unsigned char* __restrict__ wsplit, float slope, int64_t n,
                          float* __restrict__ G, float* __restrict__ T, float* __restrict__ ws,
-                         const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+                         const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count, int dbg) {
   using C = BwdTc<D>;
   constexpr int TM = kBwdTM, kNst = C::kNst, kXG = C::kXG, kSlabs = C::kSlabs, kHalves = C::kHalves, kItems = C::kItems;
   constexpr uint32_t kBlk = C::kBlk, kPair = C::kPair, kStage = C::kStage;
@@ -114,9 +119,10 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
   unsigned char* smem = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
   unsigned char* ring = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
-  uint64_t* full = bars; uint64_t* empty = bars + kNst; uint64_t* d1_full = bars + 2 * kNst; uint64_t* d1_empty = d1_full + 1;
-  uint64_t* d2_done = d1_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d1_full + 3);
+  uint64_t* full = bars; uint64_t* empty = bars + kNst; uint64_t* d1_full = bars + 2 * kNst; uint64_t* d1_empty = d1_full + 2;
+  uint64_t* d2_full = d1_full + 4; uint64_t* d2_empty = d1_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d1_full + 6);
+  constexpr int kAcc = C::kAcc;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_tiles = (n + TM - 1) / TM;
@@ -124,7 +130,8 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
 
   if (tid == 0) {
     for (int s = 0; s < kNst; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(d1_full, 1); mbar_init(d1_empty, 128); mbar_init(d2_done, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(d1_full + a, 1); mbar_init(d1_empty + a, 128); }
+    mbar_init(d2_full, 1); mbar_init(d2_empty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -146,14 +153,14 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     uint32_t s = 0, ph = 0;
     // the five row blocks a tile touches are contiguous (no row list): one thread asks for them in L2 kPfTiles tiles ahead,
     // so the register loads below and the epilogue's loads see L2 latency instead of HBM latency
-    constexpr int kPfTiles = 2;
-    auto prefetch_tile = [&](int64_t ti) {
+    const int kPfTiles = dbg & 7, pf_mode = (dbg >> 4) & 3;
+    auto prefetch_tile = [&](int64_t ti, int which) {      // which: 1 = G_next / E_next, 2 = E / LE / G, 3 = all five
       if (row_list || ti >= my_tiles) return;
       const int64_t r0 = (blockIdx.x + ti * gridDim.x) * TM;
       const int64_t rows = (n - r0) < TM ? (n - r0) : TM;
       const uint32_t bytes = (uint32_t)(rows * D * 4);
-      l2_prefetch_bulk(Gnext + r0 * D, bytes); l2_prefetch_bulk(Enext + r0 * D, bytes);
-      l2_prefetch_bulk(E + r0 * D, bytes); l2_prefetch_bulk(LE + r0 * D, bytes); l2_prefetch_bulk(G + r0 * D, bytes);
+      if (which & 1) { l2_prefetch_bulk(Gnext + r0 * D, bytes); l2_prefetch_bulk(Enext + r0 * D, bytes); }
+      if (which & 2) { l2_prefetch_bulk(E + r0 * D, bytes); l2_prefetch_bulk(LE + r0 * D, bytes); l2_prefetch_bulk(G + r0 * D, bytes); }
     };
     auto issue = [&](int64_t item, float4 (&x)[8]) {
       const int64_t tile = blockIdx.x + (item / kItems) * gridDim.x;
@@ -201,7 +208,10 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     };
     auto process = [&](int64_t item, const float4 (&x)[8]) {
       const int it = (int)(item % kItems);
-      if (it == 0 && tid == 32) prefetch_tile(item / kItems + kPfTiles);
+      if (it == 0 && tid == 32 && kPfTiles) {
+        if (pf_mode == 0) prefetch_tile(item / kItems + kPfTiles, 3);
+        else { prefetch_tile(item / kItems + kPfTiles, 1); prefetch_tile(item / kItems + kPfTiles - 1, 2); }
+      }
       unsigned char* st = ring + (size_t)s * kStage;
       if (it < kSlabs) {
         mbar_wait(empty + s, ph ^ 1);                    // the MMAs that read this stage have completed
@@ -247,7 +257,7 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
       }
     };
     if (tid == 32)
-      for (int ti = 0; ti < kPfTiles; ++ti) prefetch_tile(ti);
+      for (int ti = 0; ti < kPfTiles; ++ti) prefetch_tile(ti, 3);
     // one item ahead in registers (the bulk prefetch above has the rows in L2 by then); a third register set spills at the
     // 128 registers per thread that 13 warps leave (four warps share one 16 K-register scheduler partition)
     float4 xa[8], xb[8];
@@ -265,21 +275,54 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     const int wq = warp & 3;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     unsigned char* stg = smem + C::kEpiOff + (size_t)wq * 8192;
-    uint32_t eph = 0;
+    uint32_t fph = 0;
+    bool flushed = false;
+    const int r = wq * 32 + lane;
+    // dW accumulators -> this CTA's partial block. TMEM lane = feature (d = 64: S features in lanes 0..63 -> dW1, P features
+    // -> dW2; d = 128: lanes = features, dW1^T in the first 128 columns, dW2^T in the next), column = o.
+    auto drain_dw = [&]() {
+#pragma unroll 1
+      for (int x = 0; x < kXG; ++x) {
+        float* my = ws + (size_t)blockIdx.x * 2 * D * D + (kXG == 2 ? (size_t)x * D * D + r : (size_t)(r >> 6) * D * D + (r & 63));
+#pragma unroll 1
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + C::kColG2 + x * 128 + c0, v);
+          if (flushed) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += my[(size_t)(c0 + j) * D];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) my[(size_t)(c0 + j) * D] = v[j];      // ws[x][o][i]: lanes write consecutive i
+        }
+      }
+    };
     for (int64_t t = 0; t < my_tiles; ++t) {
+      if (t > 0 && t % kFlushTiles == 0) {
+        // the tensor core's fp32 accumulation truncates (measured: error ~ 3.5e-8 x accumulation steps), so the dW sums are
+        // taken out of TMEM every kFlushTiles tiles and continued in fp32 round-to-nearest in the CTA's partial block
+        mbar_wait(d2_full, fph);
+        fph ^= 1;
+        tc_fence_after();
+        drain_dw();
+        flushed = true;
+        tc_fence_before();
+        mbar_arrive(d2_empty);
+      }
       const int64_t q0 = (blockIdx.x + t * gridDim.x) * TM + wq * 32;          // first row of this warp
-      mbar_wait(d1_full, eph);
-      eph ^= 1;
+      const int acc = (int)(t % kAcc);
+      const uint32_t tacc = tmem_base + lane_base + acc * C::kAccCols;
+      mbar_wait(d1_full + acc, (uint32_t)(t / kAcc) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         {
           float ds[32], dp[32];
-          tmem_ld32(tmem_base + lane_base + c0, ds);
-          tmem_ld32(tmem_base + lane_base + D + c0, dp);
+          tmem_ld32(tacc + c0, ds);
+          tmem_ld32(tacc + D + c0, dp);
           if (c0 == D - 32) {
             tc_fence_before();
-            mbar_arrive(d1_empty);                          // dS / dP accumulators free for the next tile
+            mbar_arrive(d1_empty + acc);                    // this dS / dP accumulator stage is free again
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -326,32 +369,20 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
         __syncwarp();
       }
     }
-    // ---- dW partial of this CTA: TMEM lane = feature (d = 64: S features in lanes 0..63 -> dW1, P features -> dW2;
-    //      d = 128: lanes = features, dW1^T in the first 128 columns, dW2^T in the next), column = o
-    const int r = wq * 32 + lane;
     if (my_tiles > 0) {
-      mbar_wait(d2_done, 0);
+      mbar_wait(d2_full, fph);
       tc_fence_after();
-#pragma unroll 1
-      for (int x = 0; x < kXG; ++x) {
-        float* my = ws + (size_t)blockIdx.x * 2 * D * D + (kXG == 2 ? (size_t)x * D * D + r : (size_t)(r >> 6) * D * D + (r & 63));
-#pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + lane_base + C::kColG2 + x * 128 + c0, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) my[(size_t)(c0 + j) * D] = v[j];      // ws[x][o][i]: lanes write consecutive i
-        }
-      }
+      drain_dw();
     } else {                                     // a CTA without a tile (short row list) contributes zeros
       for (int idx = r; idx < 2 * D * D; idx += 128) ws[(size_t)blockIdx.x * 2 * D * D + idx] = 0.f;
     }
   } else if (lane == 0) {
     // ================= MMA issuer =================
-    uint32_t s = 0, ph = 0, first2 = 1;
+    uint32_t s = 0, ph = 0, first2 = 1, n_flush = 0;
     for (int64_t t = 0; t < my_tiles; ++t) {
       // ---- GEMM1: [dS | dP] = dZ . [W1 | W2]
-      mbar_wait(d1_empty, (uint32_t)(t & 1) ^ 1u);
+      const int acc = (int)(t % kAcc);
+      mbar_wait(d1_empty + acc, ((uint32_t)(t / kAcc) & 1u) ^ 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < kSlabs; ++j) {
@@ -368,15 +399,21 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t bd = mn_desc(b[pb[p]] + (uint32_t)(ks * 2) * C::kSboW, C::kLbo, C::kSboW);
-              umma_tf32(tmem_base + x * 128, ad + 2 * ks, bd, idesc1, (j == 0 && p == 0 && ks == 0) ? 0u : 1u);
+              umma_tf32(tmem_base + acc * C::kAccCols + x * 128, ad + 2 * ks, bd, idesc1, (j == 0 && p == 0 && ks == 0) ? 0u : 1u);
             }
           }
         }
         umma_commit(empty + s);
         if (++s == (uint32_t)kNst) { s = 0; ph ^= 1; }
       }
-      umma_commit(d1_full);
+      umma_commit(d1_full + acc);
       // ---- GEMM2: [dW1 | dW2]^T += [S | P]^T . dZ, four 32-row chunks
+      if (t > 0 && t % kFlushTiles == 0) {               // the epilogue has taken the previous tiles' sums out of TMEM
+        mbar_wait(d2_empty, n_flush & 1);
+        ++n_flush;
+        tc_fence_after();
+        first2 = 1;
+      }
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         mbar_wait(full + s, ph);
@@ -400,8 +437,8 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
         umma_commit(empty + s);
         if (++s == (uint32_t)kNst) { s = 0; ph ^= 1; }
       }
+      if ((t + 1) % kFlushTiles == 0 || t + 1 == my_tiles) umma_commit(d2_full);
     }
-    umma_commit(d2_done);
   }
   tc_fence_before();
   __syncthreads();
@@ -429,8 +466,9 @@ static int bwd_tc_launch(const float* E, const float* LE, const float* En, const
   unsigned char* wsplit = reinterpret_cast<unsigned char*>(ws) + (size_t)sms * 2 * D * D * sizeof(float);
   ngcf_split_weights_bwd_kernel<D><<<16, 256, 0, s>>>(W1, W2, wsplit);
   YR_CHECK_LAUNCH();
+  const int dbg = getenv("YR_BWD_DBG") ? atoi(getenv("YR_BWD_DBG")) : 0;
   ngcf_dense_bwd_tc_kernel<D><<<(unsigned)grid, kBwdThreads, C::kSmem, s>>>(E, LE, En, Gn, wsplit, slope, n, G, T, ws, row_list,
-                                                                            row_count);
+                                                                            row_count, dbg);
   YR_CHECK_LAUNCH();
   *n_parts = (int)grid;
   return YR_OK;

@@ -23,10 +23,10 @@ class NGCF(BaseModel):
         super().__init__()
         if cfg.embed_size not in (32, 64, 128):
             from .. import _cabi
-            raise _cabi.YelprecError(f"NGCF embed_size {cfg.embed_size}: the propagation kernels take 32, 64 (tensor cores) or 128")
+            raise _cabi.YelprecError(f"NGCF embed_size {cfg.embed_size}: the propagation kernels take 32 (FP32 pipe), 64 or 128 (tensor cores)")
         self.cfg = cfg
         # where the d x d transforms run (yr_dense_mode, include/yelprec_b200.h): per model, nothing process-wide
-        self.dense_mode = int(getattr(cfg, "ngcf_dense_mode", 1))
+        self.dense_mode = int(getattr(cfg, "ngcf_dense_mode", 2))
         if self.dense_mode not in (0, 1, 2):
             raise ValueError(f"ngcf_dense_mode {self.dense_mode} not in (0, 1, 2)")
         self.num_users = num_users

@@ -54,7 +54,7 @@ class CabiNgcfShardKernels:
         self.device = device
         self.lib = _cabi.load()
         self._ws = None
-        self.dense_mode = _cabi.YR_DENSE_TC_FWD
+        self.dense_mode = _cabi.YR_DENSE_TC
 
     def _st(self):
         return _cabi.stream_ptr(self.device)
@@ -121,6 +121,10 @@ class ShardedNGCFTrainer:
         self.rank = dist.get_rank(group) if multi else 0
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.k = kernels if kernels is not None else CabiNgcfShardKernels(self.device)
+        if kernels is None:                     # yr_dense_mode of the d x d transforms (default: tensor cores for both passes)
+            self.k.dense_mode = int(getattr(cfg, "ngcf_dense_mode", _cabi.YR_DENSE_TC))
+            if self.k.dense_mode not in (0, 1, 2):
+                raise ValueError(f"ngcf_dense_mode {self.k.dense_mode} not in (0, 1, 2)")
         self.d, self.n_layers = int(cfg.embed_size), int(cfg.num_orders)
         self.width = (self.n_layers + 1) * self.d
         if self.width not in (32, 64, 128, 256, 512, 1024):
