@@ -253,6 +253,11 @@ def config5_extras(extra, dev, rank, world, barrier, max_over_ranks, pk, args):
     X = tr.X[0] if world > 1 else tr.E[0]
     ms_spmm = timed(lambda i: [tr.k.spmm(Ap, X, tr.LE[0][a:b], False) for a, b, Ap in tr.panels], 2) / 2
     ms_dfw = timed(lambda i: [tr.k.dense_fwd(tr.E[0][a:b], tr.LE[0][a:b], tr.W1[0], tr.W2[0], tr.E[1][a:b]) for a, b, _ in tr.panels], 2) / 2
+    def dense_bwd_all(i):                       # dense backward of one layer over the local rows (T, G += ..., dW partials)
+        for pi, (a, b, _) in enumerate(tr.panels):
+            tr.k.dense_bwd(tr.E[0][a:b], tr.LE[0][a:b], tr.E[1][a:b], tr.G[1][a:b], tr.W1[0], tr.W2[0], tr.G[0][a:b], tr.T[a:b],
+                           tr.dWp[pi, 0], tr.dWp[pi, 1])
+    ms_dbw = timed(dense_bwd_all, 2) / 2
     ms_xchg = None
     if world > 1:
         def xchg(i):
@@ -270,7 +275,8 @@ def config5_extras(extra, dev, rank, world, barrier, max_over_ranks, pk, args):
         "graph_gen_s": t_gen, "shard_build_s": t_build,
         "efficiency_vs_n1": eff("c5_ngcf", val),
         "spmm_ms_per_layer": ms_spmm, "spmm_gather_TBps": gather_bytes / (ms_spmm * 1e-3) / 1e12,
-        "dense_fwd_ms_per_layer": ms_dfw,
+        "dense_fwd_ms_per_layer": ms_dfw, "dense_bwd_ms_per_layer": ms_dbw,
+        "dense_kernels": "tcgen05 3xTF32 ring kernels at d = 128 (csrc/ngcf_tc.cu, csrc/ngcf_tc_bwd.cu), yr_dense_mode 2",
         "exchange_ms_per_layer_alone": ms_xchg,
         "exchange_bytes_per_layer_per_gpu": (world - 1) * tr.per * d5 * 4 if world > 1 else 0,
         "collectives": "none (1 GPU)" if world == 1 else

@@ -366,7 +366,8 @@ int yr_shard_gather_local(const float* T0, const float* T1, int d, const int32_t
 /* Ordered (atomics-free) form of yr_shard_accumulate: the caller has grouped the n received gradient rows by local row with
  * a STABLE sort — rows_sorted[j] = local row (ascending), src[j] = index of that gradient row in G — and one warp per
  * segment sums it left to right (arrival order: requester rank, then slot) into the row's scratch. Bit-identical run to
- * run. list_rows != 0 also lists the rows for a sparse step (plain SGD, sparse Adam). */
+ * run. Entries with rows_sorted[j] < 0 are ignored (gradient rows another shard owns). list_rows != 0 also lists the rows
+ * for a sparse step (plain SGD, sparse Adam). */
 int yr_shard_accumulate_sorted(const yr_shard_state* st, const yr_opt* opt, const int32_t* rows_sorted, const int32_t* src,
                                int64_t n, const float* G, int64_t g_ld, int list_rows, yr_stream stream);
 

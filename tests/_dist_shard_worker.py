@@ -202,6 +202,11 @@ class CpuNgcfShardKernels:
         j = torch.nonzero((ids >= lo) & (ids < hi)).flatten()
         G.index_add_(0, ids[j] - lo, Gr[j, col_off:col_off + d])
 
+    def scatter_rows_sorted(self, G, rows_sorted, src, Gr, col_off, flags, scratch):
+        d = G.shape[1]
+        keep = rows_sorted >= 0
+        G.index_add_(0, rows_sorted[keep].long(), Gr[src[keep].long(), col_off:col_off + d])
+
     def opt_step(self, p, g, m, v, opt):
         _opt_step_cpu(p, g, m, v, opt)
 

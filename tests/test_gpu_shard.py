@@ -72,19 +72,27 @@ def _ngcf_problem(seed=21, nu=1203, ni=958, nnz=30000, d=64, layers=3):
     return inter, L, batches, init
 
 
-@pytest.mark.parametrize("optname,lr,wd,layers,d", [("sgd", 0.05, 0.0, 3, 64), ("adam", 1e-2, 1e-4, 3, 64),
-                                                    ("adamw", 2e-3, 1e-2, 1, 64), ("sgd", 0.05, 0.0, 1, 128),
-                                                    ("adam", 1e-2, 1e-4, 3, 32), ("sgd", 0.05, 0.0, 3, 128),
-                                                    ("adam", 1e-2, 0.0, 3, 128)])
-def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers, d):
+@pytest.mark.parametrize("optname,lr,wd,layers,d,mode", [("sgd", 0.05, 0.0, 3, 64, 2), ("adam", 1e-2, 1e-4, 3, 64, 2),
+                                                         ("adamw", 2e-3, 1e-2, 1, 64, 2), ("sgd", 0.05, 0.0, 1, 128, 2),
+                                                         ("adam", 1e-2, 1e-4, 3, 32, 2), ("sgd", 0.05, 0.0, 3, 128, 2),
+                                                         ("adam", 1e-3, 0.0, 3, 128, 2), ("adam", 1e-3, 0.0, 3, 128, 0),
+                                                         ("adam", 1e-2, 1e-4, 3, 64, 1)])
+def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers, d, mode):
     """Op-by-op sharded path (row panels of the SpMM block + yr_ngcf_dense_fwd/bwd + shard gather/scatter) vs the oracle;
-    d = 128 with 3 layers (concatenated width 512) is BASELINE config 5's model."""
+    d = 128 with 3 layers (concatenated width 512) is BASELINE config 5's model. mode = yr_dense_mode (2 = tensor cores for
+    both passes, the default). The tail sums duplicate rows in batch order without atomics, so a step is reproducible
+    (test_sharded_ngcf_step_reproducible). The d = 128 x 3-layer Adam case runs at lr = 1e-3 (10 x the reference's NGCF
+    learning rate): at lr = 1e-2 without weight decay that model is ill-conditioned — a weight-gradient element near zero
+    changes sign with the last bits and Adam's first step moves the weight by 2 lr; profiles/r02_adam_dense_modes.txt shows
+    round 2's base build itself (FP32 pipe, atomics) flipping between 5e-7 and 2e-5 from run to run on it, and the torch-CPU
+    port of another host selecting the other outcome for the FP32-pipe mode."""
     from oracle.torch_port import NGCFPort
     from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
     inter, L, batches, init = _ngcf_problem(layers=layers, d=d)
-    cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1)
+    cfg = SimpleNamespace(embed_size=d, num_orders=layers, optimizer=optname, lr=lr, weight_decay=wd, seed=1,
+                          ngcf_dense_mode=mode)
     tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init, n_panels=3)
-    assert len(tr.panels) == 3
+    assert len(tr.panels) == 3 and tr.k.dense_mode == mode
     loss = tr.train(batches)
     port = NGCFPort(init["embedding.weight"], [init[f"W1.{l}.weight"] for l in range(layers)],
                     [init[f"W2.{l}.weight"] for l in range(layers)], inter.num_users, L, optname, lr, wd)
@@ -94,6 +102,21 @@ def test_sharded_ngcf_world1_matches_oracle(optname, lr, wd, layers, d):
         assert rel_fro(tr.W1[l].cpu(), port.W1[l].detach()) < 1e-5
         assert rel_fro(tr.W2[l].cpu(), port.W2[l].detach()) < 1e-5
     assert abs(loss - ref_loss) < 1e-5 * abs(ref_loss)
+
+
+def test_sharded_ngcf_step_reproducible():
+    """Two runs of the same sharded NGCF steps give bit-identical embeddings (Adam, d = 64, 3 layers): the tail accumulates
+    in batch order (yr_shard_accumulate_sorted), the SpMM and the dW partials are reduced in fixed order."""
+    from yelprecommendation_b200.trainers.sharded_ngcf_trainer import ShardedNGCFTrainer
+    inter, L, batches, init = _ngcf_problem(layers=3, d=64)
+    cfg = SimpleNamespace(embed_size=64, num_orders=3, optimizer="adam", lr=1e-2, weight_decay=1e-4, seed=1)
+    outs = []
+    for _ in range(2):
+        tr = ShardedNGCFTrainer(cfg, inter.num_items, inter.num_users, L, init=init, n_panels=3)
+        tr.train(batches)
+        outs.append((tr.gather_embedding().clone(), [w.clone() for w in tr.W1]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")

@@ -29,9 +29,6 @@ int yr_eval_exact_launch(const float* Uemb, int64_t nU, const float* Vt, int64_t
 int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, const int32_t* act_nuniq,
                           int64_t n_eval, double* metric_sums, yr_stream stream);
 
-int yr_ngcf_dense_fwd_tc_launch(const float* E, const float* LE, const float* W1, const float* W2, float slope,
-                                int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list = nullptr,
-                                const int32_t* row_count = nullptr, int64_t row_cap = 0);
 int yr_ngcf_dense_fwd_tc_launch_d(int d, const float* E, const float* LE, const float* W1, const float* W2, float slope,
                                   int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list = nullptr,
                                   const int32_t* row_count = nullptr, int64_t row_cap = 0);
@@ -58,33 +55,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// Grid barrier of the persistent (cooperatively launched, hence co-resident) BPR-MF trainer: a monotonic arrival counter.
-// Every CTA adds 1 with a fire-and-forget `red.release.gpu` (no round trip for the arrival), thread 0 polls the counter
-// with relaxed loads (served by L2, no L1 invalidation per poll) until it reaches this barrier's target, then one
-// `fence.acq_rel.gpu` orders the next phase's reads (and drops the SM's stale L1 lines). The target advances by gridDim.x
-// per barrier and never resets, so there is no reset race and no second counter; the value it has reached is persisted
-// by the caller (yr_mf_state.counters[9]) for the next launch. cooperative_groups' grid.sync() cost ~1.5 us per barrier
-// here (MEMBAR.ALL.GPU + atomic with return + acquire polls); two barriers were ~3 of the 4.9 us SGD step.
-// Warps stay converged around the CTA barriers: with warp 0 diverged (lane 0 polling), the other lanes' bar.sync counted
-// the warp as arrived and they ran ahead into the next phase (notes/README.md) — hence the __syncwarp() calls.
-struct GridBarrier {
-  unsigned* count;
-  unsigned target;
-};
-__device__ __forceinline__ void grid_sync(GridBarrier& b) {
+// Grid barrier with the calling warp re-converged on both sides. cooperative_groups' grid sync lets thread 0 of the CTA
+// poll the barrier word between two CTA barriers; when the compiler leaves warp 0 diverged after an `if (threadIdx.x == 0)`
+// block in front of it (seen for the d = 32 instantiation of the BPR-MF trainer on sm_100a), lanes 1..31 of that warp ran
+// into the next phase before the grid barrier had completed and read rows other CTAs were still writing
+// (scripts/probe_mf, notes/README.md). __syncwarp() after the barrier holds them until lane 0 is through.
+__device__ __forceinline__ void grid_sync(cg::grid_group& grid) {
   __syncwarp();
-  __syncthreads();
-  b.target += gridDim.x;
-  if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(b.count) : "memory");
-    unsigned v;
-    do {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b.count) : "memory");
-    } while ((int)(v - b.target) < 0);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  }
+  grid.sync();
   __syncwarp();
-  __syncthreads();
 }
 
 // Per-lane slice of an embedding row of d = 32 * VPL floats. VPL = 1 / 2: lane owns VPL contiguous floats; VPL >= 4: lane

@@ -122,8 +122,7 @@ __global__ void bpr_loss_bwd_kernel(const float* __restrict__ pos, const float* 
 //    (embedding_dense_backward), then the two calls added (AccumulateGrad) — and applies ONE optimizer update.
 //    Bit-identical from run to run, and bit-identical to oracle/yr_oracle.c (which restates the same order).
 //
-// counters layout (int32): [4] = parity of the next step; [8] = grid-barrier arrivals, [9] = their value at the end of
-// the previous launch; the rest is spare. Per-CTA loss partials (double, fixed
+// counters layout (int32): [4] = parity of the next step; the rest is spare. Per-CTA loss partials (double, fixed
 // summation order) live in the workspace.
 // ---------------------------------------------------------------------------------------------
 // 512-thread CTAs (half the CTAs at the grid barrier) up to d = 256; 256 threads beyond, where a thread holds up to
@@ -254,6 +253,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
                     int64_t n_triples, int B, double* loss_sum, float* step_loss, MfWs ws) {
   constexpr int D = VPL * 32;
   constexpr int kTrainWarps = TrainCfg<VPL>::kWarps;
+  cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kTrainWarps + wib;
@@ -262,9 +262,6 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
   const int64_t n_steps = (n_triples + B - 1) / B;
   int32_t* counters = st.counters;
   const int parity0 = __ldcg(counters + 4) & 1;
-  // grid barrier: arrivals in counters[8]; counters[9] = the value they had reached when the previous launch ended (only
-  // written after a launch's last barrier, i.e. after every CTA of that launch has read it)
-  GridBarrier grid{reinterpret_cast<unsigned*>(counters + 8), (unsigned)__ldcg(counters + 9)};
   __shared__ double s_part[kTrainWarps];
 
   // per-CTA loss partial of this step (fixed order inside the CTA), summed after the barrier by warp 0 of block 0 in a
@@ -288,7 +285,7 @@ bpr_mf_train_kernel(yr_mf_state st, yr_opt opt, const int64_t* __restrict__ uid,
         const float mean = (float)(t / (double)nb);           // batch mean, then .item()
         if (step_loss) step_loss[s] = mean;
         if (loss_sum) *loss_sum += (double)mean;              // Q1: sum of batch means
-        if (s + 1 == n_steps) { counters[4] = par ^ 1; counters[9] = (int32_t)grid.target; }
+        if (s + 1 == n_steps) counters[4] = par ^ 1;
       }
     }
   };

@@ -23,8 +23,8 @@
 // row-contiguous, so that E / LE / G are read and T / G written as whole 128-byte row segments (v1 read them one row per
 // thread: 25 of its 85 us); it runs underneath the tile's GEMM2 MMAs.
 //
-// Per CTA (persistent over 128-row tiles, one CTA per SM), 416 threads: warps 0-7 loaders (rows asked for in L2 two tiles ahead,
-// one item of global loads in flight per thread), warps 8-11 epilogue, warp 12 TMEM allocator + MMA issuer (one elected lane).
+// Per CTA (persistent over 128-row tiles, one CTA per SM), 416 threads: warps 0-7 loaders (one item of
+// global loads in flight per thread), warps 8-11 epilogue, warp 12 TMEM allocator + MMA issuer (one elected lane).
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ LE, const float* __restrict__ Enext,
                          const float* __restrict__ Gnext, const unsigned char* __restrict__ wsplit, float slope, int64_t n,
                          float* __restrict__ G, float* __restrict__ T, float* __restrict__ ws,
-                         const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count, int dbg) {
+                         const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
   using C = BwdTc<D>;
   constexpr int TM = kBwdTM, kNst = C::kNst, kXG = C::kXG, kSlabs = C::kSlabs, kHalves = C::kHalves, kItems = C::kItems;
   constexpr uint32_t kBlk = C::kBlk, kPair = C::kPair, kStage = C::kStage;
@@ -151,17 +151,9 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     // 16-byte chunk of the whole row of G_next / E_next / E / LE. Eight float4 per item either way.
     const int64_t n_items = my_tiles * kItems;
     uint32_t s = 0, ph = 0;
-    // the five row blocks a tile touches are contiguous (no row list): one thread asks for them in L2 kPfTiles tiles ahead,
-    // so the register loads below and the epilogue's loads see L2 latency instead of HBM latency
-    const int kPfTiles = dbg & 7, pf_mode = (dbg >> 4) & 3;
-    auto prefetch_tile = [&](int64_t ti, int which) {      // which: 1 = G_next / E_next, 2 = E / LE / G, 3 = all five
-      if (row_list || ti >= my_tiles) return;
-      const int64_t r0 = (blockIdx.x + ti * gridDim.x) * TM;
-      const int64_t rows = (n - r0) < TM ? (n - r0) : TM;
-      const uint32_t bytes = (uint32_t)(rows * D * 4);
-      if (which & 1) { l2_prefetch_bulk(Gnext + r0 * D, bytes); l2_prefetch_bulk(Enext + r0 * D, bytes); }
-      if (which & 2) { l2_prefetch_bulk(E + r0 * D, bytes); l2_prefetch_bulk(LE + r0 * D, bytes); l2_prefetch_bulk(G + r0 * D, bytes); }
-    };
+    // (A tile-ahead bulk L2 prefetch, which pays in the forward kernel, loses here: a tile lasts ~20 us at d = 128 and the
+    // five row blocks of the next tile do not survive that long in L2 — DRAM reads 4.3 -> 8.0 GB, 1.69 -> 1.92 ms at
+    // 1.5 M x 128, profiles/r02_dense_ring.txt.)
     auto issue = [&](int64_t item, float4 (&x)[8]) {
       const int64_t tile = blockIdx.x + (item / kItems) * gridDim.x;
       const int it = (int)(item % kItems);
@@ -208,10 +200,6 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
     };
     auto process = [&](int64_t item, const float4 (&x)[8]) {
       const int it = (int)(item % kItems);
-      if (it == 0 && tid == 32 && kPfTiles) {
-        if (pf_mode == 0) prefetch_tile(item / kItems + kPfTiles, 3);
-        else { prefetch_tile(item / kItems + kPfTiles, 1); prefetch_tile(item / kItems + kPfTiles - 1, 2); }
-      }
       unsigned char* st = ring + (size_t)s * kStage;
       if (it < kSlabs) {
         mbar_wait(empty + s, ph ^ 1);                    // the MMAs that read this stage have completed
@@ -256,9 +244,7 @@ ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ 
         if (h == kHalves - 1) hand_over();
       }
     };
-    if (tid == 32)
-      for (int ti = 0; ti < kPfTiles; ++ti) prefetch_tile(ti, 3);
-    // one item ahead in registers (the bulk prefetch above has the rows in L2 by then); a third register set spills at the
+    // one item ahead in registers; a third register set spills at the
     // 128 registers per thread that 13 warps leave (four warps share one 16 K-register scheduler partition)
     float4 xa[8], xb[8];
     if (n_items > 0) issue(0, xa);
@@ -466,9 +452,8 @@ static int bwd_tc_launch(const float* E, const float* LE, const float* En, const
   unsigned char* wsplit = reinterpret_cast<unsigned char*>(ws) + (size_t)sms * 2 * D * D * sizeof(float);
   ngcf_split_weights_bwd_kernel<D><<<16, 256, 0, s>>>(W1, W2, wsplit);
   YR_CHECK_LAUNCH();
-  const int dbg = getenv("YR_BWD_DBG") ? atoi(getenv("YR_BWD_DBG")) : 0;
   ngcf_dense_bwd_tc_kernel<D><<<(unsigned)grid, kBwdThreads, C::kSmem, s>>>(E, LE, En, Gn, wsplit, slope, n, G, T, ws, row_list,
-                                                                            row_count, dbg);
+                                                                            row_count);
   YR_CHECK_LAUNCH();
   *n_parts = (int)grid;
   return YR_OK;

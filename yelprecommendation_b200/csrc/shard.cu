@@ -162,6 +162,7 @@ shard_accumulate_sorted_kernel(yr_shard_state st, const int32_t* __restrict__ ro
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += nw) {
     const int32_t r = rows_sorted[j];
+    if (r < 0) continue;                                       // not a row of this shard (callers sort those to the front)
     if (j > 0 && rows_sorted[j - 1] == r) continue;            // not a segment head
     Row<VPL> acc = ld_row<VPL>(G + (int64_t)src[j] * g_ld, lane);
     for (int64_t q = j + 1; q < n && rows_sorted[q] == r; ++q) {

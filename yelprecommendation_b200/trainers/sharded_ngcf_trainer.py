@@ -14,7 +14,7 @@ One step (reference semantics: models/ngcf.py:30-72, trainers/ngcf_trainer.py:10
                                                                           issued asynchronously: it runs underneath panel p+1
     tail                 :  owner gather of rows u / pos / neg of every layer -> all_reduce (exact gather),
                             yr_bpr_rows_grad on the concatenated rows (every rank, all B triples: the loss and the row
-                            gradients are replicated, no further collective), yr_shard_accumulate scatters owned rows into G_l
+                            gradients are replicated, no further collective), yr_shard_accumulate_sorted sums owned rows into G_l in batch order (no atomics)
     backward, per layer  :  for panel p:  yr_ngcf_dense_bwd -> T[p], G_l[p] += ..., dW partial;  exchange(T[p]) (async)
                             G_l += L^T[block, :] X_T;   all_reduce(dW1, dW2) once per step
     update               :  yr_dense_opt_step on the local rows of E_0 and (identically on every rank) on the weights
@@ -101,6 +101,18 @@ class CabiNgcfShardKernels:
         opt = _cabi.make_opt("adam", 0.0, 0.0, 1)          # dense flavour: only marks flags, no row list
         _cabi.check(self.lib.yr_shard_accumulate(C.byref(st), C.byref(opt), p(ids, I64), int(ids.numel()),
                                                  Gr.data_ptr() + col_off * 4, Gr.shape[1], self._st()), "yr_shard_accumulate")
+
+    def scatter_rows_sorted(self, G, rows_sorted, src, Gr, col_off, flags, scratch):
+        """Ordered form of scatter_rows on a G that has just been cleared: G[r] = sum, in batch order, of the gradient rows
+        Gr[src[j], col_off : col_off + d] with rows_sorted[j] == r (rows_sorted: stable-sorted local rows, < 0 = not owned).
+        No floating-point atomics: bit-identical run to run."""
+        d = G.shape[1]
+        p = _cabi.dptr
+        st = _cabi.YrShardState(p(G, F32), None, None, p(G, F32), p(flags), p(scratch), p(scratch), 0, G.shape[0], d)
+        opt = _cabi.make_opt("adam", 0.0, 0.0, 1)
+        _cabi.check(self.lib.yr_shard_accumulate_sorted(C.byref(st), C.byref(opt), p(rows_sorted, I32), p(src, I32),
+                                                        int(rows_sorted.numel()), Gr.data_ptr() + col_off * 4, Gr.shape[1], 0,
+                                                        self._st()), "yr_shard_accumulate_sorted")
 
     def opt_step(self, p, g, m, v, opt):
         ops.dense_opt_step(p, g, m, v, opt)
@@ -312,8 +324,13 @@ class ShardedNGCFTrainer:
         k.rows_grad(R, B, W, Gr, loss_acc)
         for g in self.G:
             g.zero_()
+        # owners sum the gradient rows of their table rows in batch order (stable sort of the local row ids: index plumbing,
+        # shared by all layers) — no floating-point atomics, so a step is bit-identical from run to run
+        own = (ids >= self.lo) & (ids < self.hi)
+        rows_sorted, src = torch.sort(torch.where(own, ids - self.lo, torch.full_like(ids, -1)).to(I32), stable=True)
+        src = src.to(I32)
         for l in range(L + 1):
-            k.scatter_rows(self.G[l], self.lo, self.hi, ids, Gr, l * d, self.flags, self.scratch)
+            k.scatter_rows_sorted(self.G[l], rows_sorted, src, Gr, l * d, self.flags, self.scratch)
         # ---- backward through the layers
         for l in reversed(range(L)):
             buf = l & 1
