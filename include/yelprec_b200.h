@@ -141,6 +141,10 @@ typedef struct yr_csr {
   const int32_t* big_split_idx;   /* partials are summed — same left-to-right order — by a follow-up kernel that stages them
                                      through shared memory instead of one warp walking thousands of partials; [n_big_rows]
                                      indices into split_row / split_ptr, from yr_spmm_plan_big_h. 0 / NULL if there are none. */
+  int32_t reserve_sms;            /* 0: the SpMM fills the GPU. R > 0: it runs as (SM count - R) persistent 1,024-thread CTAs,
+                                     one per SM, and leaves R SMs empty — for the NCCL kernels of a panel exchange that is meant
+                                     to run underneath it (kernels that need an empty SM never start behind a grid of small
+                                     CTAs that keeps refilling every SM). Same arithmetic, same results. */
 } yr_csr;
 
 /* Host-side plan builder (host pointers). Call _size_h first, allocate, then _fill_h. */
@@ -165,6 +169,9 @@ int yr_spmm_csr(const yr_csr* A, int d, const float* X, float* Y, int accumulate
  * The tensor-core kernels take d = 64 and d = 128; the transforms accept d in {32, 64, 128} (YR_ERR_BAD_DIM otherwise)
  * and run on the FP32 pipe at d = 32 in every mode. */
 enum yr_dense_mode { YR_DENSE_FP32 = 0, YR_DENSE_TC_FWD = 1, YR_DENSE_TC = 2 };
+/* Bits 8..15 of a `dense_mode` argument: SMs the tensor-core kernels of that call leave empty (see yr_csr.reserve_sms);
+ * 0 = none. YR_DENSE_RESERVE(mode, r) builds the argument. */
+#define YR_DENSE_RESERVE(mode, r) ((mode) | (((r) & 0xff) << 8))
 
 /* NGCF.embedding_propagation (models/ngcf.py:60-72) for one layer on the whole graph:
  *   LE = L E;  E_next = leaky_relu( (LE+E) W1^T + (E * LE) W2^T , slope )
@@ -517,6 +524,27 @@ int yr_topk_masked_row(const float* pred, int64_t nI, const int64_t* mask_idx, i
 int yr_topk_masked_rows(const float* pred, int64_t ld, int64_t n_rows, int64_t nI, const int32_t* mask_ptr,
                         const int32_t* mask_idx, float mask_value, int K, int64_t* topk_out, void* ws, size_t ws_bytes,
                         yr_stream stream);
+
+/* One item slice of an item-sliced evaluation: yr_eval_topk_metrics_tc on items [i0, i0 + nI) of the catalog (Vemb / Vt point
+ * at the slice, mask lists hold slice-local ids) as call `slice` of `n_slices` concurrent calls (one stream each) that share
+ * xchg [n_slices x n_eval] floats (-inf on entry): every call publishes its running lower bound of each row's K-th best score
+ * there and reads the others', so no slice pays the warm-up of a threshold of its own. topk_out / topk_score [n_eval x K]
+ * receive the slice's survivors (slice-local ids, exact scores; lists shorter than K are padded with id -1 / -inf);
+ * user_metrics / metric_sums are not written for n_slices > 1. yr_topk_merge + yr_topk_metrics finish the evaluation. */
+int yr_eval_topk_metrics_tc_slice(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt, int64_t ldt, int64_t nI,
+                                  int d, const int64_t* eval_uid, int64_t n_eval, const int32_t* mask_ptr,
+                                  const int32_t* mask_idx, const int32_t* act_ptr, const int32_t* act_idx,
+                                  const int32_t* act_nuniq, const double* inv_log2, int K, int64_t* topk_out,
+                                  float* topk_score, double* user_metrics, double* metric_sums, void* ws, size_t ws_bytes,
+                                  int32_t* err, int slice, int n_slices, float* xchg, yr_stream stream);
+
+/* Item-sliced evaluation (small row shards: a shard of 31 user tiles cannot fill 148 SMs, so the catalog is cut into S
+ * disjoint item slices that are evaluated by S concurrent yr_eval_topk_metrics_tc_slice calls): merges the
+ * per-slice lists ids / scores [S x n x K] (slice-local ids, exact scores, id -1 = padding) into the K best per row by
+ * (score desc, global id = id + id_offset[slice] asc) — the same lists, in the same order, as the unsliced call
+ * (trainers/mf_trainer.py:163-178 semantics). S * K <= 64. out_scores may be NULL. */
+int yr_topk_merge(const int64_t* ids, const float* scores, int S, int64_t n, int K, const int64_t* id_offset,
+                  int64_t* out_ids, float* out_scores, yr_stream stream);
 
 /* metric.py:7-109 on device for already-computed recommendations: predicted [n x ldp] int64 (first K columns
  * used), actual as CSR in original order. Same outputs as yr_eval_topk_metrics. */

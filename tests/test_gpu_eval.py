@@ -278,3 +278,38 @@ def test_chunked_evaluator_for_non_dot_product_models_like_dcn():
         assert np.array_equal(ev.last_topk.cpu().numpy(), np.stack(predicted)), mode
         want = tp.all_metrics(pos[:n_rows], predicted, K)
         assert np.allclose(got, want, rtol=1e-12), (mode, got, want)
+
+
+@pytest.mark.gpu
+def test_item_sliced_evaluation_is_identical():
+    """A row shard that cannot fill the GPU (here 1/8 of the Yelp-shape users = 31 user tiles on 148 SMs, what a rank of an
+    8-GPU run evaluates) is cut into S item slices evaluated by S concurrent tensor-core launches + yr_topk_merge: same top-K
+    ids in the same order, same exact scores, same per-row metric terms and sums as the unsliced call — MF (d = 64) and the
+    NGCF form (d_eff = 256)."""
+    from yelprecommendation_b200 import ops
+    from yelprecommendation_b200.data import synthetic as syn
+    from yelprecommendation_b200.data.graph import build_eval_csr
+    inter = syn.make_interactions()
+    split = syn.split_per_user(inter, seed=42)
+    uid, pos, mask = syn.eval_lists(split, "valid")
+    lo, hi = 3 * 3959, 4 * 3959
+    csr = build_eval_csr(uid[lo:hi], pos[lo:hi], mask[lo:hi], inter.num_items)
+    U, V = syn.planted_embeddings(inter)
+    rng = np.random.default_rng(2)
+    U4 = np.concatenate([U] + [(U * s_ + 0.05 * rng.standard_normal(U.shape)).astype(np.float32) for s_ in (0.7, 0.4, 0.2)], axis=1)
+    V4 = np.concatenate([V] + [(V * s_ + 0.05 * rng.standard_normal(V.shape)).astype(np.float32) for s_ in (0.7, 0.4, 0.2)], axis=1)
+    dev = torch.device("cuda")
+    assert ops.eval_item_slices(hi - lo, inter.num_items, 10, dev) >= 4          # what the default would pick for this shard
+    for Ue, Ve in ((U, V), (U4, V4)):
+        ecsr = ops.DeviceEvalCSR(csr, dev, 10)
+        Ud, Vd = torch.from_numpy(Ue).to(dev), torch.from_numpy(Ve).to(dev)
+        ref = ops.eval_topk_metrics(Ud, Vd, ecsr, mode="tc", slices=1)
+        assert ops.eval_topk_metrics.last_slices == 1
+        for S in (2, 4, 6):
+            got = ops.eval_topk_metrics(Ud, Vd, ecsr, mode="tc", slices=S)
+            assert ops.eval_topk_metrics.last_slices == S
+            for a, b in zip(ref[:4], got[:4]):
+                assert torch.equal(a, b), S
+            assert int(got[4].item()) == 0
+        auto = ops.eval_topk_metrics(Ud, Vd, ecsr, mode="tc")
+        assert ops.eval_topk_metrics.last_slices >= 4 and torch.equal(auto[0], ref[0]) and torch.equal(auto[3], ref[3])

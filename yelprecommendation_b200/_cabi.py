@@ -24,8 +24,8 @@ SYMBOLS = (
     "yr_ngcf_dense_fwd", "yr_ngcf_dense_bwd",
     "yr_ngcf_tail", "yr_dense_opt_step", "yr_dense_opt_step_multi", "yr_ngcf_propagate", "yr_ngcf_train_step", "yr_ngcf_concat",
     "yr_ngcf_propagate_prefix", "yr_ngcf_train_step_ex",
-    "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_masked_rows", "yr_topk_metrics",
-    "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc",
+    "yr_transpose_items", "yr_eval_ws_bytes", "yr_eval_topk_metrics", "yr_topk_masked_row", "yr_topk_masked_rows", "yr_topk_metrics", "yr_topk_merge",
+    "yr_eval_tc_supported", "yr_eval_tc_ws_bytes", "yr_eval_topk_metrics_tc", "yr_eval_topk_metrics_tc_slice",
     "yr_cdae_ws_bytes", "yr_cdae_hidden", "yr_cdae_hidden_ex", "yr_cdae_output", "yr_cdae_step", "yr_cdae_step_ex", "yr_cdae_step_idx",
     "yr_nsbce_loss",
     "yr_shard_gather_rows", "yr_bpr_rows_grad", "yr_shard_accumulate", "yr_shard_step",
@@ -71,7 +71,7 @@ class YrCsr(C.Structure):
                 ("n_split_rows", C.c_int32),
                 ("split_row", C.c_void_p), ("split_ptr", C.c_void_p), ("partials", C.c_void_p),
                 ("split_count", C.c_void_p),
-                ("n_big_rows", C.c_int32), ("big_split_idx", C.c_void_p)]
+                ("n_big_rows", C.c_int32), ("big_split_idx", C.c_void_p), ("reserve_sms", C.c_int32)]
 
 
 class YrShardState(C.Structure):
@@ -155,6 +155,7 @@ def load() -> C.CDLL:
         "yr_topk_masked_row": (C.c_int, [p, i64, p, i64, i32, p, p]),
         "yr_topk_masked_rows": (C.c_int, [p, i64, i64, i64, p, p, f32, i32, p, p, sz, p]),
         "yr_topk_metrics": (C.c_int, [p, i64, i64, p, p, p, p, i32, p, p, p]),
+        "yr_topk_merge": (C.c_int, [p, p, i32, i64, i32, p, p, p, p]),
         "yr_transpose_items": (C.c_int, [p, i64, i32, p, i64, p]),
         "yr_eval_ws_bytes": (sz, [i64, i32, i32]),
         "yr_eval_topk_metrics": (C.c_int, [p, i64, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
@@ -194,6 +195,8 @@ def load() -> C.CDLL:
         "yr_eval_tc_ws_bytes": (sz, [i64]),
         "yr_eval_topk_metrics_tc": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
                                               p, p, p, p, p, sz, p, p]),
+        "yr_eval_topk_metrics_tc_slice": (C.c_int, [p, i64, p, p, i64, i64, i32, p, i64, p, p, p, p, p, p, i32,
+                                                    p, p, p, p, p, sz, p, i32, i32, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

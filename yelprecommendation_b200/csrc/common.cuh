@@ -31,11 +31,11 @@ int yr_eval_reduce_launch(const double* user_metrics, const int32_t* act_ptr, co
 
 int yr_ngcf_dense_fwd_tc_launch_d(int d, const float* E, const float* LE, const float* W1, const float* W2, float slope,
                                   int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list = nullptr,
-                                  const int32_t* row_count = nullptr, int64_t row_cap = 0);
+                                  const int32_t* row_count = nullptr, int64_t row_cap = 0, int reserve_sms = 0);
 int yr_ngcf_dense_bwd_tc_launch(int d, const float* E, const float* LE, const float* En, const float* Gn, const float* W1,
                                 const float* W2, float slope, int64_t n, float* G, float* T, float* ws, int* n_parts,
                                 cudaStream_t s, const int32_t* row_list = nullptr, const int32_t* row_count = nullptr,
-                                int64_t row_cap = 0);
+                                int64_t row_cap = 0, int reserve_sms = 0);
 // Y = A X on the rows whose flag is set (all rows if row_flag == NULL); other rows of Y are left untouched
 int yr_spmm_csr_rows(const yr_csr* A, int d, const float* X, float* Y, const int32_t* row_flag, cudaStream_t s);
 

@@ -697,6 +697,49 @@ extern "C" int yr_topk_masked_rows(const float* pred, int64_t ld, int64_t n_rows
   return YR_OK;
 }
 
+// Merge of per-slice recommendations: the catalog is cut into S disjoint item slices, slice s delivered its K best items per
+// row (local ids, exact scores); the K best of the S * K candidates by (score desc, GLOBAL item id asc) are the K best of the
+// whole catalog, in the same order the unsliced evaluation gives. One thread per row, S * K <= 64.
+namespace yr {
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const int64_t* __restrict__ ids, const float* __restrict__ sc, int S, int64_t n, int K,
+                  const int64_t* __restrict__ id_offset, int64_t* __restrict__ out_ids, float* __restrict__ out_sc) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  unsigned long long taken = 0ull;
+  for (int k = 0; k < K; ++k) {
+    int best = -1;
+    float bs = 0.f;
+    int64_t bi = 0;
+    for (int s = 0; s < S; ++s) {
+      const int64_t off = id_offset[s];
+      for (int j = 0; j < K; ++j) {
+        const int c = s * K + j;
+        if ((taken >> c) & 1ull) continue;
+        const int64_t lid = ids[((int64_t)s * n + r) * K + j];
+        if (lid < 0) continue;                        // padding: the slice kept fewer than K items for this row
+        const float v = sc[((int64_t)s * n + r) * K + j];
+        const int64_t id = lid + off;
+        if (best < 0 || v > bs || (v == bs && id < bi)) { best = c; bs = v; bi = id; }
+      }
+    }
+    if (best >= 0) taken |= 1ull << best; else { bi = -1; bs = -INFINITY; }
+    out_ids[r * K + k] = bi;
+    if (out_sc) out_sc[r * K + k] = bs;
+  }
+}
+}  // namespace yr
+
+extern "C" int yr_topk_merge(const int64_t* ids, const float* scores, int S, int64_t n, int K, const int64_t* id_offset,
+                             int64_t* out_ids, float* out_scores, yr_stream stream) {
+  if (!ids || !scores || !id_offset || !out_ids || S < 1 || K < 1 || S * K > 64 || n < 0) return YR_ERR_BAD_ARG;
+  if (n == 0) return YR_OK;
+  yr::topk_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, scores, S, n, K, id_offset, out_ids,
+                                                                                    out_scores);
+  YR_CHECK_LAUNCH();
+  return YR_OK;
+}
+
 extern "C" int yr_topk_metrics(const int64_t* predicted, int64_t ldp, int64_t n, const int32_t* act_ptr,
                                const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2, int K,
                                double* user_metrics, double* metric_sums, yr_stream stream) {

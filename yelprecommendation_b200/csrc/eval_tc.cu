@@ -50,6 +50,9 @@ struct TcParams {
   int* cand;                     // global scratch for the candidate buffers: [grid][2 arrays][2][CAP][128]
   int SPS, NST, CAP;             // 32-float slabs per stage, pipeline stages, candidate buffer entries per half-stream
   int MCAP;                      // mask entries per row staged in shared memory (0 = none)
+  // item-sliced evaluation (yr_eval_topk_metrics_tc_slice): this call covers one of n_slices disjoint item slices; gx
+  // [n_slices x n_eval] carries every slice's current lower bound of a row's K-th best score between the concurrent calls
+  float* gx; int slice, n_slices;
 };
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ u, const float* __restrict__ v, int d) {
@@ -304,7 +307,17 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         tc_fence_after();
         {
           const float tau_o = xch_oth[0], mid_o = xch_oth[kTcTM];
-          theta = fmaxf(theta, fmaxf(tau_o, fminf(mid, mid_o)) - eps2);
+          float bound = fmaxf(tau_o, fminf(mid, mid_o));
+          if (P.n_slices > 1 && live) {
+            // The K-th best of ANY item slice is a lower bound of the K-th best of the whole catalog, so the concurrent calls
+            // on the other slices of this row lend their thresholds (global memory, monotone floats, stale reads are still
+            // valid bounds). Without this every slice pays the warm-up of its own running threshold — K ln(n / K) candidate
+            // events per slice, which is where the kernel's time goes — and slicing gains nothing (measured).
+            for (int s2 = 0; s2 < P.n_slices; ++s2)
+              if (s2 != P.slice) bound = fmaxf(bound, __ldcg(P.gx + (size_t)s2 * P.n_eval + e));
+            if (half == 0) __stcg(P.gx + (size_t)P.slice * P.n_eval + e, fmaxf(tau, fmaxf(tau_o, fminf(mid, mid_o))));
+          }
+          theta = fmaxf(theta, bound - eps2);
         }
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_e * TN + half * (TN / 2);
 #pragma unroll 1
@@ -356,7 +369,11 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
         const float tau_b = tauB[r];
         const int cnt_b = cntB[r];
         // all three are lower bounds of the K-th best s~ of the row
-        const float tau_f = fmaxf(fmaxf(tau, tau_b), fminf(mid, xch_oth[kTcTM]));
+        float tau_f = fmaxf(fmaxf(tau, tau_b), fminf(mid, xch_oth[kTcTM]));
+        const bool sliced = P.n_slices > 1;
+        if (sliced)
+          for (int s2 = 0; s2 < P.n_slices; ++s2)
+            if (s2 != P.slice) tau_f = fmaxf(tau_f, __ldcg(P.gx + (size_t)s2 * P.n_eval + e));
         const float theta_f = tau_f - eps2;
         bool fallback = overflow || cnt_b < 0 || tau_f == -INFINITY;
         int topi[kTcMaxK];
@@ -381,15 +398,18 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
               }
             }
           }
-          if (nt < K) fallback = true;
+          // a slice of a sliced evaluation may keep fewer than K items (the other slices hold the rest of the top K): the
+          // row's list is padded with id -1 / -inf, which yr_topk_merge skips
+          if (nt < K && !sliced) fallback = true;
         }
         if (fallback) {
           P.fb_rows[atomicAdd(P.fb_count, 1)] = (int32_t)e;
         } else {
           for (int j = 0; j < K; ++j) {
-            P.topk_out[e * K + j] = topi[j];
-            if (P.topk_score) P.topk_score[e * K + j] = tops[j];
+            P.topk_out[e * K + j] = j < nt ? topi[j] : -1;
+            if (P.topk_score) P.topk_score[e * K + j] = j < nt ? tops[j] : -INFINITY;
           }
+          if (!sliced) {             // (a slice's list is not the row's recommendation: metrics follow the merge)
           // metric terms, metric.py:7-109 (quirks Q6-Q8), Python's summation order
           const int a0 = P.act_ptr[e], LA = P.act_ptr[e + 1] - a0;
           int hits = 0;
@@ -415,6 +435,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap vmap, TcParams P) {
           um[1] = (nun > 0) ? (double)hits / (double)nun : 0.0;
           um[2] = (LA > 0) ? ap / (double)LA : 0.0;
           um[3] = (nun > 0 && idcg > 0.0) ? dcg / idcg : 0.0;
+          }
         }
       }
     }
@@ -500,13 +521,14 @@ extern "C" int yr_eval_tc_supported(int d, int K) {
   return tc_config(d, K, &c) && encode_tiled_fn() != nullptr;
 }
 
-extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt,
-                                       int64_t ldt, int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
-                                       const int32_t* mask_ptr, const int32_t* mask_idx, const int32_t* act_ptr,
-                                       const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2,
-                                       int K, int64_t* topk_out, float* topk_score, double* user_metrics,
-                                       double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
-                                       yr_stream stream) {
+static int eval_tc_impl(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt,
+                        int64_t ldt, int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
+                        const int32_t* mask_ptr, const int32_t* mask_idx, const int32_t* act_ptr,
+                        const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2,
+                        int K, int64_t* topk_out, float* topk_score, double* user_metrics,
+                        double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
+                        int slice, int n_slices, float* xchg, yr_stream stream) {
+  if (n_slices < 1 || slice < 0 || slice >= n_slices || (n_slices > 1 && (!xchg || !topk_score))) return YR_ERR_BAD_ARG;
   if (!Uemb || !Vemb || !Vt || !eval_uid || !mask_ptr || !mask_idx || !act_ptr || !act_idx || !act_nuniq ||
       !inv_log2 || !topk_out || !user_metrics || !metric_sums || !ws)
     return YR_ERR_BAD_ARG;
@@ -541,6 +563,7 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
     P.inv_log2 = inv_log2; P.K = K; P.topk_out = topk_out; P.topk_score = topk_score; P.user_metrics = user_metrics;
     P.err = err; P.vmax = vmax; P.fb_count = fb_count; P.fb_rows = fb_rows; P.cand = cand;
     P.SPS = cfg.SPS; P.NST = cfg.NST; P.CAP = cfg.CAP; P.MCAP = cfg.MCAP;
+    P.gx = xchg; P.slice = slice; P.n_slices = n_slices;
     YR_CUDA(cudaFuncSetAttribute(eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     const int64_t n_utiles = (n_eval + kTcTM - 1) / kTcTM;
     int64_t grid = yr_sm_count();
@@ -553,5 +576,28 @@ extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const floa
                                   stream);
     if (rc) return rc;
   }
+  if (n_slices > 1) return YR_OK;          // a slice's lists carry no metrics: yr_topk_merge + yr_topk_metrics follow
   return yr_eval_reduce_launch(user_metrics, act_ptr, act_nuniq, n_eval, metric_sums, stream);
+}
+
+extern "C" int yr_eval_topk_metrics_tc(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt,
+                                       int64_t ldt, int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
+                                       const int32_t* mask_ptr, const int32_t* mask_idx, const int32_t* act_ptr,
+                                       const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2,
+                                       int K, int64_t* topk_out, float* topk_score, double* user_metrics,
+                                       double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
+                                       yr_stream stream) {
+  return eval_tc_impl(Uemb, nU, Vemb, Vt, ldt, nI, d, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq, inv_log2,
+                      K, topk_out, topk_score, user_metrics, metric_sums, ws, ws_bytes, err, 0, 1, nullptr, stream);
+}
+
+extern "C" int yr_eval_topk_metrics_tc_slice(const float* Uemb, int64_t nU, const float* Vemb, const float* Vt,
+                                             int64_t ldt, int64_t nI, int d, const int64_t* eval_uid, int64_t n_eval,
+                                             const int32_t* mask_ptr, const int32_t* mask_idx, const int32_t* act_ptr,
+                                             const int32_t* act_idx, const int32_t* act_nuniq, const double* inv_log2,
+                                             int K, int64_t* topk_out, float* topk_score, double* user_metrics,
+                                             double* metric_sums, void* ws, size_t ws_bytes, int32_t* err,
+                                             int slice, int n_slices, float* xchg, yr_stream stream) {
+  return eval_tc_impl(Uemb, nU, Vemb, Vt, ldt, nI, d, eval_uid, n_eval, mask_ptr, mask_idx, act_ptr, act_idx, act_nuniq, inv_log2,
+                      K, topk_out, topk_score, user_metrics, metric_sums, ws, ws_bytes, err, slice, n_slices, xchg, stream);
 }

@@ -460,9 +460,14 @@ constexpr int kBwdCtasPerSm = 2;
 using namespace yr;
 
 // yr_dense_mode (include/yelprec_b200.h) travels per call / per trainer state; nothing here is process-wide.
-static inline bool mode_ok(int m) { return m == YR_DENSE_FP32 || m == YR_DENSE_TC_FWD || m == YR_DENSE_TC; }
-static inline bool fwd_tc(int m) { return m != YR_DENSE_FP32; }
-static inline bool bwd_tc(int m) { return m == YR_DENSE_TC; }
+// bits 0..7: yr_dense_mode; bits 8..15: SMs the tensor-core kernels leave empty (YR_DENSE_RESERVE)
+static inline int mode_of(int m) { return m & 0xff; }
+static inline int reserve_of(int m) { return (m >> 8) & 0xff; }
+static inline bool mode_ok(int m) {
+  return m >= 0 && (m >> 16) == 0 && (mode_of(m) == YR_DENSE_FP32 || mode_of(m) == YR_DENSE_TC_FWD || mode_of(m) == YR_DENSE_TC);
+}
+static inline bool fwd_tc(int m) { return mode_of(m) != YR_DENSE_FP32; }
+static inline bool bwd_tc(int m) { return mode_of(m) == YR_DENSE_TC; }
 
 template <int D>
 static int dense_fwd_fp32_launch(int64_t n, const float* E, const float* LE, const float* W1, const float* W2, float slope,
@@ -501,7 +506,8 @@ extern "C" int yr_ngcf_dense_fwd(int d, int64_t n, const float* E, const float* 
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (n == 0) return YR_OK;
   if (fwd_tc(dense_mode) && (d == 64 || d == 128))      // tcgen05 3xTF32 (ngcf_tc.cu); d = 32 runs on the FP32 pipe
-    return yr_ngcf_dense_fwd_tc_launch_d(d, E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream);
+    return yr_ngcf_dense_fwd_tc_launch_d(d, E, LE, W1, W2, slope, n, E_next, (cudaStream_t)stream, nullptr, nullptr, 0,
+                                         reserve_of(dense_mode));
   switch (d) {
     case 32: return dense_fwd_fp32_launch<32>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
     case 64: return dense_fwd_fp32_launch<64>(n, E, LE, W1, W2, slope, E_next, (cudaStream_t)stream);
@@ -530,7 +536,8 @@ static int dense_bwd_launch(int d, int64_t n, const float* E, const float* LE, c
   if (d != 32 && d != 64 && d != 128) return YR_ERR_BAD_DIM;
   if (ws_bytes < yr_ngcf_layer_bwd_ws_bytes(d)) return YR_ERR_WORKSPACE;
   if (bwd_tc(dense_mode) && (d == 64 || d == 128))          // tcgen05 3xTF32 (ngcf_tc_bwd.cu); d = 32 runs on the FP32 pipe
-    return yr_ngcf_dense_bwd_tc_launch(d, E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s);
+    return yr_ngcf_dense_bwd_tc_launch(d, E, LE, E_next, G_next, W1, W2, slope, n, G, T, (float*)ws, n_parts, s, nullptr, nullptr,
+                                       0, reserve_of(dense_mode));
   switch (d) {
     case 32: return dense_bwd_fp32_launch<32>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);
     case 64: return dense_bwd_fp32_launch<64>(n, E, LE, E_next, G_next, W1, W2, slope, G, T, (float*)ws, s, n_parts);

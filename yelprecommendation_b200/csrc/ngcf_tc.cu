@@ -306,12 +306,13 @@ using namespace yr;
 
 template <int D>
 static int fwd_tc_launch(const float* E, const float* LE, const float* W1, const float* W2, float slope, int64_t n,
-                         float* Eout, cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
+                         float* Eout, cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap,
+                         int reserve_sms) {
   using C = FwdTc<D>;
   static yr::AttrOnce attr;
   { int rc_ = attr.set(ngcf_dense_fwd_tc_kernel<D>, (int)C::kSmem); if (rc_) return rc_; }
   const int64_t n_tiles = ((row_list ? row_cap : n) + kFwdTM - 1) / kFwdTM;
-  int64_t grid = yr_sm_count();
+  int64_t grid = yr_sm_count() - reserve_sms;
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) grid = 1;
   unsigned char* ws = nullptr;
@@ -339,8 +340,8 @@ static int fwd_tc_launch(const float* E, const float* LE, const float* W1, const
 // internal launcher used by yr_ngcf_dense_fwd / yr_ngcf_train_step (ngcf.cu): d in {64, 128}
 int yr_ngcf_dense_fwd_tc_launch_d(int d, const float* E, const float* LE, const float* W1, const float* W2, float slope,
                                   int64_t n, float* Eout, cudaStream_t s, const int32_t* row_list,
-                                  const int32_t* row_count, int64_t row_cap) {
-  if (d == 64) return fwd_tc_launch<64>(E, LE, W1, W2, slope, n, Eout, s, row_list, row_count, row_cap);
-  if (d == 128) return fwd_tc_launch<128>(E, LE, W1, W2, slope, n, Eout, s, row_list, row_count, row_cap);
+                                  const int32_t* row_count, int64_t row_cap, int reserve_sms) {
+  if (d == 64) return fwd_tc_launch<64>(E, LE, W1, W2, slope, n, Eout, s, row_list, row_count, row_cap, reserve_sms);
+  if (d == 128) return fwd_tc_launch<128>(E, LE, W1, W2, slope, n, Eout, s, row_list, row_count, row_cap, reserve_sms);
   return YR_ERR_BAD_ARG;
 }

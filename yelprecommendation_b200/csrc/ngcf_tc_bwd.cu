@@ -438,13 +438,13 @@ using namespace yr;
 template <int D>
 static int bwd_tc_launch(const float* E, const float* LE, const float* En, const float* Gn, const float* W1, const float* W2,
                          float slope, int64_t n, float* G, float* T, float* ws, int* n_parts, cudaStream_t s,
-                         const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
+                         const int32_t* row_list, const int32_t* row_count, int64_t row_cap, int reserve_sms) {
   using C = BwdTc<D>;
   static yr::AttrOnce attr;
   { int rc_ = attr.set(ngcf_dense_bwd_tc_kernel<D>, (int)C::kSmem); if (rc_) return rc_; }
   const int64_t n_tiles = ((row_list ? row_cap : n) + kBwdTM - 1) / kBwdTM;
   const int64_t sms = yr_sm_count();
-  int64_t grid = sms;
+  int64_t grid = sms - reserve_sms;
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) grid = 1;
   // the split weights live behind the per-CTA dW partials: yr_ngcf_layer_bwd_ws_bytes() sizes the workspace for two CTAs
@@ -463,8 +463,9 @@ static int bwd_tc_launch(const float* E, const float* LE, const float* En, const
 // *n_parts. ws: yr_ngcf_layer_bwd_ws_bytes(d) bytes.
 int yr_ngcf_dense_bwd_tc_launch(int d, const float* E, const float* LE, const float* En, const float* Gn, const float* W1,
                                 const float* W2, float slope, int64_t n, float* G, float* T, float* ws, int* n_parts,
-                                cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap) {
-  if (d == 64) return bwd_tc_launch<64>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap);
-  if (d == 128) return bwd_tc_launch<128>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap);
+                                cudaStream_t s, const int32_t* row_list, const int32_t* row_count, int64_t row_cap,
+                                int reserve_sms) {
+  if (d == 64) return bwd_tc_launch<64>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap, reserve_sms);
+  if (d == 128) return bwd_tc_launch<128>(E, LE, En, Gn, W1, W2, slope, n, G, T, ws, n_parts, s, row_list, row_count, row_cap, reserve_sms);
   return YR_ERR_BAD_DIM;
 }

@@ -240,6 +240,11 @@ static int launch_spmm_v(const yr_csr* A, const float* X, float* Y, int accumula
   int64_t blocks = ((int64_t)A->n_chunks + (int64_t)wpb * C::CPW - 1) / ((int64_t)wpb * C::CPW);
   const int64_t cap = (int64_t)yr_sm_count() * 8 * 32;
   if (blocks > cap) blocks = cap;
+  if (THREADS == 1024) {           // reserve_sms: one persistent CTA per SM (1,024 threads x >= 33 registers exclude a second one)
+    int64_t sms = (int64_t)yr_sm_count() - A->reserve_sms;
+    if (sms < 1) sms = 1;
+    if (blocks > sms) blocks = sms;
+  }
   if (accumulate) spmm_chunk_kernel<D, true, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
   else spmm_chunk_kernel<D, false, THREADS, MINB, U, DIRECT><<<(unsigned)blocks, THREADS, 0, s>>>(*A, X, Y, row_flag);
   YR_CHECK_LAUNCH();
@@ -265,6 +270,7 @@ static int launch_spmm(const yr_csr* A, const float* X, float* Y, int accumulate
   // CTAs bounded to 48 registers (10 CTAs = 40 warps per SM), 4 neighbour rows in flight per group, direct index loads:
   // 53.8 us at d = 64 (14.9 TB/s of gathers) / 98.9 us at d = 128 (16.2 TB/s) against a measured L2 -> SM gather ceiling of
   // 17.6 TB/s (scripts/l2_gather_bench.cu); the round-1 shape (variant 0, row-order plan) took 85.5 / 216 us.
+  if (A->reserve_sms > 0) return launch_spmm_v<D, 1024, 1, 4, true>(A, X, Y, accumulate, s, row_flag);
   switch (spmm_variant()) {
     case 0: return launch_spmm_v<D, 256, (D <= 64 ? 3 : 2), 8, false>(A, X, Y, accumulate, s, row_flag);
     case 1: return launch_spmm_v<D, 128, 8, 4, false>(A, X, Y, accumulate, s, row_flag);

@@ -110,7 +110,8 @@ class CSRMatrix:
         return _cabi.YrCsr(self.n_rows, self.nnz, p(self.rowptr), p(self.col), p(self.val), self.n_chunks,
                            p(self.chunk_desc), self.n_split_rows,
                            p(self.split_row), p(self.split_ptr), p(part), p(self.split_count),
-                           self.n_big_rows, p(self.big_split_idx) if self.n_big_rows else None)
+                           self.n_big_rows, p(self.big_split_idx) if self.n_big_rows else None,
+                           int(getattr(self, "reserve_sms", 0)))
 
 
 @dataclass

@@ -366,12 +366,148 @@ def transpose_items(V: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return Vt, ldt
 
 
-def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None, mode: str = None):
+_SM_COUNT = {}
+_SLICE_STREAMS = {}
+
+
+def _sm_count(dev) -> int:
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    if i not in _SM_COUNT:
+        _SM_COUNT[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SM_COUNT[i]
+
+
+def eval_item_slices(n_eval: int, nI: int, K: int, dev) -> int:
+    """How many item slices a full-catalog evaluation of n_eval rows is cut into. The tensor-core kernel runs one CTA per SM
+    over 128-row user tiles, each streaming the whole catalog: a row shard of 31 tiles (8 ranks at Yelp shape) leaves 117 of
+    148 SMs idle. Cut into S item slices evaluated by S concurrent launches, S x tiles CTAs are busy and a tile's stream is S
+    times shorter. YR_EVAL_SLICES overrides (1 = never slice)."""
+    import os
+    env = os.environ.get("YR_EVAL_SLICES")
+    tiles = max(1, (n_eval + 127) // 128)
+    S = int(env) if env else _sm_count(dev) // tiles
+    S = max(1, min(S, 8, 64 // max(K, 1)))
+    while S > 1 and -(-nI // S) < 2048:          # keep slices long enough for the running threshold to settle
+        S -= 1
+    return S
+
+
+def _sliced_masks(ecsr: DeviceEvalCSR, S: int, per: int):
+    """Per item slice s: the mask CSR restricted to items [s * per, (s + 1) * per), ids re-based to the slice (ascending per
+    row, like the original). Index plumbing with torch ops, once per (evaluation set, S); cached on the DeviceEvalCSR.
+    Returns None when some row has fewer than K unmasked items inside a slice (the unsliced path handles such rows)."""
+    cache = ecsr.__dict__.setdefault("_slice_cache", {})
+    key = (S, per)
+    if key in cache:
+        return cache[key]
+    n, dev = ecsr.n_eval, ecsr.eval_uid.device
+    ptr = ecsr.mask_ptr.to(I64)
+    nnz = int(ptr[n].item())
+    idx = ecsr.mask_idx[:nnz].to(I64)
+    row = torch.repeat_interleave(torch.arange(n, device=dev), ptr[1:n + 1] - ptr[:n])
+    sl = torch.div(idx, per, rounding_mode="floor")
+    out, ok = [], True
+    for s_ in range(S):
+        sel = sl == s_
+        cnt = torch.bincount(row[sel], minlength=n)
+        size = min(per, ecsr_items(ecsr) - s_ * per) if ecsr_items(ecsr) else per
+        if n and int(cnt.max().item()) > size - ecsr.K:
+            ok = False
+            break
+        p_s = torch.zeros(n + 1, device=dev, dtype=I64)
+        p_s[1:] = torch.cumsum(cnt, 0)
+        i_s = (idx[sel] - s_ * per).to(I32)
+        out.append((p_s.to(I32).contiguous(), i_s.contiguous() if i_s.numel() else torch.zeros(1, dtype=I32, device=dev)))
+    cache[key] = out if ok else None
+    return cache[key]
+
+
+def ecsr_items(ecsr) -> int:
+    return int(getattr(ecsr, "_nI", 0))
+
+
+def _eval_tc_call(lib, Uemb, Vemb, Vt, ldt, nI, d, ecsr, mask_ptr, mask_idx, topk, tsc, um, sums, ws, err, slice_, n_slices, xchg,
+                  stream):
+    n, K = ecsr.n_eval, ecsr.K
+    check(lib.yr_eval_topk_metrics_tc_slice(dptr(Uemb, F32), Uemb.shape[0], Vemb.data_ptr(), Vt.data_ptr(), ldt, nI, d,
+                                            dptr(ecsr.eval_uid, I64), n, dptr(mask_ptr, I32), dptr(mask_idx, I32),
+                                            dptr(ecsr.act_ptr, I32), dptr(ecsr.act_idx, I32), dptr(ecsr.act_nuniq, I32),
+                                            dptr(ecsr.inv_log2, F64), K, dptr(topk), dptr(tsc), dptr(um), dptr(sums),
+                                            dptr(ws), ws.numel(), dptr(err), slice_, n_slices, dptr(xchg, F32), stream),
+          "yr_eval_topk_metrics_tc_slice")
+
+
+def _eval_tc_sliced(lib, Uemb, Vemb, Vt, ldt, ecsr, S: int):
+    """S concurrent tensor-core evaluations on disjoint item slices, then yr_topk_merge + yr_topk_metrics: the same top-K
+    lists (ids, order, exact scores) and metrics as the unsliced call."""
+    dev = Uemb.device
+    nI, d = Vemb.shape
+    n, K = ecsr.n_eval, ecsr.K
+    per = (-(-nI // S) + 127) // 128 * 128
+    S = -(-nI // per)
+    ecsr._nI = nI
+    masks = _sliced_masks(ecsr, S, per) if S > 1 else None
+    if masks is None:
+        return None
+    ids = torch.empty(S, n, K, device=dev, dtype=I64)
+    scs = torch.empty(S, n, K, device=dev, dtype=F32)
+    um_s = torch.zeros(S, n, 4, device=dev, dtype=F64)              # per-slice metrics: not meaningful, never read
+    sums_s = torch.zeros(S, 6, device=dev, dtype=F64)
+    errs = torch.zeros(S, device=dev, dtype=I32)
+    wsb = lib.yr_eval_tc_ws_bytes(n)
+    wss = torch.empty(S, wsb, device=dev, dtype=torch.uint8)
+    xchg = torch.full((S, max(n, 1)), float("-inf"), device=dev, dtype=F32)     # the slices' shared thresholds
+    key = (dev.index, S)
+    if key not in _SLICE_STREAMS:
+        _SLICE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    cur = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    esz = Vemb.element_size()
+    for s_, st in enumerate(_SLICE_STREAMS[key]):
+        i0 = s_ * per
+        n_s = min(per, nI - i0)
+        st.wait_event(ready)
+        mp, mi = masks[s_]
+        # item slice = rows [i0, i0 + n_s) of V (row-major) and columns [i0, ...) of the transposed copy
+        _eval_tc_call(lib, Uemb, _PtrView(Vemb.data_ptr() + i0 * d * esz), _PtrView(Vt.data_ptr() + i0 * esz), ldt, n_s, d, ecsr,
+                      mp, mi, ids[s_], scs[s_], um_s[s_], sums_s[s_], wss[s_], errs[s_:s_ + 1], s_, S, xchg, st.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(st)
+        cur.wait_event(done)
+    for t in (ids, scs, um_s, sums_s, errs, wss, xchg):
+        for st in _SLICE_STREAMS[key]:
+            t.record_stream(st)
+    off = torch.arange(S, device=dev, dtype=I64) * per
+    topk = torch.empty(max(n, 1), K, device=dev, dtype=I64)
+    tsc = torch.empty(max(n, 1), K, device=dev, dtype=F32)
+    check(lib.yr_topk_merge(dptr(ids, I64), dptr(scs, F32), S, n, K, dptr(off, I64), dptr(topk), dptr(tsc), stream_ptr(dev)),
+          "yr_topk_merge")
+    um, sums = topk_metrics(topk[:n], ecsr)
+    err = errs.max().reshape(1)
+    eval_topk_metrics.last_fallback_rows = wss[:, 4:8].contiguous().view(I32).sum().reshape(1)
+    eval_topk_metrics.last_slices = S
+    return topk[:n], tsc[:n], um, sums, err
+
+
+class _PtrView:
+    """A device address handed to the C ABI in place of a tensor (an item-table slice that starts inside a tensor)."""
+
+    def __init__(self, ptr: int):
+        self._ptr = ptr
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+
+def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCSR, Vt=None, mode: str = None,
+                      slices: int = None):
     """Returns (topk [n_eval x K] int64, topk_score, user_metrics [n_eval x 4] f64, sums [6] f64, err) on device.
 
     mode 'tc'    : tensor-core filter + exact re-score (yr_eval_topk_metrics_tc) — bit-identical outputs;
     mode 'exact' : FP32-pipe kernel (yr_eval_topk_metrics);
-    mode None    : env YR_EVAL_MODE, else 'tc' whenever the library supports (d, K), 'exact' otherwise."""
+    mode None    : env YR_EVAL_MODE, else 'tc' whenever the library supports (d, K), 'exact' otherwise.
+    slices       : item slices for small row sets (tensor-core mode only; None = eval_item_slices()); identical outputs."""
     import os
     lib = _cabi.load()
     Uemb = Uemb.detach().contiguous()
@@ -380,6 +516,17 @@ def eval_topk_metrics(Uemb: torch.Tensor, Vemb: torch.Tensor, ecsr: DeviceEvalCS
     nI, d = Vemb.shape
     mode = mode or os.environ.get("YR_EVAL_MODE") or "auto"
     use_tc = mode == "tc" or (mode == "auto" and lib.yr_eval_tc_supported(d, ecsr.K) != 0)
+    eval_topk_metrics.last_slices = 1
+    if use_tc and ecsr.n_eval > 0:
+        S = int(slices) if slices is not None else eval_item_slices(ecsr.n_eval, nI, ecsr.K, dev)
+        if S > 1:
+            if Vt is None:
+                Vt, ldt = transpose_items(Vemb)
+            else:
+                ldt = Vt.shape[1]
+            res = _eval_tc_sliced(lib, Uemb, Vemb, Vt, ldt, ecsr, S)
+            if res is not None:
+                return res
     if use_tc:
         if Vt is None:
             Vt, ldt = transpose_items(Vemb)

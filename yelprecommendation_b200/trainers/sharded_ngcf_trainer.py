@@ -55,13 +55,16 @@ class CabiNgcfShardKernels:
         self.lib = _cabi.load()
         self._ws = None
         self.dense_mode = _cabi.YR_DENSE_TC
+        self.reserve_sms = 0
 
     def _st(self):
         return _cabi.stream_ptr(self.device)
 
     def make_csr(self, rowptr, col, val):
         """rowptr: absolute offsets into col / val (a row panel shares the block's storage)"""
-        return CSRMatrix(rowptr, col, val, self.device)
+        m = CSRMatrix(rowptr, col, val, self.device)
+        m.reserve_sms = self.reserve_sms          # yr_csr.reserve_sms: SMs left empty for the exchange's NCCL kernels
+        return m
 
     def spmm(self, A, X, out, accumulate):
         ops.spmm_csr(A, X, out=out, accumulate=accumulate)
@@ -132,11 +135,30 @@ class ShardedNGCFTrainer:
         self.world = dist.get_world_size(group) if multi else 1
         self.rank = dist.get_rank(group) if multi else 0
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        # The panel rounds go through a process group of their own with high-priority NCCL streams (YR_SHARD_HIPRIO=0: the
+        # caller's / default group). Priority alone changes nothing (measured on 2 GPUs: 285.7 vs 287.1 ms per step): NCCL's
+        # 640-thread CTAs need an EMPTY SM and never start while a grid of small CTAs keeps refilling every SM — what lets the
+        # exchange run underneath the SpMM is YR_SHARD_RESERVE_SMS below.
+        self.xgroup = group
+        if (multi and self.world > 1 and kernels is None and dist.get_backend(group) == "nccl"
+                and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            self.xgroup = dist.new_group(ranks=dist.get_process_group_ranks(group if group is not None else dist.group.WORLD),
+                                         backend="nccl", pg_options=opts)
         self.k = kernels if kernels is not None else CabiNgcfShardKernels(self.device)
         if kernels is None:                     # yr_dense_mode of the d x d transforms (default: tensor cores for both passes)
             self.k.dense_mode = int(getattr(cfg, "ngcf_dense_mode", _cabi.YR_DENSE_TC))
             if self.k.dense_mode not in (0, 1, 2):
                 raise ValueError(f"ngcf_dense_mode {self.k.dense_mode} not in (0, 1, 2)")
+            # YR_SHARD_RESERVE_SMS=R (world > 1): the SpMM and the dense transforms run on SM count - R persistent one-per-SM
+            # CTAs and leave R SMs empty for the NCCL kernels of the panel exchange (yr_csr.reserve_sms, YR_DENSE_RESERVE);
+            # NCCL is told to use at most R CTAs unless NCCL_MAX_CTAS is already set.
+            R = int(os.environ.get("YR_SHARD_RESERVE_SMS", "0")) if (multi and self.world > 1) else 0
+            if R > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", str(R))
+                self.k.reserve_sms = R
+                self.k.dense_mode |= (R & 0xff) << 8
         self.d, self.n_layers = int(cfg.embed_size), int(cfg.num_orders)
         self.width = (self.n_layers + 1) * self.d
         if self.width not in (32, 64, 128, 256, 512, 1024):
@@ -174,7 +196,7 @@ class ShardedNGCFTrainer:
         # every rank sent in exchange round p, so it can run underneath round p+1 — used where the whole operand is
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
         self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "p2p")
-        self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode != "allgather"
+        self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode not in ("allgather", "symm")
                                and int(os.environ.get("YR_SHARD_COLPANELS", "1" if interleave else "0")) != 0)
         self.colA = self.colAT = None
         if self.use_col_panels:
@@ -203,6 +225,9 @@ class ShardedNGCFTrainer:
         # gathered operands: two buffers, so that the exchange of layer l+1 can land while layer l's SpMM still reads
         self.X = [z(self.total, d) for _ in range(2)] if self.world > 1 else None
         self._pending = [[], []]
+        self._symm = None
+        if self.world > 1 and self._xmode == "symm":
+            self._init_symm(d)
         self.W1, self.W2 = [f(w) for w in W1], [f(w) for w in W2]
         self.dW = z(2 * self.n_layers, d, d)
         self.dWp = z(len(self.panels), 2, d, d)
@@ -238,12 +263,72 @@ class ShardedNGCFTrainer:
         return [self.k.make_csr(ptr_h[p * per: (p + 1) * per + 1], ci_p, va_p) for p in range(P)]
 
     # ------------------------------------------------------------------------------------------
+    def _init_symm(self, d: int) -> None:
+        """YR_SHARD_EXCHANGE=symm: the gathered operands live in symmetric memory (torch.distributed._symmetric_memory: every
+        rank maps every peer's buffer) and a panel is PUSHED into the peers' buffers with plain device-to-device copies, one
+        stream per peer — the copy engines move the data over NVLink, no SM is involved, so the exchange really runs underneath
+        the SpMM (NCCL's send / recv kernels need SMs of their own: measured, they queued behind the compute kernels and a
+        step cost compute + exchange). A layer's exchange ends with one put_signal per peer behind the copies; the consumer
+        waits for the peers' signals on its compute stream."""
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._symm = []
+        for b in range(2):
+            t = symm_mem.empty((self.total, d), dtype=F32, device=self.device)
+            t.zero_()
+            h = symm_mem.rendezvous(t, group=grp)
+            views = {r: h.get_buffer(r, (self.total, d), F32, 0) for r in self._peers_list()}
+            self.X[b] = t
+            self._symm.append((h, views))
+        self._pstreams = {r: torch.cuda.Stream(device=self.device) for r in self._peers_list()}
+        self._xchan = [[], []]                    # signal channels of the posted, not yet awaited, exchanges per buffer
+        self._xseq = 0
+        self._copied = []                         # events: my outgoing copies of the current exchange
+
+    def _peers_list(self):
+        return [(self.rank + i) % self.world for i in range(1, self.world)]
+
+    def _post_symm(self, src: torch.Tensor, a: int, b: int, buf: int) -> None:
+        h, views = self._symm[buf]
+        cur = torch.cuda.current_stream(self.device)
+        self.X[buf][self.lo + a: self.lo + b].copy_(src[a:b])
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        first, last = a == 0, b >= self.per
+        if first:
+            self._xchan[buf].append(self._xseq % 8)
+            self._xseq += 1
+        ch = self._xchan[buf][-1]
+        for r, st in self._pstreams.items():
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                views[r][self.lo + a: self.lo + b].copy_(src[a:b], non_blocking=True)
+                if last:
+                    h.put_signal(r, ch)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    self._copied.append(ev)
+
+    def _wait_symm(self, buf: int) -> None:
+        h, _ = self._symm[buf]
+        cur = torch.cuda.current_stream(self.device)
+        while self._xchan[buf]:
+            ch = self._xchan[buf].pop(0)
+            for r in self._pstreams:
+                h.wait_signal(r, ch)              # peer r's rows of this exchange are in my buffer
+        for ev in self._copied:                   # ... and my rows have left (the source may be overwritten)
+            cur.wait_event(ev)
+        self._copied = []
+
     def _post_exchange(self, src: torch.Tensor, a: int, b: int, buf: int) -> None:
         """rows [a, b) of the local [per x d] matrix -> the same rows of this rank's slot in EVERY rank's X[buf]:
         one grouped send/recv per panel, asynchronous (waited for by _wait before X[buf] is read)."""
         if self.world == 1:
             return
         X, per = self.X[buf], self.per
+        if self._symm is not None:
+            self._post_symm(src, a, b, buf)
+            return
         if self._xmode == "allgather":
             # experiment (YR_SHARD_EXCHANGE=allgather): ONE NCCL all-gather of the whole matrix, posted with the last panel
             # (the rank-major layout of X is exactly all_gather_into_tensor's output) — no panel pipelining
@@ -256,11 +341,14 @@ class ShardedNGCFTrainer:
             return
         ops_ = []
         for r in self._peers:
-            ops_.append(dist.P2POp(dist.isend, src[a:b], self._grank(r), self.group))
-            ops_.append(dist.P2POp(dist.irecv, X[r * per + a: r * per + b], self._grank(r), self.group))
+            ops_.append(dist.P2POp(dist.isend, src[a:b], self._grank(r), self.xgroup))
+            ops_.append(dist.P2POp(dist.irecv, X[r * per + a: r * per + b], self._grank(r), self.xgroup))
         self._pending[buf].append(dist.batch_isend_irecv(ops_))      # one entry per posted round, in posting order
 
     def _wait(self, buf: int) -> None:
+        if self._symm is not None:
+            self._wait_symm(buf)
+            return
         for works in self._pending[buf]:
             for w in works:
                 w.wait()
