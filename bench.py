@@ -279,9 +279,12 @@ def config5_extras(extra, dev, rank, world, barrier, max_over_ranks, pk, args):
         "dense_kernels": "tcgen05 3xTF32 ring kernels at d = 128 (csrc/ngcf_tc.cu, csrc/ngcf_tc_bwd.cu), yr_dense_mode 2",
         "exchange_ms_per_layer_alone": ms_xchg,
         "exchange_bytes_per_layer_per_gpu": (world - 1) * tr.per * d5 * 4 if world > 1 else 0,
+        "exchange": None if world == 1 else tr._xmode,
         "collectives": "none (1 GPU)" if world == 1 else
-        f"per layer fwd and bwd: {len(tr.panels)} grouped NCCL send/recv rounds (one row panel each, {(world - 1) * tr.per * d5 * 4 / 1e9:.2f} GB received per GPU "
-        "per layer) issued underneath the next panel's SpMM/transform; all_reduce(tail rows 3B x 512 floats) + all_reduce(dW) per step",
+        f"per layer fwd and bwd: {len(tr.panels)} panel rounds ({(world - 1) * tr.per * d5 * 4 / 1e9:.2f} GB received per GPU per layer) "
+        + ("pushed into the peers' symmetric-memory buffers by the copy engines (one stream per peer, one signal per peer and layer)"
+           if tr._xmode == "symm" else "as grouped NCCL send/recv") +
+        " underneath the next panel's SpMM/transform; all_reduce(tail rows 3B x 512 floats) + all_reduce(dW) per step",
         "loss_mean": float(acc.item()) / ((n_ng + 1) * B5)}
     del tr
     torch.cuda.empty_cache()

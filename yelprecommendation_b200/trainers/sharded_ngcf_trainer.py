@@ -141,7 +141,7 @@ class ShardedNGCFTrainer:
         # exchange run underneath the SpMM is YR_SHARD_RESERVE_SMS below.
         self.xgroup = group
         if (multi and self.world > 1 and kernels is None and dist.get_backend(group) == "nccl"
-                and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
+                and os.environ.get("YR_SHARD_EXCHANGE", "symm") == "p2p" and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
             self.xgroup = dist.new_group(ranks=dist.get_process_group_ranks(group if group is not None else dist.group.WORLD),
@@ -195,7 +195,9 @@ class ShardedNGCFTrainer:
         # COLUMN panels (one per row panel of the gathered operand): the SpMM over column panel p only needs the rows
         # every rank sent in exchange round p, so it can run underneath round p+1 — used where the whole operand is
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
-        self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "p2p")
+        # how a panel reaches the peers: 'symm' (default on NCCL/CUDA runs) = copy-engine pushes through symmetric memory,
+        # 'p2p' = grouped NCCL send / recv, 'allgather' / 'none' = experiments (one NCCL all-gather per layer / compute only)
+        self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "symm" if (self.world > 1 and kernels is None) else "p2p")
         self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode not in ("allgather", "symm")
                                and int(os.environ.get("YR_SHARD_COLPANELS", "1" if interleave else "0")) != 0)
         self.colA = self.colAT = None
@@ -227,7 +229,16 @@ class ShardedNGCFTrainer:
         self._pending = [[], []]
         self._symm = None
         if self.world > 1 and self._xmode == "symm":
-            self._init_symm(d)
+            ok = torch.ones(1, device=dev, dtype=I32)
+            try:
+                self._init_symm(d)
+            except Exception as ex:                    # no symmetric-memory support on this system: NCCL send / recv instead
+                ok.zero_()
+                self._symm_error = repr(ex)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank takes the same path
+            if int(ok.item()) == 0:
+                self._symm, self._xmode = None, "p2p"
+                self.X = [z(self.total, d) for _ in range(2)]
         self.W1, self.W2 = [f(w) for w in W1], [f(w) for w in W2]
         self.dW = z(2 * self.n_layers, d, d)
         self.dWp = z(len(self.panels), 2, d, d)
