@@ -592,8 +592,10 @@ def main():
                                      "metrics": [round(x, 6) for x in ops.metrics_from_sums(sums.cpu(), w.ecsr.n_eval)],
                                      "fallback_rows": int(ops.eval_topk_metrics.last_fallback_rows.item())
                                      if hasattr(ops.eval_topk_metrics, "last_fallback_rows") else None,
+                                     "item_slices": int(getattr(ops.eval_topk_metrics, "last_slices", 1)),
                                      "note": "tcgen05 TF32 filter + exact fp32 fma-chain re-score (bit-identical top-K to the "
-                                             "FP32-pipe kernel); rows sharded over ranks, no data-path collective"}
+                                             "FP32-pipe kernel); rows sharded over ranks, no data-path collective; a shard too small to "
+                                             "fill the SMs is cut into item_slices concurrent launches that share their thresholds"}
             # e2e: host lists -> CSR upload -> kernel -> metrics back
         # CPU baselines of the evaluation leg: the reference's per-user loop (trainers/mf_trainer.py:134-161:
         # score every item, mask, argpartition, metric.py) on the first 512 evaluation rows, for MF and — with the

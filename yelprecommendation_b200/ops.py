@@ -449,19 +449,26 @@ def _eval_tc_sliced(lib, Uemb, Vemb, Vt, ldt, ecsr, S: int):
     masks = _sliced_masks(ecsr, S, per) if S > 1 else None
     if masks is None:
         return None
-    ids = torch.empty(S, n, K, device=dev, dtype=I64)
-    scs = torch.empty(S, n, K, device=dev, dtype=F32)
-    um_s = torch.zeros(S, n, 4, device=dev, dtype=F64)              # per-slice metrics: not meaningful, never read
-    sums_s = torch.zeros(S, 6, device=dev, dtype=F64)
-    errs = torch.zeros(S, device=dev, dtype=I32)
+    # buffers, streams and events of the sliced call are kept with the evaluation set: the S launches are short, so the host
+    # side (allocations, event creation) would otherwise show up between them
     wsb = lib.yr_eval_tc_ws_bytes(n)
-    wss = torch.empty(S, wsb, device=dev, dtype=torch.uint8)
-    xchg = torch.full((S, max(n, 1)), float("-inf"), device=dev, dtype=F32)     # the slices' shared thresholds
+    wkey = ("ws", S, per, K)
+    cache = ecsr.__dict__.setdefault("_slice_cache", {})
+    if wkey not in cache:
+        cache[wkey] = dict(ids=torch.empty(S, n, K, device=dev, dtype=I64), scs=torch.empty(S, n, K, device=dev, dtype=F32),
+                           um=torch.zeros(S, n, 4, device=dev, dtype=F64), sums=torch.zeros(S, 6, device=dev, dtype=F64),
+                           errs=torch.zeros(S, device=dev, dtype=I32), wss=torch.empty(S, wsb, device=dev, dtype=torch.uint8),
+                           xchg=torch.empty(S, max(n, 1), device=dev, dtype=F32),
+                           off=torch.arange(S, device=dev, dtype=I64) * per,
+                           ready=torch.cuda.Event(), done=[torch.cuda.Event() for _ in range(S)])
+    c = cache[wkey]
+    ids, scs, um_s, sums_s, errs, wss, xchg = c["ids"], c["scs"], c["um"], c["sums"], c["errs"], c["wss"], c["xchg"]
+    xchg.fill_(float("-inf"))                                       # the slices' shared thresholds
     key = (dev.index, S)
     if key not in _SLICE_STREAMS:
         _SLICE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(S)]
     cur = torch.cuda.current_stream(dev)
-    ready = torch.cuda.Event()
+    ready = c["ready"]
     ready.record(cur)
     esz = Vemb.element_size()
     for s_, st in enumerate(_SLICE_STREAMS[key]):
@@ -472,13 +479,10 @@ def _eval_tc_sliced(lib, Uemb, Vemb, Vt, ldt, ecsr, S: int):
         # item slice = rows [i0, i0 + n_s) of V (row-major) and columns [i0, ...) of the transposed copy
         _eval_tc_call(lib, Uemb, _PtrView(Vemb.data_ptr() + i0 * d * esz), _PtrView(Vt.data_ptr() + i0 * esz), ldt, n_s, d, ecsr,
                       mp, mi, ids[s_], scs[s_], um_s[s_], sums_s[s_], wss[s_], errs[s_:s_ + 1], s_, S, xchg, st.cuda_stream)
-        done = torch.cuda.Event()
-        done.record(st)
-        cur.wait_event(done)
-    for t in (ids, scs, um_s, sums_s, errs, wss, xchg):
-        for st in _SLICE_STREAMS[key]:
-            t.record_stream(st)
-    off = torch.arange(S, device=dev, dtype=I64) * per
+        c["done"][s_].record(st)
+    for ev in c["done"]:
+        cur.wait_event(ev)
+    off = c["off"]
     topk = torch.empty(max(n, 1), K, device=dev, dtype=I64)
     tsc = torch.empty(max(n, 1), K, device=dev, dtype=F32)
     check(lib.yr_topk_merge(dptr(ids, I64), dptr(scs, F32), S, n, K, dptr(off, I64), dptr(topk), dptr(tsc), stream_ptr(dev)),

@@ -121,6 +121,10 @@ class CabiNgcfShardKernels:
         ops.dense_opt_step(p, g, m, v, opt)
 
 
+def _default_exchange(world: int) -> str:
+    return "symm" if 1 < world <= 4 else "p2p"
+
+
 class ShardedNGCFTrainer:
     def __init__(self, cfg, num_items: int, num_users: int, laplacian_matrix, init=None, group=None,
                  device=None, kernels=None, n_panels: int = None, solo: bool = False):
@@ -141,7 +145,8 @@ class ShardedNGCFTrainer:
         # exchange run underneath the SpMM is YR_SHARD_RESERVE_SMS below.
         self.xgroup = group
         if (multi and self.world > 1 and kernels is None and dist.get_backend(group) == "nccl"
-                and os.environ.get("YR_SHARD_EXCHANGE", "symm") == "p2p" and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
+                and os.environ.get("YR_SHARD_EXCHANGE", _default_exchange(self.world)) == "p2p"
+                and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
             self.xgroup = dist.new_group(ranks=dist.get_process_group_ranks(group if group is not None else dist.group.WORLD),
@@ -195,9 +200,12 @@ class ShardedNGCFTrainer:
         # COLUMN panels (one per row panel of the gathered operand): the SpMM over column panel p only needs the rows
         # every rank sent in exchange round p, so it can run underneath round p+1 — used where the whole operand is
         # exchanged right before it is consumed (layer 0 after the optimizer step; every backward layer)
-        # how a panel reaches the peers: 'symm' (default on NCCL/CUDA runs) = copy-engine pushes through symmetric memory,
-        # 'p2p' = grouped NCCL send / recv, 'allgather' / 'none' = experiments (one NCCL all-gather per layer / compute only)
-        self._xmode = os.environ.get("YR_SHARD_EXCHANGE", "symm" if (self.world > 1 and kernels is None) else "p2p")
+        # how a panel reaches the peers: 'symm' = copy-engine pushes through symmetric memory, 'p2p' = grouped NCCL send / recv,
+        # 'allgather' / 'none' = experiments (one NCCL all-gather per layer / compute only). Measured at config 5
+        # (profiles/README.md): 2 GPUs 269 ms (symm) vs 285 ms (p2p) per step — the pushes run underneath the SpMM, NCCL's SM
+        # kernels queue behind it; 8 GPUs 123.4 vs 118.6 ms — seven concurrent copy streams per GPU reach 418 GB/s where NCCL
+        # reaches 553 GB/s, which costs more than the overlap gains. Default: symm up to 4 ranks (4 not measured), p2p beyond.
+        self._xmode = os.environ.get("YR_SHARD_EXCHANGE", _default_exchange(self.world) if kernels is None else "p2p")
         self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode not in ("allgather", "symm")
                                and int(os.environ.get("YR_SHARD_COLPANELS", "1" if interleave else "0")) != 0)
         self.colA = self.colAT = None
