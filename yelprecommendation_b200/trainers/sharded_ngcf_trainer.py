@@ -204,7 +204,7 @@ class ShardedNGCFTrainer:
         # 'allgather' / 'none' = experiments (one NCCL all-gather per layer / compute only). Measured at config 5
         # (profiles/README.md): 2 GPUs 269 ms (symm) vs 285 ms (p2p) per step — the pushes run underneath the SpMM, NCCL's SM
         # kernels queue behind it; 8 GPUs 123.4 vs 118.6 ms — seven concurrent copy streams per GPU reach 418 GB/s where NCCL
-        # reaches 553 GB/s, which costs more than the overlap gains. Default: symm up to 4 ranks (4 not measured), p2p beyond.
+        # reaches 553 GB/s, which costs more than the overlap gains; 4 GPUs 165.5 vs 172.6 ms. Default: symm up to 4 ranks, p2p beyond.
         self._xmode = os.environ.get("YR_SHARD_EXCHANGE", _default_exchange(self.world) if kernels is None else "p2p")
         self.use_col_panels = (self.world > 1 and len(self.panels) > 1 and self._xmode not in ("allgather", "symm")
                                and int(os.environ.get("YR_SHARD_COLPANELS", "1" if interleave else "0")) != 0)
