@@ -174,3 +174,47 @@ def test_sparse_cdae_batch_equals_the_dense_masks():
             want = np.nonzero((tgt[b] + neg[b]) != 0)[0]
             assert np.array_equal(li[lp[b]:lp[b + 1]], want)
             assert np.array_equal(lv[lp[b]:lp[b + 1]], tgt[b][want])
+
+
+def test_eval_slice_rule_and_sliced_masks():
+    """Item-sliced evaluation, host side: the slice-count rule (ops.slices_for) and the per-slice mask CSRs (ops._sliced_masks:
+    entries of a slice, re-based, ascending per row) against a numpy restatement; rows that would have fewer than K unmasked
+    items inside a slice make the call fall back to the unsliced path."""
+    import torch
+    from yelprecommendation_b200 import ops
+    # Yelp shape, K = 10, 148 SMs: what one rank of a 1 / 2 / 4 / 8-GPU run evaluates
+    assert [ops.slices_for(31668 // w, 38048, 10, 148) for w in (1, 2, 4, 8)] == [1, 1, 2, 4]
+    assert ops.slices_for(3958, 38048, 16, 148) == 4 and ops.slices_for(3958, 38048, 10, 148, forced=6) == 6
+    assert ops.slices_for(100, 3000, 10, 148) == 1 and ops.slices_for(100, 5000, 10, 148) == 2      # slices stay >= 2,048 items
+    assert ops.slices_for(0, 38048, 10, 148) == 6                                                   # 64 // K caps S * K
+    rng = np.random.default_rng(0)
+    n, nI, K, S = 37, 1000, 10, 3
+    per = (-(-nI // S) + 127) // 128 * 128                 # 384
+    rows = [np.sort(rng.choice(nI, size=rng.integers(0, 60), replace=False)).astype(np.int32) for _ in range(n)]
+    ptr = np.zeros(n + 1, np.int32)
+    ptr[1:] = np.cumsum([len(r) for r in rows])
+    idx = np.concatenate(rows) if ptr[-1] else np.zeros(0, np.int32)
+    t = torch.from_numpy
+    ecsr = ops.DeviceEvalCSR.from_device(t(np.arange(n, dtype=np.int64)), t(ptr), t(idx), t(np.zeros(n + 1, np.int32)),
+                                         t(np.zeros(1, np.int32)), t(np.zeros(n, np.int32)), K)
+    ecsr._nI = nI
+    masks = ops._sliced_masks(ecsr, S, per)
+    assert masks is not None and len(masks) == S
+    for s_, (p_s, i_s) in enumerate(masks):
+        p_s, i_s = p_s.numpy(), i_s.numpy()
+        for r in range(n):
+            want = rows[r][(rows[r] >= s_ * per) & (rows[r] < (s_ + 1) * per)] - s_ * per
+            assert np.array_equal(i_s[p_s[r]:p_s[r + 1]], want)
+    assert ops._sliced_masks(ecsr, S, per) is masks                                   # cached with the evaluation set
+    # a row that masks all but K - 1 items of the last slice (232 items: 768 .. 999): not sliceable
+    full = np.arange(nI - 232 + (K - 1), nI, dtype=np.int32)
+    ptr2 = np.array([0, full.size], np.int32)
+    e2 = ops.DeviceEvalCSR.from_device(t(np.zeros(1, np.int64)), t(ptr2), t(full), t(np.zeros(2, np.int32)), t(np.zeros(1, np.int32)),
+                                       t(np.zeros(1, np.int32)), K)
+    e2._nI = nI
+    assert ops._sliced_masks(e2, S, per) is None
+
+
+def test_default_exchange_by_world_size():
+    from yelprecommendation_b200.trainers.sharded_ngcf_trainer import _default_exchange
+    assert [_default_exchange(w) for w in (1, 2, 3, 4, 5, 8)] == ["p2p", "symm", "symm", "symm", "p2p", "p2p"]

@@ -384,8 +384,14 @@ def eval_item_slices(n_eval: int, nI: int, K: int, dev) -> int:
     times shorter. YR_EVAL_SLICES overrides (1 = never slice)."""
     import os
     env = os.environ.get("YR_EVAL_SLICES")
+    return slices_for(n_eval, nI, K, _sm_count(dev), int(env) if env else None)
+
+
+def slices_for(n_eval: int, nI: int, K: int, sm_count: int, forced: int = None) -> int:
+    """The rule behind eval_item_slices (host arithmetic only): as many slices as it takes for tiles x slices CTAs to fill the SMs,
+    at most 8 and at most 64 // K (yr_topk_merge keeps S * K <= 64 candidates per row), each slice at least 2,048 items long."""
     tiles = max(1, (n_eval + 127) // 128)
-    S = int(env) if env else _sm_count(dev) // tiles
+    S = forced if forced is not None else sm_count // tiles
     S = max(1, min(S, 8, 64 // max(K, 1)))
     while S > 1 and -(-nI // S) < 2048:          # keep slices long enough for the running threshold to settle
         S -= 1
