@@ -139,14 +139,13 @@ class ShardedNGCFTrainer:
         self.world = dist.get_world_size(group) if multi else 1
         self.rank = dist.get_rank(group) if multi else 0
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        # The panel rounds go through a process group of their own with high-priority NCCL streams (YR_SHARD_HIPRIO=0: the
-        # caller's / default group). Priority alone changes nothing (measured on 2 GPUs: 285.7 vs 287.1 ms per step): NCCL's
-        # 640-thread CTAs need an EMPTY SM and never start while a grid of small CTAs keeps refilling every SM — what lets the
-        # exchange run underneath the SpMM is YR_SHARD_RESERVE_SMS below.
+        # YR_SHARD_HIPRIO=1: the NCCL panel rounds go through a process group of their own with high-priority streams. Off by
+        # default — it changes nothing (measured on 2 GPUs: 285.7 vs 287.1 ms per step): NCCL's 640-thread CTAs need an EMPTY SM
+        # and do not start while a grid of small CTAs keeps refilling every SM, whatever their priority (notes/README.md).
         self.xgroup = group
         if (multi and self.world > 1 and kernels is None and dist.get_backend(group) == "nccl"
                 and os.environ.get("YR_SHARD_EXCHANGE", _default_exchange(self.world)) == "p2p"
-                and int(os.environ.get("YR_SHARD_HIPRIO", "1")) != 0):
+                and int(os.environ.get("YR_SHARD_HIPRIO", "0")) != 0):
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
             self.xgroup = dist.new_group(ranks=dist.get_process_group_ranks(group if group is not None else dist.group.WORLD),
