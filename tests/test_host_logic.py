@@ -197,22 +197,20 @@ def test_eval_slice_rule_and_sliced_masks():
     t = torch.from_numpy
     ecsr = ops.DeviceEvalCSR.from_device(t(np.arange(n, dtype=np.int64)), t(ptr), t(idx), t(np.zeros(n + 1, np.int32)),
                                          t(np.zeros(1, np.int32)), t(np.zeros(n, np.int32)), K)
-    ecsr._nI = nI
-    masks = ops._sliced_masks(ecsr, S, per)
+    masks = ops._sliced_masks(ecsr, S, per, nI)
     assert masks is not None and len(masks) == S
     for s_, (p_s, i_s) in enumerate(masks):
         p_s, i_s = p_s.numpy(), i_s.numpy()
         for r in range(n):
             want = rows[r][(rows[r] >= s_ * per) & (rows[r] < (s_ + 1) * per)] - s_ * per
             assert np.array_equal(i_s[p_s[r]:p_s[r + 1]], want)
-    assert ops._sliced_masks(ecsr, S, per) is masks                                   # cached with the evaluation set
+    assert ops._sliced_masks(ecsr, S, per, nI) is masks                                   # cached with the evaluation set
     # a row that masks all but K - 1 items of the last slice (232 items: 768 .. 999): not sliceable
     full = np.arange(nI - 232 + (K - 1), nI, dtype=np.int32)
     ptr2 = np.array([0, full.size], np.int32)
     e2 = ops.DeviceEvalCSR.from_device(t(np.zeros(1, np.int64)), t(ptr2), t(full), t(np.zeros(2, np.int32)), t(np.zeros(1, np.int32)),
                                        t(np.zeros(1, np.int32)), K)
-    e2._nI = nI
-    assert ops._sliced_masks(e2, S, per) is None
+    assert ops._sliced_masks(e2, S, per, nI) is None
 
 
 def test_default_exchange_by_world_size():

@@ -398,12 +398,12 @@ def slices_for(n_eval: int, nI: int, K: int, sm_count: int, forced: int = None) 
     return S
 
 
-def _sliced_masks(ecsr: DeviceEvalCSR, S: int, per: int):
+def _sliced_masks(ecsr: DeviceEvalCSR, S: int, per: int, nI: int):
     """Per item slice s: the mask CSR restricted to items [s * per, (s + 1) * per), ids re-based to the slice (ascending per
     row, like the original). Index plumbing with torch ops, once per (evaluation set, S); cached on the DeviceEvalCSR.
     Returns None when some row has fewer than K unmasked items inside a slice (the unsliced path handles such rows)."""
     cache = ecsr.__dict__.setdefault("_slice_cache", {})
-    key = (S, per)
+    key = (S, per, nI)
     if key in cache:
         return cache[key]
     n, dev = ecsr.n_eval, ecsr.eval_uid.device
@@ -416,7 +416,7 @@ def _sliced_masks(ecsr: DeviceEvalCSR, S: int, per: int):
     for s_ in range(S):
         sel = sl == s_
         cnt = torch.bincount(row[sel], minlength=n)
-        size = min(per, ecsr_items(ecsr) - s_ * per) if ecsr_items(ecsr) else per
+        size = min(per, nI - s_ * per)
         if n and int(cnt.max().item()) > size - ecsr.K:
             ok = False
             break
@@ -426,10 +426,6 @@ def _sliced_masks(ecsr: DeviceEvalCSR, S: int, per: int):
         out.append((p_s.to(I32).contiguous(), i_s.contiguous() if i_s.numel() else torch.zeros(1, dtype=I32, device=dev)))
     cache[key] = out if ok else None
     return cache[key]
-
-
-def ecsr_items(ecsr) -> int:
-    return int(getattr(ecsr, "_nI", 0))
 
 
 def _eval_tc_call(lib, Uemb, Vemb, Vt, ldt, nI, d, ecsr, mask_ptr, mask_idx, topk, tsc, um, sums, ws, err, slice_, n_slices, xchg,
@@ -451,8 +447,7 @@ def _eval_tc_sliced(lib, Uemb, Vemb, Vt, ldt, ecsr, S: int):
     n, K = ecsr.n_eval, ecsr.K
     per = (-(-nI // S) + 127) // 128 * 128
     S = -(-nI // per)
-    ecsr._nI = nI
-    masks = _sliced_masks(ecsr, S, per) if S > 1 else None
+    masks = _sliced_masks(ecsr, S, per, nI) if S > 1 else None
     if masks is None:
         return None
     # buffers, streams and events of the sliced call are kept with the evaluation set: the S launches are short, so the host
