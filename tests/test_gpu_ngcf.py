@@ -102,7 +102,7 @@ def test_layer_forward_tensor_core_3xtf32():
 
 @pytest.mark.parametrize("dense_mode", [1, 2])
 def test_layer_backward_vs_oracle_and_autograd_golden(dense_mode):
-    """dense_mode 1: FP32-pipe backward kernel (default); 2: tcgen05 backward (3xTF32, MN-major operands for dW)."""
+    """dense_mode 1: tensor-core forward + FP32-pipe backward kernel; 2 (default of the trainers): tcgen05 backward (3xTF32, MN-major operands for dW)."""
     from yelprecommendation_b200 import ops
     from yelprecommendation_b200.data.graph import laplacian_to_csr
     _layer_backward_case(ops, laplacian_to_csr, dense_mode)
