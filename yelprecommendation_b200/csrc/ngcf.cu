@@ -657,7 +657,10 @@ static int ngcf_layer_bwd_rows(const yr_ngcf_state* st, int l, float slope, cuda
   const int d = st->d;
   using C = DenseCfg<64>;
   if (d != 64) return YR_ERR_BAD_DIM;
-  if (bwd_tc(st->dense_mode)) {
+  // The tensor-core kernel has fixed costs (weight split launch, TMEM, ring fill: 22.7 us for the 48 tiles of a B = 2,048
+  // step against 15.4 us for the FP32-pipe kernel, profiles/r02_launches_ngcf_step.csv; 42 vs 67 us on all 69,716 rows): it
+  // takes over from ~16 k listed rows.
+  if (bwd_tc(st->dense_mode) && st->row_list_cap >= 16384) {
     int parts = 0;
     int rc = yr_ngcf_dense_bwd_tc_launch(d, st->E[l], st->LE[l], st->E[l + 1], st->G[l + 1], st->W1[l], st->W2[l], slope,
                                          st->nU + st->nI, st->G[l], st->T, (float*)st->ws, &parts, s, st->row_list,
