@@ -776,9 +776,10 @@ def main():
             cpu_baseline["verbatim_eye"] = {"skipped": repr(ex)}
 
     if rank == 0:
-        # kernels of one yr_ngcf_train_step (profiles/ launch list): touched rows 1, forward 2 per layer, tail 2,
-        # backward: last layer 4 (dense-on-rows, reduce, scatter, clear) + 3 per other layer, optimizer 1
-        launches_per_step = 1 + 2 * LAYERS + 2 + 4 + 3 * (LAYERS - 1) + 1
+        # kernels of one yr_ngcf_train_step (profiles/r02_launches_ngcf_step.csv): touched rows 1, forward 2 per layer, tail 2,
+        # backward: last layer 4 (dense-on-rows, reduce, scatter, clear) + 4 per other layer (weight split, tensor-core
+        # backward, reduce, transposed SpMM), optimizer 1
+        launches_per_step = 1 + 2 * LAYERS + 2 + 4 + 4 * (LAYERS - 1) + 1
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
