@@ -4,13 +4,15 @@
 //     A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi      (relative error ~2^-21 per product, fp32 accumulation in TMEM)
 // which keeps the layer inside the 1e-5 parity bar while the 2*N*d*2d flops leave the FP32 pipe.
 //
-// Per CTA (persistent over 128-row tiles, one CTA per SM):
-//   warps 0-7 : loaders   — coalesced float4 reads of E, LE (next tile prefetched into registers), S = LE+E, P = E*LE, split hi/lo, store the
-//                           four [128 x 64] operands in the K-major 128B-swizzled layout the UMMA descriptor expects
-//   warps 8-11: epilogue  — thread = row = TMEM lane: tcgen05.ld 64 columns, LeakyReLU, store E_next
-//   warp  12  : TMEM allocator + MMA issuer (one elected lane): 48 MMAs (M=128, N=64, K=8) per tile
-// W1/W2 are nn.Linear weights [out x in] = K-major B operands as stored; their hi/lo copies are built once per CTA.
-// Two TMEM accumulator stages let the epilogue of tile t overlap the loads + MMAs of tile t+1.
+// Per CTA (persistent over 128-row tiles, one CTA per SM), 13 warps:
+//   warps 0-7 : loaders   — float4 reads of E, LE one 32-column slab at a time (two slabs in flight per thread, the next tile's
+//                           rows asked for in L2 by one bulk prefetch), S = LE+E, P = E*LE, split hi/lo, stores into the ring
+//                           stage in the K-major 128B-swizzled layout the UMMA descriptor expects
+//   warps 8-11: epilogue  — TMEM lane = row: tcgen05.ld of the two accumulators, LeakyReLU, rows leave through a per-warp
+//                           shared-memory transpose as whole 256-byte segments
+//   warp  12  : TMEM allocator + MMA issuer (one elected lane): 12 MMAs (M = 128, N = d, K = 8) per ring stage
+// W1/W2 are nn.Linear weights [out x in] = K-major B operands as stored. Two TMEM accumulator stages let the epilogue of
+// tile t overlap the loads + MMAs of tile t+1. (Round 1's kernel handed a whole tile from the loaders to the MMA warp at once.)
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -28,7 +30,7 @@ constexpr int kFwdTM = 128;
 //        pre-swizzled workspace that ngcf_split_weights_kernel fills once per launch; L2-resident)          2 x 16 KB
 // and feeds 12 MMAs (M = 128, N = d, K = 8; lo.hi, hi.lo, hi.hi). Loaders run up to kNst stages ahead of the MMA warp
 // with two slabs of global loads in flight per thread, so staging, MMAs and the epilogue of the previous tile overlap
-// inside a tile as well as across tiles (v1 handed the whole tile over at once).
+// inside a tile as well as across tiles.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int D>
 struct FwdTc {
